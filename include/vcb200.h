@@ -1,0 +1,111 @@
+/* vcb200.h -- C ABI of libvcb200.so: the B200-native VisualCloze denoising hot path.
+ *
+ * The reference (lzyhha/VisualCloze) is pure Python and has no FFI layer; its boundary for this path is a set
+ * of Python call signatures.  Each entry point below names the reference code it replaces
+ * (file:line under the reference tree).  The Python mirror of the reference interface
+ * (visualcloze_b200/model.py, sampling.py, transport.py, pipeline.py) binds these symbols with ctypes; the
+ * binding a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless named host_*; the caller owns every buffer;
+ *   - bf16 tensors are passed as void* / uint16 storage, row-major, leading dimensions in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); work is only enqueued;
+ *   - every function returns 0 on success, non-zero on error; vcb_last_error() gives the message
+ *     (thread-local).  No C++ exception crosses the boundary.  No CPU fallback exists.
+ */
+#ifndef VCB200_H_
+#define VCB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VCB_ABI_VERSION 1
+
+/* ---- library ------------------------------------------------------------------------------ */
+int         vcb_abi_version(void);
+const char* vcb_last_error(void);
+/* number of kernels this library has launched since load / since the last reset (bench.py gpu_launches) */
+long long   vcb_launch_count(void);
+void        vcb_reset_launch_count(void);
+
+/* ---- fused-epilogue GEMM:  D = epilogue(A[M,K] * W[N,K]^T)   (bf16 x bf16 -> fp32 -> bf16) --------------
+ * Replaces every nn.Linear on the path (models/modules/layers.py:165,172,190-195,235,244; model.py:101,108;
+ * lora.py:92-98 with merged weights) together with the elementwise ops that follow it in the reference. */
+enum vcb_epilogue {
+    VCB_EPI_BIAS = 0,      /* out = bf16(acc + bias) */
+    VCB_EPI_BIAS_GELU = 1, /* out = bf16(gelu_tanh(bf16(acc + bias)))                    layers.py:143,154 */
+    VCB_EPI_GATE_RES = 2,  /* out = bf16(res + bf16(gate * bf16(acc + bias)))             layers.py:190-195,245 */
+    VCB_EPI_QKV = 3,       /* bias; q,k: RMSNorm(128) * scale then RoPE; v: bias only     layers.py:165-174, math.py:112-117 */
+    VCB_EPI_LINEAR1 = 4    /* cols < 3H as QKV -> out; cols >= 3H as BIAS_GELU -> out2     layers.py:235-244 */
+};
+
+typedef struct vcb_gemm_args {
+    int32_t M, N, K;
+    const void* A;  int64_t lda;     /* [M, K] bf16 */
+    const void* W;  int64_t ldw;     /* [N, K] bf16 (nn.Linear.weight layout) */
+    const float* bias;               /* [N] fp32 or NULL */
+    void* out;      int64_t ldo;     /* bf16 */
+    int32_t out_col_offset;
+    /* row mapping: input row r -> sample b = r / rows_per_batch, i = r % rows_per_batch,
+       output row = b * out_batch_rows + out_row_offset + i.  Set rows_per_batch = M,
+       out_batch_rows = M, out_row_offset = 0 for the identity. */
+    int32_t rows_per_batch, out_batch_rows, out_row_offset;
+    int32_t epilogue;                /* enum vcb_epilogue */
+    /* VCB_EPI_GATE_RES */
+    const void* gate; int64_t gate_stride;   /* [B, gate_stride] bf16 */
+    const void* res;  int64_t ld_res;        /* bf16, indexed by OUTPUT row; may alias out */
+    /* VCB_EPI_QKV / VCB_EPI_LINEAR1 (head_dim is 128) */
+    int32_t hidden;
+    const void* q_scale; const void* k_scale;   /* [128] bf16 */
+    const void* rope;                            /* [out rows, 64] float2 (cos, sin) */
+    void* out2; int64_t ldo2; int32_t out2_col_offset;
+    /* tuning: 0 = library heuristic */
+    int32_t block_n;                 /* 64 / 128 / 192 / 256 */
+    int32_t cta_group;               /* 1 or 2 (CTA pair, tcgen05 cta_group::2) */
+} vcb_gemm_args;
+
+int vcb_gemm_bf16(const vcb_gemm_args* args, void* stream);
+
+/* ---- joint attention (models/math.py:63-99: attention/_upad_input/flash_attn_varlen_func/pad_input) ------
+ * qkv: [B, L, ld_qkv] bf16, head h of q/k/v at columns {q,k,v}_col + 128*h, RoPE + QK-norm already applied.
+ * seqlens: [B] int32 valid tokens (right padding) or NULL.  out rows >= seqlen are written as zeros. */
+int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_col, int32_t v_col,
+                      const int32_t* seqlens, int32_t B, int32_t L, int32_t heads,
+                      void* out, int64_t ldo, int32_t out_col_offset, void* stream);
+
+/* ---- AdaLN modulated LayerNorm (layers.py:163-164,191,195,234,257):
+ *      y = bf16( bf16(1 + scale[b]) * LayerNorm(x) + shift[b] ), eps 1e-6, no affine; hidden % 256 == 0 */
+int vcb_ln_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, const void* shift, const void* scale,
+                    int64_t mod_stride, int32_t rows, int32_t hidden, int32_t rows_per_batch, void* stream);
+
+/* ---- small helpers --------------------------------------------------------------------------------------- */
+/* layers.py:28-49; t_scaled = time_factor * t already in the reference's dtype; freqs[128] fp32; out [n,256] bf16 */
+int vcb_timestep_embedding(const float* t_scaled, const float* freqs, void* out, int32_t n, void* stream);
+int vcb_silu(const void* x, void* y, int64_t n, void* stream);
+/* out[r] = bf16(bf16(a[r] + b[r % b_rows]) + c[r % c_rows]); b, c may be NULL   (model.py:102-107) */
+int vcb_add3(const void* a, const void* b, int32_t b_rows, const void* c, int32_t c_rows, void* out,
+             int32_t rows, int32_t hidden, void* stream);
+/* layers.py:11-25 + math.py:102-109: ids [rows,3] fp32 -> (cos,sin) [rows,64] fp32 pairs */
+int vcb_rope_table(const float* ids, void* out, int32_t rows, int32_t d0, int32_t d1, int32_t d2, double theta,
+                   void* stream);
+/* torchdiffeq euler step as used by transport/integrators.py:119 (bf16 state, dt rounded to bf16, v negated);
+ * model_in may be NULL, else x_new is also written into its first C columns. */
+int vcb_euler_update(const void* x, const void* v, float dt_bf16, void* x_new, void* model_in, int64_t ld_in,
+                     int64_t rows, int32_t C, void* stream);
+int vcb_copy_cols(const void* src, int64_t lds, void* dst, int64_t ldd, int32_t col0, int64_t rows, int32_t C,
+                  void* stream);
+
+/* ---- test hook: one 128x128x(16*ksteps) tcgen05 MMA with caller-chosen descriptor fields -------------------
+ * Used by tests/ to pin the smem/TMEM operand layouts the kernels rely on.  a: [128, K] bf16 (K-major),
+ * b: B operand, either [128(N), K] K-major (b_mn_major=0) or [K, 128(N)] N-contiguous (b_mn_major=1);
+ * a_from_tmem: stage A through TMEM (tcgen05.st) instead of smem.  out: [128,128] fp32. */
+int vcb_debug_umma_probe(const void* a, const void* b, float* out, int32_t ksteps, int32_t b_mn_major,
+                         int32_t a_from_tmem, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCB200_H_ */

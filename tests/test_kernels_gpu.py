@@ -1,0 +1,300 @@
+"""Per-kernel parity on the B200: every test calls through the C ABI (visualcloze_b200.ops -> libvcb200.so)
+and compares with the CPU oracle (oracle/flux_oracle.py) or, for the bare GEMM, a plain fp32 torch matmul of
+the same bf16 operands.  Tolerances are stated per test."""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from visualcloze_b200 import ops as _ops
+    return _ops
+
+
+def _randn(*shape, seed=0, scale=1.0, dtype=BF16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype)
+
+
+def _stats(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    d = (got - ref).abs()
+    return f"rel_l2={rel_l2(got, ref):.3e} max_abs={d.max().item():.3e} ref_absmax={ref.abs().max().item():.3e} " \
+           f"nan={int(torch.isnan(got).sum())} argmax={tuple(int(i) for i in torch.unravel_index(d.argmax(), d.shape))}"
+
+
+# ------------------------------------------------------------------------------------------------
+# operand-layout probes (single tcgen05 MMA tile)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ksteps", [4, 8])
+def test_probe_kmajor_ss(ops, ksteps):
+    K = 16 * ksteps
+    a, b = _randn(128, K, seed=1), _randn(128, K, seed=2)
+    out = ops.umma_probe(a.cuda(), b.cuda(), ksteps, False, False)
+    ref = a.float() @ b.float().T
+    assert rel_l2(out.cpu(), ref) < 1e-5, _stats(out, ref)
+
+
+@pytest.mark.parametrize("ksteps", [4, 8])
+def test_probe_b_mn_major(ops, ksteps):
+    """B given as [K, N] with N contiguous (the V tile of attention)."""
+    K = 16 * ksteps
+    a, b = _randn(128, K, seed=3), _randn(K, 128, seed=4)
+    out = ops.umma_probe(a.cuda(), b.cuda(), ksteps, True, False, b_lbo=K * 128, b_sbo=1024, b_kstep_bytes=2048)
+    ref = a.float() @ b.float()
+    assert rel_l2(out.cpu(), ref) < 1e-5, _stats(out, ref)
+
+
+@pytest.mark.parametrize("ksteps", [4, 8])
+def test_probe_a_from_tmem(ops, ksteps):
+    """A staged in TMEM as packed bf16 pairs (the P tile of attention), B MN-major."""
+    K = 16 * ksteps
+    a, b = _randn(128, K, seed=5), _randn(K, 128, seed=6)
+    out = ops.umma_probe(a.cuda(), b.cuda(), ksteps, True, True, b_lbo=K * 128, b_sbo=1024, b_kstep_bytes=2048)
+    ref = a.float() @ b.float()
+    assert rel_l2(out.cpu(), ref) < 1e-5, _stats(out, ref)
+
+
+def test_probe_a_from_tmem_b_kmajor(ops):
+    a, b = _randn(128, 128, seed=7), _randn(128, 128, seed=8)
+    out = ops.umma_probe(a.cuda(), b.cuda(), 8, False, True)
+    ref = a.float() @ b.float().T
+    assert rel_l2(out.cpu(), ref) < 1e-5, _stats(out, ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [
+    (128, 256, 64), (128, 256, 512), (200, 264, 384), (384, 768, 3072), (1000, 64, 3072), (29, 1536, 256),
+    (3456, 3072, 3072),
+]
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("block_n", [0, 128, 192, 256])
+@pytest.mark.parametrize("shape", GEMM_SHAPES)
+def test_gemm_bias(ops, shape, block_n, cta_group):
+    M, N, K = shape
+    a, w = _randn(M, K, seed=1), _randn(N, K, seed=2, scale=1 / math.sqrt(K))
+    bias = _randn(N, seed=3, dtype=torch.float32)
+    out = torch.full((M, N), 7.0, dtype=BF16, device="cuda")
+    ops.gemm(a.cuda(), w.cuda(), bias.cuda(), out, block_n=block_n, cta_group=cta_group)
+    torch.cuda.synchronize()
+    ref = (a.float() @ w.float().T + bias).to(BF16)
+    # fp32 accumulation both sides; difference = summation order + one bf16 rounding
+    assert rel_l2(out.cpu(), ref) < 3e-3, _stats(out, ref)
+
+
+def test_gemm_block64_and_strided_output(ops):
+    M, N, K = 300, 64, 512
+    a, w = _randn(M, K, seed=1), _randn(N, K, seed=2, scale=1 / math.sqrt(K))
+    buf = torch.zeros(M, 256, dtype=BF16, device="cuda")
+    ops.gemm(a.cuda(), w.cuda(), None, buf, out_col_offset=128, block_n=64, cta_group=1)
+    ref = (a.float() @ w.float().T).to(BF16)
+    assert rel_l2(buf[:, 128:192].cpu(), ref) < 3e-3, _stats(buf[:, 128:192], ref)
+    assert float(buf[:, :128].abs().max()) == 0 and float(buf[:, 192:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gemm_gelu(ops, cta_group):
+    M, N, K = 520, 1024, 256
+    a, w = _randn(M, K, seed=1), _randn(N, K, seed=2, scale=1 / math.sqrt(K))
+    bias = _randn(N, seed=3, dtype=torch.float32, scale=0.1)
+    out = torch.empty(M, N, dtype=BF16, device="cuda")
+    ops.gemm(a.cuda(), w.cuda(), bias.cuda(), out, epilogue=ops.EPI_BIAS_GELU, cta_group=cta_group)
+    lin = (a.float() @ w.float().T + bias).to(BF16)
+    ref = torch.nn.functional.gelu(lin, approximate="tanh")
+    assert rel_l2(out.cpu(), ref) < 4e-3, _stats(out, ref)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gemm_gate_residual_batched(ops, cta_group):
+    """x <- x + gate[b] * (attn @ W^T + bias), in place, two samples with their own gate rows (layers.py:190)."""
+    B, Lb, H, K = 2, 150, 512, 256
+    a, w = _randn(B * Lb, K, seed=1), _randn(H, K, seed=2, scale=1 / math.sqrt(K))
+    bias = _randn(H, seed=3, dtype=torch.float32, scale=0.1)
+    gate, x = _randn(B, H, seed=4), _randn(B * Lb, H, seed=5)
+    xg = x.cuda().clone()
+    ops.gemm(a.cuda(), w.cuda(), bias.cuda(), xg, epilogue=ops.EPI_GATE_RES, rows_per_batch=Lb, gate=gate.cuda(),
+             res=xg, cta_group=cta_group)
+    lin = (a.float() @ w.float().T + bias).to(BF16).reshape(B, Lb, H)
+    ref = (x.reshape(B, Lb, H) + gate[:, None, :] * lin).reshape(B * Lb, H)
+    assert rel_l2(xg.cpu(), ref) < 4e-3, _stats(xg, ref)
+
+
+def _qkv_reference(a, w, bias, qs, ks, cos, sin, heads):
+    from oracle import flux_oracle as fo
+    L = a.shape[0]
+    lin = (a.float() @ w.float().T + bias).to(BF16)[None]              # [1, L, 3H]
+    q, k, v = fo._split_heads(lin, heads)
+    q = fo.apply_rope(fo.rms_norm(q, qs), cos[None], sin[None])
+    k = fo.apply_rope(fo.rms_norm(k, ks), cos[None], sin[None])
+    return torch.cat([t.permute(0, 2, 1, 3).reshape(L, -1) for t in (q, k, v)], dim=-1)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_gemm_qkv_epilogue(ops, block_n, cta_group):
+    """bias + QK-RMSNorm + RoPE fused into the projection (layers.py:165-174, math.py:112-117), written at a row
+    offset of a joint txt||img buffer."""
+    L, H, heads, K, row_off, Ltot = 200, 256, 2, 256, 24, 256
+    a, w = _randn(L, K, seed=1), _randn(3 * H, K, seed=2, scale=1 / math.sqrt(K))
+    bias = _randn(3 * H, seed=3, dtype=torch.float32, scale=0.1)
+    qs, ks = (1 + 0.1 * _randn(128, seed=4, dtype=torch.float32)).to(BF16), (1 + 0.1 * _randn(128, seed=5, dtype=torch.float32)).to(BF16)
+    ang = _randn(Ltot, 64, seed=6, dtype=torch.float32) * 3
+    cos, sin = torch.cos(ang), torch.sin(ang)
+    rope = torch.stack([cos, sin], -1).contiguous()
+    out = torch.zeros(Ltot, 3 * H, dtype=BF16, device="cuda")
+    ops.gemm(a.cuda(), w.cuda(), bias.cuda(), out, epilogue=ops.EPI_QKV, hidden=H, q_scale=qs.cuda(), k_scale=ks.cuda(),
+             rope=rope.cuda(), rows_per_batch=L, out_batch_rows=Ltot, out_row_offset=row_off, block_n=block_n,
+             cta_group=cta_group)
+    ref = _qkv_reference(a, w, bias, qs, ks, cos[row_off:row_off + L], sin[row_off:row_off + L], heads)
+    got = out[row_off:row_off + L].cpu()
+    assert rel_l2(got, ref) < 6e-3, _stats(got, ref)
+    assert float(out[:row_off].abs().max()) == 0 and float(out[row_off + L:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gemm_linear1_epilogue(ops, cta_group):
+    """single-stream linear1: qkv columns get norm+rope, mlp columns get GELU into the linear2 input (layers.py:235-244)."""
+    L, H, heads, mlp = 160, 256, 2, 512
+    a, w = _randn(L, H, seed=1), _randn(3 * H + mlp, H, seed=2, scale=1 / math.sqrt(H))
+    bias = _randn(3 * H + mlp, seed=3, dtype=torch.float32, scale=0.1)
+    qs, ks = (1 + 0.1 * _randn(128, seed=4, dtype=torch.float32)).to(BF16), (1 + 0.1 * _randn(128, seed=5, dtype=torch.float32)).to(BF16)
+    ang = _randn(L, 64, seed=6, dtype=torch.float32) * 3
+    cos, sin = torch.cos(ang), torch.sin(ang)
+    rope = torch.stack([cos, sin], -1).contiguous()
+    qkv = torch.zeros(L, 3 * H, dtype=BF16, device="cuda")
+    cat = torch.zeros(L, H + mlp, dtype=BF16, device="cuda")
+    ops.gemm(a.cuda(), w.cuda(), bias.cuda(), qkv, epilogue=ops.EPI_LINEAR1, hidden=H, q_scale=qs.cuda(), k_scale=ks.cuda(),
+             rope=rope.cuda(), out2=cat, out2_col_offset=H, cta_group=cta_group)
+    ref_qkv = _qkv_reference(a, w[:3 * H], bias[:3 * H], qs, ks, cos, sin, heads)
+    lin = (a.float() @ w[3 * H:].float().T + bias[3 * H:]).to(BF16)
+    ref_mlp = torch.nn.functional.gelu(lin, approximate="tanh")
+    assert rel_l2(qkv.cpu(), ref_qkv) < 6e-3, _stats(qkv, ref_qkv)
+    assert rel_l2(cat[:, H:].cpu(), ref_mlp) < 4e-3, _stats(cat[:, H:], ref_mlp)
+    assert float(cat[:, :H].abs().max()) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def _attn_case(ops, B, L, heads, seqlens, seed, scale=1.0):
+    from oracle import flux_oracle as fo
+    H = heads * 128
+    qkv = _randn(B * L, 3 * H, seed=seed, scale=scale)
+    out = torch.full((B * L, H), 5.0, dtype=BF16, device="cuda")
+    sl = None if seqlens is None else torch.tensor(seqlens, dtype=torch.int32, device="cuda")
+    ops.attention(qkv.cuda(), B, L, heads, out, q_col=0, k_col=H, v_col=2 * H, seqlens=sl)
+    torch.cuda.synchronize()
+    q, k, v = fo._split_heads(qkv.reshape(B, L, 3 * H), heads)
+    ones, zeros = torch.ones(B, L, 64), torch.zeros(B, L, 64)
+    mask = torch.ones(B, L, dtype=torch.int32)
+    if seqlens is not None:
+        for b, s in enumerate(seqlens):
+            mask[b, s:] = 0
+    ref = fo.joint_attention(q, k, v, ones, zeros, mask, fo.Numerics("cuda_bf16")).reshape(B * L, H)
+    return out.cpu(), ref
+
+
+@pytest.mark.parametrize("L", [128, 200, 1088, 3968])
+def test_attention_full(ops, L):
+    got, ref = _attn_case(ops, 1, L, 2, None, seed=L)
+    # P is rounded to bf16 on both sides; O differs by fp32 summation order + final bf16 rounding
+    assert rel_l2(got, ref) < 8e-3, _stats(got, ref)
+
+
+def test_attention_peaked_scores_exercise_rescale(ops):
+    """large-magnitude q.k -> row max jumps by >> 2^8 between tiles: exercises the O-correction path."""
+    got, ref = _attn_case(ops, 1, 640, 1, None, seed=3, scale=4.0)
+    assert rel_l2(got, ref) < 1e-2, _stats(got, ref)
+
+
+def test_attention_ragged_batch(ops):
+    """right-padded batch: masked keys, zeroed padded query rows (math.py:9-60 + pad_input)."""
+    B, L, seqlens = 2, 520, [520, 301]
+    got, ref = _attn_case(ops, B, L, 2, seqlens, seed=9)
+    assert rel_l2(got, ref) < 8e-3, _stats(got, ref)
+    assert float(got.reshape(B, L, -1)[1, 301:].abs().max()) == 0
+
+
+def test_attention_strided_output_columns(ops):
+    """writes into columns [0, H) of the [L, H + mlp] linear2 input of a single block."""
+    from oracle import flux_oracle as fo
+    B, L, heads = 1, 256, 2
+    H = heads * 128
+    qkv = _randn(L, 3 * H, seed=4)
+    cat = torch.zeros(L, H + 512, dtype=BF16, device="cuda")
+    ops.attention(qkv.cuda(), B, L, heads, cat, q_col=0, k_col=H, v_col=2 * H)
+    q, k, v = fo._split_heads(qkv.reshape(B, L, 3 * H), heads)
+    ref = fo.joint_attention(q, k, v, torch.ones(B, L, 64), torch.zeros(B, L, 64), torch.ones(B, L, dtype=torch.int32),
+                             fo.Numerics("cuda_bf16")).reshape(L, H)
+    assert rel_l2(cat[:, :H].cpu(), ref) < 8e-3, _stats(cat[:, :H], ref)
+    assert float(cat[:, H:].abs().max()) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# elementwise
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H", [256, 3072])
+def test_ln_modulate(ops, H):
+    from oracle import flux_oracle as fo
+    B, Lb = 2, 77
+    x = _randn(B * Lb, H, seed=1, scale=2.0)
+    shift, scale = _randn(B, H, seed=2, scale=0.5), _randn(B, H, seed=3, scale=0.5)
+    out = torch.empty(B * Lb, H, dtype=BF16, device="cuda")
+    ops.ln_modulate(x.cuda(), shift.cuda(), scale.cuda(), out, rows_per_batch=Lb)
+    ref = fo._modulate(x.reshape(B, Lb, H), shift[:, None], scale[:, None], fo.Numerics("cuda_bf16")).to(BF16)
+    # identical rounding points; fp32 statistics differ in summation order only
+    assert rel_l2(out.cpu(), ref.reshape(B * Lb, H)) < 2e-3, _stats(out, ref.reshape(B * Lb, H))
+
+
+def test_timestep_embedding_silu_add3(ops):
+    from oracle import flux_oracle as fo
+    t = torch.tensor([1.0, 0.76096, 0.25, 0.0])
+    g = torch.full((4,), 30.0, dtype=BF16)
+    freqs = torch.exp(-math.log(10000) * torch.arange(0, 128, dtype=torch.float32) / 128)
+    for tin, ref in ((1000.0 * t, fo.timestep_embedding(t).to(BF16)), ((1000.0 * g).float(), fo.timestep_embedding(g))):
+        out = torch.empty(4, 256, dtype=BF16, device="cuda")
+        ops.timestep_embedding(tin.cuda(), freqs.cuda(), out)
+        assert (out.cpu().float() - ref.float()).abs().max() < 1.6e-2, _stats(out, ref)   # 1-2 bf16 ulp at |x|<=1
+    x = _randn(4, 512, seed=1, scale=3)
+    y = torch.empty_like(x, device="cuda")
+    ops.silu(x.cuda(), y)
+    assert rel_l2(y.cpu(), torch.nn.functional.silu(x)) < 3e-3
+    a, b, c = _randn(6, 512, seed=2), _randn(2, 512, seed=3), _randn(2, 512, seed=4)
+    o = torch.empty(6, 512, dtype=BF16, device="cuda")
+    ops.add3(a.cuda(), b.cuda(), c.cuda(), o)
+    ref = (a.reshape(3, 2, 512) + b[None]) + c[None]
+    assert torch.equal(o.cpu(), ref.reshape(6, 512))
+
+
+def test_rope_table_and_euler(ops):
+    from oracle import flux_oracle as fo
+    ids = torch.zeros(300, 3)
+    ids[:, 0] = torch.arange(300) % 3 + 1
+    ids[:, 1] = torch.arange(300) // 24
+    ids[:, 2] = torch.arange(300) % 72
+    out = torch.empty(300, 64, 2, dtype=torch.float32, device="cuda")
+    ops.rope_table(ids.cuda(), [16, 56, 56], 10000, out)
+    cos, sin = fo.rope_table(ids[None], [16, 56, 56], 10000)
+    assert (out[..., 0].cpu() - cos[0]).abs().max() < 1e-6 and (out[..., 1].cpu() - sin[0]).abs().max() < 1e-6
+    x, v = _randn(500, 64, seed=1), _randn(500, 64, seed=2)
+    dt = torch.tensor(1.0 / 29)                                  # 0-dim fp32 like torchdiffeq's dt
+    ref = x + dt * (-v)                                          # torch promotion -> bf16(x + bf16(bf16(dt)*f))
+    xn = torch.empty(500, 64, dtype=BF16, device="cuda")
+    inp = torch.zeros(500, 384, dtype=BF16, device="cuda")
+    ops.euler_update(x.cuda(), v.cuda(), float(dt.to(BF16)), xn, inp)
+    assert torch.equal(xn.cpu(), ref), _stats(xn, ref)
+    assert torch.equal(inp[:, :64].cpu(), ref) and float(inp[:, 64:].abs().max()) == 0

@@ -1,0 +1,93 @@
+"""ctypes binding of libvcb200.so (include/vcb200.h).  Fails loudly when the library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvcb200.so")
+ABI_VERSION = 1
+
+_lib = None
+
+
+class VcbError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    """struct vcb_gemm_args (include/vcb200.h)."""
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64),
+        ("W", C.c_void_p), ("ldw", C.c_int64),
+        ("bias", C.c_void_p),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("out_col_offset", C.c_int32),
+        ("rows_per_batch", C.c_int32), ("out_batch_rows", C.c_int32), ("out_row_offset", C.c_int32),
+        ("epilogue", C.c_int32),
+        ("gate", C.c_void_p), ("gate_stride", C.c_int64),
+        ("res", C.c_void_p), ("ld_res", C.c_int64),
+        ("hidden", C.c_int32),
+        ("q_scale", C.c_void_p), ("k_scale", C.c_void_p),
+        ("rope", C.c_void_p),
+        ("out2", C.c_void_p), ("ldo2", C.c_int64), ("out2_col_offset", C.c_int32),
+        ("block_n", C.c_int32), ("cta_group", C.c_int32),
+    ]
+
+
+_SIGNATURES = {
+    "vcb_abi_version": (C.c_int, []),
+    "vcb_last_error": (C.c_char_p, []),
+    "vcb_launch_count": (C.c_longlong, []),
+    "vcb_reset_launch_count": (None, []),
+    "vcb_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "vcb_attention_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "vcb_ln_modulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "vcb_timestep_embedding": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vcb_silu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "vcb_add3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                           C.c_int32, C.c_void_p]),
+    "vcb_rope_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                 C.c_void_p]),
+    "vcb_euler_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                   C.c_int32, C.c_void_p]),
+    "vcb_copy_cols": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
+                                C.c_void_p]),
+    "vcb_debug_umma_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
+}
+
+# symbols added by later translation units (flux_engine.cu, vae.cu); bound when present in the header list below
+_OPTIONAL: dict = {}
+
+
+def exported_symbols() -> list[str]:
+    return list(_SIGNATURES) + list(_OPTIONAL)
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the library; raises VcbError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VcbError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(visualcloze_b200/csrc/build.sh).  There is no CPU / PyTorch fallback for this path.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in {**_SIGNATURES, **_OPTIONAL}.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if l.vcb_abi_version() != ABI_VERSION:
+            raise VcbError(f"libvcb200.so ABI {l.vcb_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().vcb_last_error()
+        raise VcbError(f"{what}: {msg.decode() if msg else 'error ' + str(rc)}")

@@ -1,0 +1,282 @@
+// capi.cu -- extern "C" boundary of libvcb200.so (see include/vcb200.h) and the host-side launch code.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/vcb200.h"
+#include "attn_sm100.cuh"
+#include "elementwise.cuh"
+#include "gemm_sm100.cuh"
+#include "host_util.cuh"
+#include "probe.cuh"
+
+using namespace vcb;
+
+// ------------------------------------------------------------------------------------------------
+// GEMM dispatch
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <int BN, int CG, int EPI>
+int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    using Cfg = GemmCfg<BN, CG>;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, CG, EPI>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    });
+    if (attr_err != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(attr_err));
+    const int tile_m = kBlockM * CG;
+    const int tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
+    int clusters = num_sms() / CG;
+    if (tiles < clusters) clusters = tiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * CG);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e != cudaSuccess) return set_error("gemm launch (BN=%d CG=%d EPI=%d): %s", BN, CG, EPI, cudaGetErrorString(e));
+    count_launch();
+    return 0;
+}
+
+template <int BN, int CG>
+int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    switch (epi) {
+        case EPI_BIAS: return launch_gemm_inst<BN, CG, EPI_BIAS>(ta, tb, p, st);
+        case EPI_BIAS_GELU: return launch_gemm_inst<BN, CG, EPI_BIAS_GELU>(ta, tb, p, st);
+        case EPI_GATE_RES: return launch_gemm_inst<BN, CG, EPI_GATE_RES>(ta, tb, p, st);
+        default: break;
+    }
+    if constexpr (BN % 128 == 0) {
+        if (epi == EPI_QKV) return launch_gemm_inst<BN, CG, EPI_QKV>(ta, tb, p, st);
+        if (epi == EPI_LINEAR1) return launch_gemm_inst<BN, CG, EPI_LINEAR1>(ta, tb, p, st);
+    }
+    return set_error("gemm: epilogue %d not available for block_n %d", epi, BN);
+}
+
+int default_cta_group() {
+    static int v = [] {
+        const char* e = getenv("VCB_GEMM_CTA_GROUP");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+
+// pick the N tile that minimises (waves x tile width); ties go to the wider tile
+int pick_block_n(int M, int N, int cg, bool head_structured) {
+    const int cands_simple[] = {256, 192, 128};
+    const int cands_head[] = {256, 128};
+    const int* cands = head_structured ? cands_head : cands_simple;
+    const int nc = head_structured ? 2 : 3;
+    const int slots = num_sms() / cg;
+    const int mt = (M + kBlockM * cg - 1) / (kBlockM * cg);
+    long best_cost = -1;
+    int best = 256;
+    for (int i = 0; i < nc; ++i) {
+        const int bn = cands[i];
+        const long tiles = (long)mt * ((N + bn - 1) / bn);
+        const long waves = (tiles + slots - 1) / slots;
+        const long cost = waves * bn;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+    }
+    if (N <= 64 && !head_structured && cg == 1) best = 64;
+    return best;
+}
+
+}  // namespace
+
+extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
+    if (!a) return set_error("gemm: null args");
+    if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error("gemm: bad shape %d %d %d", a->M, a->N, a->K);
+    if (a->K % 8 || a->lda % 8 || a->ldw % 8 || a->ldo % 8 || a->N % 8 || a->out_col_offset % 8)
+        return set_error("gemm: K, N, leading dims and column offsets must be multiples of 8 (16-byte rows)");
+    if (!a->A || !a->W || !a->out) return set_error("gemm: null operand");
+    const bool head = a->epilogue == VCB_EPI_QKV || a->epilogue == VCB_EPI_LINEAR1;
+    if (head) {
+        if (a->hidden <= 0 || a->hidden % 128 || !a->q_scale || !a->k_scale || !a->rope)
+            return set_error("gemm: QKV epilogue needs hidden %% 128 == 0, q/k scales and the rope table");
+        if (a->epilogue == VCB_EPI_LINEAR1 && (!a->out2 || a->ldo2 % 8 || a->out2_col_offset % 8))
+            return set_error("gemm: LINEAR1 epilogue needs out2");
+        if (a->epilogue == VCB_EPI_QKV && a->N != 3 * a->hidden) return set_error("gemm: QKV epilogue needs N == 3*hidden");
+    }
+    if (a->epilogue == VCB_EPI_GATE_RES && (!a->gate || !a->res || a->ld_res % 8 || a->gate_stride % 8))
+        return set_error("gemm: GATE_RES epilogue needs gate and res");
+    if (a->rows_per_batch <= 0) return set_error("gemm: rows_per_batch must be > 0");
+    if (int rc = ensure_device()) return rc;
+
+    int cg = a->cta_group ? a->cta_group : default_cta_group();
+    if (cg == 0) cg = 1;
+    if (cg != 1 && cg != 2) return set_error("gemm: cta_group must be 1 or 2");
+    int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, cg, head);
+
+    GemmParams p{};
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.rows_per_batch = a->rows_per_batch; p.out_batch_rows = a->out_batch_rows; p.out_row_offset = a->out_row_offset;
+    p.bias = a->bias;
+    p.out = (__nv_bfloat16*)a->out; p.ldo = a->ldo; p.out_col_offset = a->out_col_offset;
+    p.gate = (const __nv_bfloat16*)a->gate; p.gate_stride = a->gate_stride;
+    p.res = (const __nv_bfloat16*)a->res; p.ld_res = a->ld_res;
+    p.hidden = a->hidden; p.q_scale = (const __nv_bfloat16*)a->q_scale; p.k_scale = (const __nv_bfloat16*)a->k_scale;
+    p.rope = (const float2*)a->rope;
+    p.out2 = (__nv_bfloat16*)a->out2; p.ldo2 = a->ldo2; p.out2_col_offset = a->out2_col_offset;
+
+    CUtensorMap ta, tb;
+    if (int rc = make_tmap_2d(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, 64, 128)) return rc;
+    if (int rc = make_tmap_2d(&tb, a->W, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldw, 64, (uint32_t)(bn / cg))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+#define VCB_GEMM_CASE(BN, CG) \
+    if (bn == BN && cg == CG) return launch_gemm_epi<BN, CG>(a->epilogue, ta, tb, p, st);
+    VCB_GEMM_CASE(64, 1)
+    VCB_GEMM_CASE(128, 1)
+    VCB_GEMM_CASE(192, 1)
+    VCB_GEMM_CASE(256, 1)
+    VCB_GEMM_CASE(128, 2)
+    VCB_GEMM_CASE(192, 2)
+    VCB_GEMM_CASE(256, 2)
+#undef VCB_GEMM_CASE
+    return set_error("gemm: unsupported (block_n=%d, cta_group=%d)", bn, cg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention
+// ------------------------------------------------------------------------------------------------
+extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_col, int32_t v_col,
+                                 const int32_t* seqlens, int32_t B, int32_t L, int32_t heads, void* out, int64_t ldo,
+                                 int32_t out_col_offset, void* stream) {
+    if (!qkv || !out || B <= 0 || L <= 0 || heads <= 0) return set_error("attention: bad arguments");
+    if (ld_qkv % 8 || ldo % 8 || q_col % 8 || k_col % 8 || v_col % 8 || out_col_offset % 8)
+        return set_error("attention: leading dims / column offsets must be multiples of 8");
+    if (int rc = ensure_device()) return rc;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+    });
+    if (attr_err != cudaSuccess) return set_error("cudaFuncSetAttribute(attn): %s", cudaGetErrorString(attr_err));
+    CUtensorMap tm;
+    if (int rc = make_tmap_3d(&tm, qkv, (uint64_t)ld_qkv, (uint64_t)L, (uint64_t)B, (uint64_t)ld_qkv, (uint64_t)ld_qkv * L, 64, 128)) return rc;
+    AttnParams p{};
+    p.B = B; p.L = L; p.H = heads; p.seqlens = seqlens;
+    p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.out_col_offset = out_col_offset;
+    p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
+    p.scale_log2 = 0.08838834764831845f * 1.4426950408889634f;     // 128^-0.5 * log2(e)
+    dim3 grid((L + kAttnTile - 1) / kAttnTile, heads, B);
+    attn_fwd_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmemBytes, (cudaStream_t)stream>>>(tm, p);
+    return check_launch("attention");
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise
+// ------------------------------------------------------------------------------------------------
+extern "C" int vcb_ln_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, const void* shift, const void* scale,
+                               int64_t mod_stride, int32_t rows, int32_t hidden, int32_t rows_per_batch, void* stream) {
+    if (!x || !y || !shift || !scale || rows <= 0) return set_error("ln_modulate: bad arguments");
+    if (hidden % 256 || hidden > 256 * kLnMaxChunks) return set_error("ln_modulate: hidden must be a multiple of 256, <= %d", 256 * kLnMaxChunks);
+    if (ldx % 8 || ldy % 8 || mod_stride % 8 || rows_per_batch <= 0) return set_error("ln_modulate: strides must be multiples of 8");
+    if (int rc = ensure_device()) return rc;
+    ln_modulate_kernel<<<(rows + kLnWarps - 1) / kLnWarps, kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const __nv_bfloat16*)shift, (const __nv_bfloat16*)scale,
+        mod_stride, rows, hidden, rows_per_batch);
+    return check_launch("ln_modulate");
+}
+
+extern "C" int vcb_timestep_embedding(const float* t_scaled, const float* freqs, void* out, int32_t n, void* stream) {
+    if (!t_scaled || !freqs || !out || n <= 0) return set_error("timestep_embedding: bad arguments");
+    if (int rc = ensure_device()) return rc;
+    timestep_embedding_kernel<<<(n * 128 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t_scaled, freqs, (__nv_bfloat16*)out, n);
+    return check_launch("timestep_embedding");
+}
+
+extern "C" int vcb_silu(const void* x, void* y, int64_t n, void* stream) {
+    if (!x || !y || n <= 0 || n % 2) return set_error("silu: bad arguments");
+    if (int rc = ensure_device()) return rc;
+    const long long thr = n / 2;
+    silu_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n);
+    return check_launch("silu");
+}
+
+extern "C" int vcb_add3(const void* a, const void* b, int32_t b_rows, const void* c, int32_t c_rows, void* out,
+                        int32_t rows, int32_t hidden, void* stream) {
+    if (!a || !out || rows <= 0 || hidden <= 0) return set_error("add3: bad arguments");
+    if ((b && b_rows <= 0) || (c && c_rows <= 0)) return set_error("add3: bad row counts");
+    if (int rc = ensure_device()) return rc;
+    const long long n = (long long)rows * hidden;
+    add3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, b_rows > 0 ? b_rows : 1, (const __nv_bfloat16*)c,
+        c_rows > 0 ? c_rows : 1, (__nv_bfloat16*)out, rows, hidden);
+    return check_launch("add3");
+}
+
+extern "C" int vcb_rope_table(const float* ids, void* out, int32_t rows, int32_t d0, int32_t d1, int32_t d2, double theta,
+                              void* stream) {
+    if (!ids || !out || rows <= 0) return set_error("rope_table: bad arguments");
+    if (d0 + d1 + d2 != 128 || d0 % 2 || d1 % 2 || d2 % 2) return set_error("rope_table: axes must be even and sum to 128");
+    if (int rc = ensure_device()) return rc;
+    const int n = rows * 64;
+    rope_table_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ids, (float2*)out, rows, d0, d1, d2, theta);
+    return check_launch("rope_table");
+}
+
+extern "C" int vcb_euler_update(const void* x, const void* v, float dt_bf16, void* x_new, void* model_in, int64_t ld_in,
+                                int64_t rows, int32_t C, void* stream) {
+    if (!x || !v || !x_new || rows <= 0 || C <= 0) return set_error("euler_update: bad arguments");
+    if (int rc = ensure_device()) return rc;
+    const long long n = rows * C;
+    euler_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)v, dt_bf16, (__nv_bfloat16*)x_new, (__nv_bfloat16*)model_in, ld_in, rows, C);
+    return check_launch("euler_update");
+}
+
+extern "C" int vcb_copy_cols(const void* src, int64_t lds, void* dst, int64_t ldd, int32_t col0, int64_t rows, int32_t C,
+                             void* stream) {
+    if (!src || !dst || rows <= 0 || C <= 0) return set_error("copy_cols: bad arguments");
+    if (int rc = ensure_device()) return rc;
+    const long long n = rows * C;
+    copy_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, col0, rows, C);
+    return check_launch("copy_cols");
+}
+
+// ------------------------------------------------------------------------------------------------
+// probe
+// ------------------------------------------------------------------------------------------------
+extern "C" int vcb_debug_umma_probe(const void* a, const void* b, float* out, int32_t ksteps, int32_t b_mn_major,
+                                    int32_t a_from_tmem, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep_bytes,
+                                    void* stream) {
+    if (!a || !b || !out || (ksteps != 4 && ksteps != 8)) return set_error("probe: ksteps must be 4 or 8");
+    if (int rc = ensure_device()) return rc;
+    const int K = 16 * ksteps;
+    static std::once_flag once;
+    std::call_once(once, [&] { cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 67 * 1024); });
+    CUtensorMap ta, tb;
+    if (int rc = make_tmap_2d(&ta, a, (uint64_t)K, 128, (uint64_t)K, 64, 128)) return rc;
+    if (b_mn_major) {
+        if (int rc = make_tmap_2d(&tb, b, 128, (uint64_t)K, 128, 64, (uint32_t)K)) return rc;
+    } else {
+        if (int rc = make_tmap_2d(&tb, b, (uint64_t)K, 128, (uint64_t)K, 64, 128)) return rc;
+    }
+    ProbeParams p{(const __nv_bfloat16*)a, out, ksteps, b_mn_major, a_from_tmem, b_lbo, b_sbo, b_kstep_bytes};
+    umma_probe_kernel<<<1, 192, 67 * 1024, (cudaStream_t)stream>>>(ta, tb, p);
+    return check_launch("umma_probe");
+}
+
+// ------------------------------------------------------------------------------------------------
+// library
+// ------------------------------------------------------------------------------------------------
+extern "C" int vcb_abi_version(void) { return VCB_ABI_VERSION; }
+extern "C" const char* vcb_last_error(void) { return error_buf(); }
+extern "C" long long vcb_launch_count(void) { return launch_counter().load(); }
+extern "C" void vcb_reset_launch_count(void) { launch_counter().store(0); }

@@ -1,0 +1,333 @@
+// gemm_sm100.cuh -- persistent warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   D[M,N] = epilogue( A[M,K] (bf16, K-major) * W[N,K]^T (bf16, K-major), fp32 accumulate in TMEM )
+//
+// One CTA (or CTA pair, cta_group::2) per SM, 192 threads:
+//   warp 0      TMA producer      global -> 128B-swizzled smem ring (mbarrier full/empty)
+//   warp 1      MMA issuer        one thread issues tcgen05.mma; accumulators double-buffered in TMEM
+//   warps 2..5  epilogue          tcgen05.ld (thread == accumulator row) -> fused math -> global
+//
+// Epilogues replace the reference's un-fused elementwise passes and keep the
+// reference's bf16 rounding points under CUDA autocast (models/modules/layers.py:158-245).
+#pragma once
+#include "vcb_common.cuh"
+
+namespace vcb {
+
+enum GemmEpilogue : int {
+    EPI_BIAS = 0,       // out = bf16(acc + bias)
+    EPI_BIAS_GELU = 1,  // out = bf16(gelu_tanh(bf16(acc + bias)))                         layers.py:143,154
+    EPI_GATE_RES = 2,   // out = bf16(res + bf16(gate * bf16(acc + bias)))                  layers.py:190-195,245
+    EPI_QKV = 3,        // q,k: bias -> QK-RMSNorm -> RoPE ; v: bias                        layers.py:165-174, math.py:112
+    EPI_LINEAR1 = 4,    // cols < 3H as EPI_QKV into out ; cols >= 3H as EPI_BIAS_GELU into out2   layers.py:235-244
+};
+
+struct GemmParams {
+    int M, N, K;
+    // row mapping: input row r -> sample b = r / rows_per_batch, position i = r % rows_per_batch
+    // output row  = b * out_batch_rows + out_row_offset + i   (lets the txt / img streams write one joint buffer)
+    int rows_per_batch;
+    int out_batch_rows;
+    int out_row_offset;
+    const float* bias;           // [N] fp32 (may be null)
+    __nv_bfloat16* out;          // primary output
+    long long ldo;               // elements
+    int out_col_offset;
+    // EPI_GATE_RES
+    const __nv_bfloat16* gate;   // [B, gate_stride] bf16, column n
+    long long gate_stride;
+    const __nv_bfloat16* res;    // [rows, ld_res]; may alias out
+    long long ld_res;
+    // EPI_QKV / EPI_LINEAR1
+    int hidden;                  // H (3H = end of the qkv columns); head_dim is 128
+    const __nv_bfloat16* q_scale;  // [128] RMSNorm scale for q
+    const __nv_bfloat16* k_scale;  // [128]
+    const float2* rope;          // [out rows, 64] (cos, sin), indexed by the mapped output row
+    __nv_bfloat16* out2;         // EPI_LINEAR1: gelu(mlp) destination
+    long long ldo2;
+    int out2_col_offset;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+
+template <int BLOCK_N, int kCtaGroup>
+struct GemmCfg {
+    static constexpr int kBRows = BLOCK_N / kCtaGroup;           // B rows held by one CTA
+    static constexpr int kABytes = kBlockM * kBlockK * 2;        // 16 KB
+    static constexpr int kBBytes = kBRows * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+    static constexpr int kAccStride = BLOCK_N;                   // TMEM columns per accumulator stage
+    static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                     : (2 * BLOCK_N <= 256) ? 256 : 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
+    static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
+};
+
+// ----------------------------------------------------------------------------------------------
+// epilogue helpers (one thread == one accumulator row; v[] holds 32 consecutive columns in fp32)
+// ----------------------------------------------------------------------------------------------
+VCB_DEVICE void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int n0, int N) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (n0 + g * 8 < N) {
+            uint4 u;
+            u.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+            u.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+            u.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+            u.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(dst + g * 8) = u;
+        }
+    }
+}
+
+VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, int n0, int N, float (&v)[32]) {
+    uint32_t r[32];
+    tmem_ld_x32(taddr, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float b = (bias != nullptr && n0 + j < N) ? __ldg(bias + n0 + j) : 0.0f;
+        v[j] = bf16_round(__uint_as_float(r[j]) + b);   // Linear output is a bf16 tensor in the reference
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// the kernel
+// ----------------------------------------------------------------------------------------------
+template <int BLOCK_N, int kCtaGroup, int kEpi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N, kCtaGroup>;
+    constexpr int kStages = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;                    // [kStages]
+    uint64_t* empty_bar = bars + kStages;         // [kStages]
+    uint64_t* tmem_full = bars + 2 * kStages;     // [2]
+    uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const uint32_t warp = warp_id_uniform();
+    const uint32_t lane = lane_id();
+    const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
+    const bool is_leader = (cta_rank == 0);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 128 * kCtaGroup);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<kCtaGroup>(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    if constexpr (kCtaGroup == 2) cluster_sync(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tile_m = kBlockM * kCtaGroup;
+    const int num_m = (p.M + tile_m - 1) / tile_m;
+    const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+    const int cluster_id = blockIdx.x / kCtaGroup;
+    const int num_clusters = gridDim.x / kCtaGroup;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                const int m0 = (t % num_m) * tile_m + (int)cta_rank * kBlockM;
+                const int n0 = (t / num_m) * BLOCK_N + (int)cta_rank * Cfg::kBRows;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (is_leader) mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes * kCtaGroup);
+                    tma_load_2d<kCtaGroup == 2>(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBlockK,
+                                                m0, kEvictNormal);
+                    tma_load_2d<kCtaGroup == 2>(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBlockK,
+                                                n0, kEvictNormal);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA) =====================
+        if (is_leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCtaGroup, BLOCK_N, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes), 16, 1024, kSwizzle128B);
+                    const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024, kSwizzle128B);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        // advance 16 bf16 = 32 B inside the 128B swizzle span: +2 in the (addr >> 4) field
+                        umma_ss<kCtaGroup>(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                                           (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit<kCtaGroup>(&empty_bar[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit<kCtaGroup>(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const uint32_t quarter = warp & 3;                  // TMEM lane quarter this warp may access
+        const int row_in_tile = quarter * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+            const int m0 = (t % num_m) * tile_m + (int)cta_rank * kBlockM;
+            const int n_tile0 = (t / num_m) * BLOCK_N;
+            const int r = m0 + row_in_tile;
+            const bool row_ok = r < p.M;
+            const int b = row_ok ? r / p.rows_per_batch : 0;
+            const int i = row_ok ? r % p.rows_per_batch : 0;
+            const long long orow = (long long)b * p.out_batch_rows + p.out_row_offset + i;
+
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * Cfg::kAccStride;
+
+            if constexpr (kEpi == EPI_BIAS || kEpi == EPI_BIAS_GELU || kEpi == EPI_GATE_RES) {
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    const int n0 = n_tile0 + c * 32;
+                    if (n0 >= p.N) break;
+                    float v[32];
+                    load_acc_bias(taddr + c * 32, p.bias, n0, p.N, v);
+                    if (!row_ok) continue;
+                    if constexpr (kEpi == EPI_BIAS_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+                    }
+                    if constexpr (kEpi == EPI_GATE_RES) {
+                        const __nv_bfloat16* g = p.gate + (long long)b * p.gate_stride + n0;
+                        const __nv_bfloat16* rs = p.res + orow * p.ld_res + n0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (n0 + q * 8 < p.N) {
+                                uint4 gu = __ldg(reinterpret_cast<const uint4*>(g + q * 8));
+                                uint4 ru = *reinterpret_cast<const uint4*>(rs + q * 8);
+                                const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
+                                const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float2 gf = unpack_bf16x2(gw[e]);
+                                    float2 rf = unpack_bf16x2(rw[e]);
+                                    float a0 = bf16_round(gf.x * v[q * 8 + 2 * e]);
+                                    float a1 = bf16_round(gf.y * v[q * 8 + 2 * e + 1]);
+                                    v[q * 8 + 2 * e] = rf.x + a0;
+                                    v[q * 8 + 2 * e + 1] = rf.y + a1;
+                                }
+                            }
+                        }
+                    }
+                    store_bf16x32(p.out + orow * p.ldo + p.out_col_offset + n0, v, n0, p.N);
+                }
+            } else {
+                // EPI_QKV / EPI_LINEAR1: the tile is processed in 128-column groups (one head each)
+                static_assert(kEpi != EPI_QKV && kEpi != EPI_LINEAR1 || BLOCK_N % 128 == 0, "head-structured epilogue");
+#pragma unroll 1
+                for (int hg = 0; hg < BLOCK_N / 128; ++hg) {
+                    const int ng = n_tile0 + hg * 128;           // first column of this 128-group
+                    if (ng >= p.N) break;
+                    const uint32_t tg = taddr + hg * 128;
+                    const int region = ng / p.hidden;            // 0 q, 1 k, 2 v, >= 3 mlp (LINEAR1)
+                    if (region >= 2) {
+#pragma unroll 1
+                        for (int c = 0; c < 4; ++c) {
+                            const int n0 = ng + c * 32;
+                            float v[32];
+                            load_acc_bias(tg + c * 32, p.bias, n0, p.N, v);
+                            if (!row_ok) continue;
+                            if (kEpi == EPI_LINEAR1 && region >= 3) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+                                store_bf16x32(p.out2 + orow * p.ldo2 + p.out2_col_offset + (n0 - 3 * p.hidden), v, n0, p.N);
+                            } else {
+                                store_bf16x32(p.out + orow * p.ldo + p.out_col_offset + n0, v, n0, p.N);
+                            }
+                        }
+                    } else {
+                        // pass 1: sum of squares of the bf16-rounded projection over the head (RMSNorm, layers.py:68-72)
+                        float ss = 0.f;
+#pragma unroll 1
+                        for (int c = 0; c < 4; ++c) {
+                            float v[32];
+                            load_acc_bias(tg + c * 32, p.bias, ng + c * 32, p.N, v);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
+                        }
+                        const float rrms = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
+                        const __nv_bfloat16* sc = region == 0 ? p.q_scale : p.k_scale;
+                        const float2* rp = p.rope + orow * 64;
+                        // pass 2: normalise, scale, rotate, store
+#pragma unroll 1
+                        for (int c = 0; c < 4; ++c) {
+                            const int n0 = ng + c * 32;
+                            float v[32];
+                            load_acc_bias(tg + c * 32, p.bias, n0, p.N, v);
+                            if (!row_ok) continue;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const int d = c * 32 + j;       // dim inside the head
+                                float s0 = __bfloat162float(sc[d]), s1 = __bfloat162float(sc[d + 1]);
+                                float x0 = bf16_round(bf16_round(v[j] * rrms) * s0);
+                                float x1 = bf16_round(bf16_round(v[j + 1] * rrms) * s1);
+                                float2 cs = __ldg(rp + (d >> 1));
+                                // math.py:112-117: two fp32 products, one fp32 add (no contraction)
+                                v[j] = __fadd_rn(__fmul_rn(cs.x, x0), __fmul_rn(-cs.y, x1));
+                                v[j + 1] = __fadd_rn(__fmul_rn(cs.y, x0), __fmul_rn(cs.x, x1));
+                            }
+                            store_bf16x32(p.out + orow * p.ldo + p.out_col_offset + n0, v, n0, p.N);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            if constexpr (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
+            else mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    // ===================== teardown =====================
+    tc_fence_before();
+    if constexpr (kCtaGroup == 2) cluster_sync(); else __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<kCtaGroup>(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+}  // namespace vcb

@@ -1,0 +1,140 @@
+"""Thin torch-tensor wrappers over the C ABI (pointer + size marshalling only; no arithmetic here)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, check
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RES, EPI_QKV, EPI_LINEAR1 = range(5)
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _lib.VcbError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.VcbError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise _lib.VcbError(f"{name} must be contiguous in its last dimension")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: torch.Tensor, *, epilogue: int = EPI_BIAS,
+         out_col_offset: int = 0, rows_per_batch: int | None = None, out_batch_rows: int | None = None,
+         out_row_offset: int = 0, gate: torch.Tensor | None = None, res: torch.Tensor | None = None,
+         hidden: int = 0, q_scale=None, k_scale=None, rope=None, out2=None, out2_col_offset: int = 0,
+         block_n: int = 0, cta_group: int = 0) -> torch.Tensor:
+    """out[...] = epilogue(a @ w.T).  a [M,K], w [N,K], out 2-D (rows, ld); see include/vcb200.h."""
+    _req(a, BF16, "a"); _req(w, BF16, "w"); _req(out, BF16, "out")
+    M, K = a.shape
+    N = w.shape[0]
+    g = GemmArgs()
+    g.M, g.N, g.K = M, N, K
+    g.A, g.lda = a.data_ptr(), a.stride(0)
+    g.W, g.ldw = w.data_ptr(), w.stride(0)
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+    g.bias = _p(bias)
+    g.out, g.ldo, g.out_col_offset = out.data_ptr(), out.stride(0), out_col_offset
+    g.rows_per_batch = rows_per_batch or M
+    g.out_batch_rows = out_batch_rows if out_batch_rows is not None else g.rows_per_batch
+    g.out_row_offset = out_row_offset
+    g.epilogue = epilogue
+    if gate is not None:
+        _req(gate, BF16, "gate"); _req(res, BF16, "res")
+        g.gate, g.gate_stride = gate.data_ptr(), gate.stride(0)
+        g.res, g.ld_res = res.data_ptr(), res.stride(0)
+    g.hidden = hidden
+    g.q_scale, g.k_scale, g.rope = _p(q_scale), _p(k_scale), _p(rope)
+    if out2 is not None:
+        _req(out2, BF16, "out2")
+        g.out2, g.ldo2, g.out2_col_offset = out2.data_ptr(), out2.stride(0), out2_col_offset
+    g.block_n, g.cta_group = block_n, cta_group
+    check(_lib.lib().vcb_gemm_bf16(C.byref(g), _stream()), "vcb_gemm_bf16")
+    return out
+
+
+def attention(qkv: torch.Tensor, B: int, L: int, heads: int, out: torch.Tensor, *, q_col: int, k_col: int, v_col: int,
+              seqlens: torch.Tensor | None = None, out_col_offset: int = 0) -> torch.Tensor:
+    """qkv [B*L, ld] bf16 (post RoPE / QK-norm) -> out [B*L, ldo]; models/math.py:63-99."""
+    _req(qkv, BF16, "qkv"); _req(out, BF16, "out")
+    if seqlens is not None:
+        _req(seqlens, torch.int32, "seqlens")
+    check(_lib.lib().vcb_attention_fwd(qkv.data_ptr(), qkv.stride(0), q_col, k_col, v_col, _p(seqlens), B, L, heads,
+                                       out.data_ptr(), out.stride(0), out_col_offset, _stream()), "vcb_attention_fwd")
+    return out
+
+
+def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: torch.Tensor, rows_per_batch: int,
+                mod_stride: int | None = None) -> torch.Tensor:
+    """out = bf16((1 + scale[b]) * LayerNorm(x) + shift[b]); x/out [rows, H]; shift/scale rows per sample."""
+    _req(x, BF16, "x"); _req(out, BF16, "out"); _req(shift, BF16, "shift"); _req(scale, BF16, "scale")
+    rows, H = x.shape
+    ms = mod_stride if mod_stride is not None else (shift.stride(0) if shift.dim() > 1 else 0)
+    check(_lib.lib().vcb_ln_modulate(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), shift.data_ptr(),
+                                     scale.data_ptr(), ms, rows, H, rows_per_batch, _stream()), "vcb_ln_modulate")
+    return out
+
+
+def timestep_embedding(t_scaled: torch.Tensor, freqs: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _req(t_scaled, torch.float32, "t_scaled"); _req(freqs, torch.float32, "freqs"); _req(out, BF16, "out")
+    check(_lib.lib().vcb_timestep_embedding(t_scaled.data_ptr(), freqs.data_ptr(), out.data_ptr(), t_scaled.numel(),
+                                            _stream()), "vcb_timestep_embedding")
+    return out
+
+
+def silu(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _req(x, BF16, "x"); _req(out, BF16, "out")
+    check(_lib.lib().vcb_silu(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "vcb_silu")
+    return out
+
+
+def add3(a, b, c, out) -> torch.Tensor:
+    _req(a, BF16, "a"); _req(out, BF16, "out")
+    rows, H = a.shape
+    check(_lib.lib().vcb_add3(a.data_ptr(), _p(b), 0 if b is None else b.shape[0], _p(c), 0 if c is None else c.shape[0],
+                              out.data_ptr(), rows, H, _stream()), "vcb_add3")
+    return out
+
+
+def rope_table(ids: torch.Tensor, axes_dim, theta: float, out: torch.Tensor) -> torch.Tensor:
+    """ids [rows, 3] fp32 -> out [rows, 64, 2] fp32 (cos, sin)."""
+    _req(ids, torch.float32, "ids"); _req(out, torch.float32, "out")
+    check(_lib.lib().vcb_rope_table(ids.data_ptr(), out.data_ptr(), ids.shape[0], axes_dim[0], axes_dim[1], axes_dim[2],
+                                    float(theta), _stream()), "vcb_rope_table")
+    return out
+
+
+def euler_update(x, v, dt_bf16: float, x_new, model_in=None) -> torch.Tensor:
+    _req(x, BF16, "x"); _req(v, BF16, "v"); _req(x_new, BF16, "x_new")
+    rows, Cc = x.shape
+    check(_lib.lib().vcb_euler_update(x.data_ptr(), v.data_ptr(), dt_bf16, x_new.data_ptr(), _p(model_in),
+                                      0 if model_in is None else model_in.stride(0), rows, Cc, _stream()),
+          "vcb_euler_update")
+    return x_new
+
+
+def copy_cols(src, dst, col0: int) -> torch.Tensor:
+    _req(src, BF16, "src"); _req(dst, BF16, "dst")
+    rows, Cc = src.shape
+    check(_lib.lib().vcb_copy_cols(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), col0, rows, Cc,
+                                   _stream()), "vcb_copy_cols")
+    return dst
+
+
+def umma_probe(a, b, ksteps: int, b_mn_major: bool, a_from_tmem: bool, b_lbo: int = 0, b_sbo: int = 0,
+               b_kstep_bytes: int = 0) -> torch.Tensor:
+    out = torch.empty(128, 128, dtype=torch.float32, device=a.device)
+    check(_lib.lib().vcb_debug_umma_probe(a.data_ptr(), b.data_ptr(), out.data_ptr(), ksteps, int(b_mn_major),
+                                          int(a_from_tmem), b_lbo, b_sbo, b_kstep_bytes, _stream()), "vcb_debug_umma_probe")
+    return out
