@@ -44,14 +44,15 @@ enum vcb_epilogue {
 
 typedef struct vcb_gemm_args {
     int32_t M, N, K;
-    const void* A;  int64_t lda;     /* [M, K] bf16 */
+    const void* A;  int64_t lda;     /* [M, K] bf16; with batching: sample b starts at A + b * a_batch_stride */
+    int64_t a_batch_stride;          /* elements; 0 = rows_per_batch * lda (plain matrix) */
     const void* W;  int64_t ldw;     /* [N, K] bf16 (nn.Linear.weight layout) */
     const float* bias;               /* [N] fp32 or NULL */
     void* out;      int64_t ldo;     /* bf16 */
     int32_t out_col_offset;
-    /* row mapping: input row r -> sample b = r / rows_per_batch, i = r % rows_per_batch,
-       output row = b * out_batch_rows + out_row_offset + i.  Set rows_per_batch = M,
-       out_batch_rows = M, out_row_offset = 0 for the identity. */
+    /* batching: M = batch * rows_per_batch; row i of sample b is read from A + b * a_batch_stride + i * lda and
+       written to output row b * out_batch_rows + out_row_offset + i (res is indexed the same way, gate by b).
+       Set rows_per_batch = M, out_batch_rows = M, out_row_offset = 0 for a plain matrix. */
     int32_t rows_per_batch, out_batch_rows, out_row_offset;
     int32_t epilogue;                /* enum vcb_epilogue */
     /* VCB_EPI_GATE_RES */
@@ -77,9 +78,12 @@ int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_
                       void* out, int64_t ldo, int32_t out_col_offset, void* stream);
 
 /* ---- AdaLN modulated LayerNorm (layers.py:163-164,191,195,234,257):
- *      y = bf16( bf16(1 + scale[b]) * LayerNorm(x) + shift[b] ), eps 1e-6, no affine; hidden % 256 == 0 */
+ *      y = bf16( bf16(1 + scale[b]) * LayerNorm(x) + shift[b] ), eps 1e-6, no affine; hidden % 256 == 0.
+ *      Logical row r = (b, i) with b = r / rows_per_batch lives at physical row b * batch_rows + i of x and y
+ *      (batch_rows = 0 means rows_per_batch, i.e. a plain [rows, hidden] matrix). */
 int vcb_ln_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, const void* shift, const void* scale,
-                    int64_t mod_stride, int32_t rows, int32_t hidden, int32_t rows_per_batch, void* stream);
+                    int64_t mod_stride, int32_t rows, int32_t hidden, int32_t rows_per_batch, int32_t batch_rows,
+                    void* stream);
 
 /* ---- small helpers --------------------------------------------------------------------------------------- */
 /* layers.py:28-49; t_scaled = time_factor * t already in the reference's dtype; freqs[128] fp32; out [n,256] bf16 */
@@ -97,6 +101,54 @@ int vcb_euler_update(const void* x, const void* v, float dt_bf16, void* x_new, v
                      int64_t rows, int32_t C, void* stream);
 int vcb_copy_cols(const void* src, int64_t lds, void* dst, int64_t ldd, int32_t col0, int64_t rows, int32_t C,
                   void* stream);
+
+
+/* ---- FLUX-DiT engine: the whole Flux.forward (models/model.py:85-124) and the Euler loop around it -----------
+ * Weights are the reference's tensors with LoRA merged (W' = W + s*B*A, b' = b + s*b_B; lora.py:92-98), bf16
+ * weights [out, in], fp32 biases.  The engine keeps pointers only; the caller owns weights and workspace. */
+typedef struct vcb_linear_w { const void* w; const float* b; } vcb_linear_w;
+
+typedef struct vcb_stream_w {           /* one stream of a DoubleStreamBlock (layers.py:129-156) */
+    vcb_linear_w mod, qkv, proj, mlp0, mlp2;
+    const void* q_scale; const void* k_scale;      /* [128] bf16 */
+} vcb_stream_w;
+typedef struct vcb_double_w { vcb_stream_w img, txt; } vcb_double_w;
+typedef struct vcb_single_w {           /* SingleStreamBlock (layers.py:199-230) */
+    vcb_linear_w mod, linear1, linear2;
+    const void* q_scale; const void* k_scale;
+} vcb_single_w;
+
+typedef struct vcb_flux_config {        /* FluxParams (models/model.py:18-32) */
+    int32_t in_channels, out_channels, vec_in_dim, context_in_dim, hidden, mlp_hidden, heads;
+    int32_t depth, depth_single, axes_dim[3], guidance_embed;
+    double theta;
+} vcb_flux_config;
+
+typedef struct vcb_flux_weights {
+    vcb_linear_w img_in, txt_in, time_in0, time_in1, vector_in0, vector_in1, guidance_in0, guidance_in1;
+    vcb_linear_w final_mod, final_linear;
+    const vcb_double_w* dbl;            /* host array [depth] */
+    const vcb_single_w* sgl;            /* host array [depth_single] */
+} vcb_flux_weights;
+
+typedef struct vcb_flux vcb_flux;       /* opaque */
+
+int  vcb_flux_create(const vcb_flux_config* cfg, const vcb_flux_weights* w, vcb_flux** out);
+void vcb_flux_destroy(vcb_flux* f);
+/* bytes of device workspace for B samples of Li image + Lt text tokens and n_evals model evaluations */
+int64_t vcb_flux_workspace_bytes(const vcb_flux* f, int32_t B, int32_t Li, int32_t Lt, int32_t n_evals);
+/* Step-invariant work, once per image (txt_in, RoPE table, and the AdaLN modulation vectors of
+ * all n_evals steps as one batched GEMM per block).  t_scaled: [n_evals * B] fp32 = 1000 * flux_time (row e*B+b);
+ * g_scaled: [B] fp32 = float(bf16(1000 * guidance)) or NULL; freqs: [128] fp32 (layers.py:39); txt [B,Lt,ctx] bf16;
+ * y [B, vec_in] bf16; ids [B, Lt+Li, 3] fp32 (txt ids first); seqlens [B] int32 valid tokens of the joint
+ * sequence (Lt + valid img tokens) or NULL. */
+int vcb_flux_prepare(vcb_flux* f, void* workspace, int64_t workspace_bytes, int32_t B, int32_t Li, int32_t Lt,
+                     int32_t n_evals, const void* txt, const void* y, const float* ids, const float* t_scaled,
+                     const float* g_scaled, const float* freqs, const int32_t* seqlens, void* stream);
+/* One model evaluation (Flux.forward) with the tables of evaluation `eval_idx`:
+ * img [B*Li, in_channels] bf16 (latent || cond) -> out [B*Li, out_channels] bf16. */
+int vcb_flux_forward(vcb_flux* f, int32_t eval_idx, const void* img, int64_t ld_img, void* out, int64_t ld_out,
+                     void* stream);
 
 /* ---- test hook: one 128x128x(16*ksteps) tcgen05 MMA with caller-chosen descriptor fields -------------------
  * Used by tests/ to pin the smem/TMEM operand layouts the kernels rely on.  a: [128, K] bf16 (K-major),

@@ -3,7 +3,7 @@
 # Usage (on the GPU box, from the repo root): tools/gpu_diag.sh [pytest -k expressions...]
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > gpurun_out/diag_gpu.txt 2>&1
-GROUPS_DEFAULT=("probe" "gemm_bias and cta_group1" "gemm_bias and cta_group2" "gemm_block64 or gemm_gelu or gemm_gate" "gemm_qkv or gemm_linear1" "attention" "ln_modulate or timestep or rope_table")
+GROUPS_DEFAULT=("probe" "gemm_bias and (0-1 or 128-1 or 192-1 or 256-1)" "gemm_bias and (0-2 or 128-2 or 192-2 or 256-2)" "gemm_block64 or gemm_gelu or gemm_gate" "gemm_qkv or gemm_linear1" "attention" "ln_modulate or timestep or rope_table")
 if [[ $# -gt 0 ]]; then GROUPS_SEL=("$@"); else GROUPS_SEL=("${GROUPS_DEFAULT[@]}"); fi
 i=0
 for g in "${GROUPS_SEL[@]}"; do

@@ -19,7 +19,7 @@ class GemmArgs(C.Structure):
     """struct vcb_gemm_args (include/vcb200.h)."""
     _fields_ = [
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
-        ("A", C.c_void_p), ("lda", C.c_int64),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("a_batch_stride", C.c_int64),
         ("W", C.c_void_p), ("ldw", C.c_int64),
         ("bias", C.c_void_p),
         ("out", C.c_void_p), ("ldo", C.c_int64),
@@ -45,7 +45,7 @@ _SIGNATURES = {
     "vcb_attention_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "vcb_ln_modulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
-                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vcb_timestep_embedding": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "vcb_silu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "vcb_add3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
@@ -60,8 +60,47 @@ _SIGNATURES = {
                                        C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
 }
 
-# symbols added by later translation units (flux_engine.cu, vae.cu); bound when present in the header list below
-_OPTIONAL: dict = {}
+class LinearW(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p)]
+
+
+class StreamW(C.Structure):
+    _fields_ = [("mod", LinearW), ("qkv", LinearW), ("proj", LinearW), ("mlp0", LinearW), ("mlp2", LinearW),
+                ("q_scale", C.c_void_p), ("k_scale", C.c_void_p)]
+
+
+class DoubleW(C.Structure):
+    _fields_ = [("img", StreamW), ("txt", StreamW)]
+
+
+class SingleW(C.Structure):
+    _fields_ = [("mod", LinearW), ("linear1", LinearW), ("linear2", LinearW), ("q_scale", C.c_void_p),
+                ("k_scale", C.c_void_p)]
+
+
+class FluxConfigC(C.Structure):
+    _fields_ = [("in_channels", C.c_int32), ("out_channels", C.c_int32), ("vec_in_dim", C.c_int32),
+                ("context_in_dim", C.c_int32), ("hidden", C.c_int32), ("mlp_hidden", C.c_int32), ("heads", C.c_int32),
+                ("depth", C.c_int32), ("depth_single", C.c_int32), ("axes_dim", C.c_int32 * 3),
+                ("guidance_embed", C.c_int32), ("theta", C.c_double)]
+
+
+class FluxWeightsC(C.Structure):
+    _fields_ = [("img_in", LinearW), ("txt_in", LinearW), ("time_in0", LinearW), ("time_in1", LinearW),
+                ("vector_in0", LinearW), ("vector_in1", LinearW), ("guidance_in0", LinearW), ("guidance_in1", LinearW),
+                ("final_mod", LinearW), ("final_linear", LinearW),
+                ("dbl", C.POINTER(DoubleW)), ("sgl", C.POINTER(SingleW))]
+
+
+_OPTIONAL: dict = {
+    "vcb_flux_create": (C.c_int, [C.POINTER(FluxConfigC), C.POINTER(FluxWeightsC), C.POINTER(C.c_void_p)]),
+    "vcb_flux_destroy": (None, [C.c_void_p]),
+    "vcb_flux_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "vcb_flux_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
+    "vcb_flux_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+}
 
 
 def exported_symbols() -> list[str]:

@@ -31,7 +31,7 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     });
     if (attr_err != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(attr_err));
     const int tile_m = kBlockM * CG;
-    const int tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
+    const int tiles = p.batch * ((p.rows_per_batch + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
     int clusters = num_sms() / CG;
     if (tiles < clusters) clusters = tiles;
     cudaLaunchConfig_t cfg{};
@@ -76,13 +76,13 @@ int default_cta_group() {
 }
 
 // pick the N tile that minimises (waves x tile width); ties go to the wider tile
-int pick_block_n(int M, int N, int cg, bool head_structured) {
+int pick_block_n(int batch, int rows, int N, int cg, bool head_structured) {
     const int cands_simple[] = {256, 192, 128};
     const int cands_head[] = {256, 128};
     const int* cands = head_structured ? cands_head : cands_simple;
     const int nc = head_structured ? 2 : 3;
     const int slots = num_sms() / cg;
-    const int mt = (M + kBlockM * cg - 1) / (kBlockM * cg);
+    const int mt = batch * ((rows + kBlockM * cg - 1) / (kBlockM * cg));
     long best_cost = -1;
     int best = 256;
     for (int i = 0; i < nc; ++i) {
@@ -114,16 +114,19 @@ extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
     }
     if (a->epilogue == VCB_EPI_GATE_RES && (!a->gate || !a->res || a->ld_res % 8 || a->gate_stride % 8))
         return set_error("gemm: GATE_RES epilogue needs gate and res");
-    if (a->rows_per_batch <= 0) return set_error("gemm: rows_per_batch must be > 0");
+    if (a->rows_per_batch <= 0 || a->M % a->rows_per_batch) return set_error("gemm: M must be a multiple of rows_per_batch");
+    const int batch = a->M / a->rows_per_batch;
+    const int64_t a_bstride = a->a_batch_stride ? a->a_batch_stride : (int64_t)a->rows_per_batch * a->lda;
+    if (a_bstride % 8) return set_error("gemm: a_batch_stride must be a multiple of 8");
     if (int rc = ensure_device()) return rc;
 
     int cg = a->cta_group ? a->cta_group : default_cta_group();
     if (cg == 0) cg = 1;
     if (cg != 1 && cg != 2) return set_error("gemm: cta_group must be 1 or 2");
-    int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, cg, head);
+    int bn = a->block_n ? a->block_n : pick_block_n(batch, a->rows_per_batch, a->N, cg, head);
 
     GemmParams p{};
-    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.N = a->N; p.K = a->K; p.batch = batch;
     p.rows_per_batch = a->rows_per_batch; p.out_batch_rows = a->out_batch_rows; p.out_row_offset = a->out_row_offset;
     p.bias = a->bias;
     p.out = (__nv_bfloat16*)a->out; p.ldo = a->ldo; p.out_col_offset = a->out_col_offset;
@@ -134,7 +137,8 @@ extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
     p.out2 = (__nv_bfloat16*)a->out2; p.ldo2 = a->ldo2; p.out2_col_offset = a->out2_col_offset;
 
     CUtensorMap ta, tb;
-    if (int rc = make_tmap_2d(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, 64, 128)) return rc;
+    if (int rc = make_tmap_3d(&ta, a->A, (uint64_t)a->K, (uint64_t)a->rows_per_batch, (uint64_t)batch, (uint64_t)a->lda,
+                              (uint64_t)a_bstride, 64, 128)) return rc;
     if (int rc = make_tmap_2d(&tb, a->W, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldw, 64, (uint32_t)(bn / cg))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
 #define VCB_GEMM_CASE(BN, CG) \
@@ -182,14 +186,15 @@ extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col,
 // elementwise
 // ------------------------------------------------------------------------------------------------
 extern "C" int vcb_ln_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, const void* shift, const void* scale,
-                               int64_t mod_stride, int32_t rows, int32_t hidden, int32_t rows_per_batch, void* stream) {
+                               int64_t mod_stride, int32_t rows, int32_t hidden, int32_t rows_per_batch, int32_t batch_rows,
+                               void* stream) {
     if (!x || !y || !shift || !scale || rows <= 0) return set_error("ln_modulate: bad arguments");
     if (hidden % 256 || hidden > 256 * kLnMaxChunks) return set_error("ln_modulate: hidden must be a multiple of 256, <= %d", 256 * kLnMaxChunks);
     if (ldx % 8 || ldy % 8 || mod_stride % 8 || rows_per_batch <= 0) return set_error("ln_modulate: strides must be multiples of 8");
     if (int rc = ensure_device()) return rc;
     ln_modulate_kernel<<<(rows + kLnWarps - 1) / kLnWarps, kLnWarps * 32, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const __nv_bfloat16*)shift, (const __nv_bfloat16*)scale,
-        mod_stride, rows, hidden, rows_per_batch);
+        mod_stride, rows, hidden, rows_per_batch, batch_rows > 0 ? batch_rows : rows_per_batch);
     return check_launch("ln_modulate");
 }
 

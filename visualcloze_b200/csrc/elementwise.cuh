@@ -16,13 +16,15 @@ constexpr int kLnWarps = 4;
 __global__ void __launch_bounds__(kLnWarps * 32)
 ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
                    const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
-                   long long mod_stride, int rows, int H, int rows_per_batch) {
+                   long long mod_stride, int rows, int H, int rows_per_batch, int batch_rows) {
     const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const int nchunks = H >> 8;                    // H % 256 == 0
     const int b = row / rows_per_batch;
-    const __nv_bfloat16* xr = x + (long long)row * ldx;
+    // logical row (b, i) lives at physical row b * batch_rows + i of x and y (a stream inside a joint [B, L, H] buffer)
+    const long long prow = (long long)b * batch_rows + (row - b * rows_per_batch);
+    const __nv_bfloat16* xr = x + prow * ldx;
     float v[kLnMaxChunks][8];
     float sum = 0.f;
 #pragma unroll
@@ -57,7 +59,7 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bflo
     const float rstd = rsqrtf(sq / (float)H + 1e-6f);
     const __nv_bfloat16* sh = shift + (long long)b * mod_stride;
     const __nv_bfloat16* sc = scale + (long long)b * mod_stride;
-    __nv_bfloat16* yr = y + (long long)row * ldy;
+    __nv_bfloat16* yr = y + prow * ldy;
 #pragma unroll
     for (int c = 0; c < kLnMaxChunks; ++c)
         if (c < nchunks) {

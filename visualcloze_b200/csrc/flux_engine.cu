@@ -1,0 +1,279 @@
+// flux_engine.cu -- Flux.forward (models/model.py:85-124) as a fixed sequence of libvcb200 kernel launches.
+//
+// Data layout in HBM (all bf16 unless noted), B samples, L = Lt + Li tokens per sample, txt rows first:
+//   x    [B, L, H]         residual stream of both streams (the reference keeps img/txt apart and cats them at
+//                          model.py:116; here the double blocks address their stream through row offsets)
+//   xm   [B, L, H]         AdaLN-modulated LayerNorm output (GEMM A operand)
+//   qkv  [B, L, 3H]        q | k | v after bias, QK-RMSNorm and RoPE (GEMM epilogue) -> attention operand
+//   cat  [B, L, H + mlp]   columns [0,H): attention output; [H,H+mlp): GELU(mlp-up)  == linear2 input (layers.py:244)
+//   rope [B, L, 64] float2, txt0 [B, Lt, H] (txt_in output), modulation tables for all evaluations.
+// Step-invariant work is hoisted into vcb_flux_prepare.
+#include <vector>
+
+#include "../../include/vcb200.h"
+#include "host_util.cuh"
+
+using namespace vcb;
+
+struct vcb_flux {
+    vcb_flux_config cfg;
+    vcb_flux_weights w;
+    std::vector<vcb_double_w> dbl;
+    std::vector<vcb_single_w> sgl;
+    // prepared state
+    bool prepared = false;
+    int B = 0, Li = 0, Lt = 0, L = 0, E = 0;
+    const int32_t* seqlens = nullptr;
+    float2* rope = nullptr;
+    uint16_t *txt0 = nullptr, *temb_t = nullptr, *temb_g = nullptr, *h1 = nullptr, *e_time = nullptr, *e_guid = nullptr,
+             *e_vec = nullptr, *vec = nullptr, *svec = nullptr, *mod_final = nullptr, *x = nullptr, *xm = nullptr,
+             *qkv = nullptr, *cat = nullptr;
+    std::vector<uint16_t*> mod_dbl;   // [depth * 2] (img, txt), each [E*B, 6H]
+    std::vector<uint16_t*> mod_sgl;   // [depth_single], each [E*B, 3H]
+};
+
+namespace {
+
+struct Carver {
+    uint8_t* base;
+    int64_t off = 0;
+    template <class T>
+    T* take(int64_t count) {
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += ((count * (int64_t)sizeof(T) + 255) / 256) * 256;
+        return p;
+    }
+};
+
+// carve the workspace; with base == nullptr only the size is computed
+int64_t carve(vcb_flux* f, uint8_t* base, int B, int Li, int Lt, int E) {
+    const vcb_flux_config& c = f->cfg;
+    const int64_t H = c.hidden, L = Li + Lt, EB = (int64_t)E * B;
+    Carver cv{base};
+    float2* rope = cv.take<float2>((int64_t)B * L * 64);
+    uint16_t* txt0 = cv.take<uint16_t>((int64_t)B * Lt * H);
+    uint16_t* temb_t = cv.take<uint16_t>(EB * 256);
+    uint16_t* temb_g = cv.take<uint16_t>((int64_t)B * 256);
+    uint16_t* h1 = cv.take<uint16_t>(EB * H);
+    uint16_t* e_time = cv.take<uint16_t>(EB * H);
+    uint16_t* e_guid = cv.take<uint16_t>((int64_t)B * H);
+    uint16_t* e_vec = cv.take<uint16_t>((int64_t)B * H);
+    uint16_t* vec = cv.take<uint16_t>(EB * H);
+    uint16_t* svec = cv.take<uint16_t>(EB * H);
+    std::vector<uint16_t*> md(c.depth * 2), ms(c.depth_single);
+    for (auto& p : md) p = cv.take<uint16_t>(EB * 6 * H);
+    for (auto& p : ms) p = cv.take<uint16_t>(EB * 3 * H);
+    uint16_t* mod_final = cv.take<uint16_t>(EB * 2 * H);
+    uint16_t* x = cv.take<uint16_t>((int64_t)B * L * H);
+    uint16_t* xm = cv.take<uint16_t>((int64_t)B * L * H);
+    uint16_t* qkv = cv.take<uint16_t>((int64_t)B * L * 3 * H);
+    uint16_t* cat = cv.take<uint16_t>((int64_t)B * L * (H + c.mlp_hidden));
+    if (base) {
+        f->rope = rope; f->txt0 = txt0; f->temb_t = temb_t; f->temb_g = temb_g; f->h1 = h1; f->e_time = e_time;
+        f->e_guid = e_guid; f->e_vec = e_vec; f->vec = vec; f->svec = svec; f->mod_dbl = md; f->mod_sgl = ms;
+        f->mod_final = mod_final; f->x = x; f->xm = xm; f->qkv = qkv; f->cat = cat;
+    }
+    return cv.off;
+}
+
+// plain [M,K] x [N,K]^T GEMM through the public entry point
+int linear(const void* A, int64_t lda, int M, int K, const vcb_linear_w& w, int N, void* out, int64_t ldo, int epi,
+           void* stream) {
+    vcb_gemm_args g{};
+    g.M = M; g.N = N; g.K = K;
+    g.A = A; g.lda = lda;
+    g.W = w.w; g.ldw = K; g.bias = w.b;
+    g.out = out; g.ldo = ldo;
+    g.rows_per_batch = M; g.out_batch_rows = M;
+    g.epilogue = epi;
+    return vcb_gemm_bf16(&g, stream);
+}
+
+}  // namespace
+
+extern "C" int vcb_flux_create(const vcb_flux_config* cfg, const vcb_flux_weights* w, vcb_flux** out) {
+    if (!cfg || !w || !out) return set_error("flux_create: null argument");
+    if (cfg->hidden != cfg->heads * 128) return set_error("flux_create: head_dim must be 128 (hidden = heads * 128)");
+    if (cfg->hidden % 256) return set_error("flux_create: hidden must be a multiple of 256");
+    if (cfg->axes_dim[0] + cfg->axes_dim[1] + cfg->axes_dim[2] != 128) return set_error("flux_create: axes_dim must sum to 128");
+    if (cfg->in_channels % 8 || cfg->out_channels % 8 || cfg->vec_in_dim % 8 || cfg->context_in_dim % 8 || cfg->mlp_hidden % 128)
+        return set_error("flux_create: channel counts must be multiples of 8 (mlp_hidden of 128)");
+    if (cfg->depth < 0 || cfg->depth_single < 0 || (cfg->depth && !w->dbl) || (cfg->depth_single && !w->sgl))
+        return set_error("flux_create: missing block weights");
+    vcb_flux* f = new vcb_flux();
+    f->cfg = *cfg;
+    f->w = *w;
+    f->dbl.assign(w->dbl, w->dbl + cfg->depth);
+    f->sgl.assign(w->sgl, w->sgl + cfg->depth_single);
+    f->w.dbl = f->dbl.data();
+    f->w.sgl = f->sgl.data();
+    *out = f;
+    return 0;
+}
+
+extern "C" void vcb_flux_destroy(vcb_flux* f) { delete f; }
+
+extern "C" int64_t vcb_flux_workspace_bytes(const vcb_flux* f, int32_t B, int32_t Li, int32_t Lt, int32_t n_evals) {
+    if (!f || B <= 0 || Li <= 0 || Lt < 0 || n_evals <= 0) return -1;
+    return carve(const_cast<vcb_flux*>(f), nullptr, B, Li, Lt, n_evals);
+}
+
+extern "C" int vcb_flux_prepare(vcb_flux* f, void* workspace, int64_t workspace_bytes, int32_t B, int32_t Li, int32_t Lt,
+                                int32_t n_evals, const void* txt, const void* y, const float* ids, const float* t_scaled,
+                                const float* g_scaled, const float* freqs, const int32_t* seqlens, void* stream) {
+    if (!f || !workspace || !txt || !y || !ids || !t_scaled || !freqs) return set_error("flux_prepare: null argument");
+    if (B <= 0 || Li <= 0 || Lt <= 0 || n_evals <= 0) return set_error("flux_prepare: bad sizes");
+    const vcb_flux_config& c = f->cfg;
+    if (c.guidance_embed && !g_scaled) return set_error("Didn't get guidance strength for guidance distilled model.");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return set_error("flux_prepare: workspace must be 256-byte aligned");
+    const int64_t need = carve(f, nullptr, B, Li, Lt, n_evals);
+    if (workspace_bytes < need) return set_error("flux_prepare: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+    carve(f, static_cast<uint8_t*>(workspace), B, Li, Lt, n_evals);
+    f->B = B; f->Li = Li; f->Lt = Lt; f->L = Li + Lt; f->E = n_evals; f->seqlens = seqlens;
+    f->prepared = false;
+    const int H = c.hidden, EB = n_evals * B;
+    int rc;
+    // RoPE table (constant across steps; the reference recomputes it per call, model.py:110-111)
+    if ((rc = vcb_rope_table(ids, f->rope, B * f->L, c.axes_dim[0], c.axes_dim[1], c.axes_dim[2], c.theta, stream))) return rc;
+    // txt_in (constant across steps, model.py:108)
+    if ((rc = linear(txt, c.context_in_dim, B * Lt, c.context_in_dim, f->w.txt_in, H, f->txt0, H, VCB_EPI_BIAS, stream))) return rc;
+    // vec for every evaluation (model.py:102-107)
+    if ((rc = vcb_timestep_embedding(t_scaled, freqs, f->temb_t, EB, stream))) return rc;
+    if ((rc = linear(f->temb_t, 256, EB, 256, f->w.time_in0, H, f->h1, H, VCB_EPI_BIAS, stream))) return rc;
+    if ((rc = vcb_silu(f->h1, f->h1, (int64_t)EB * H, stream))) return rc;
+    if ((rc = linear(f->h1, H, EB, H, f->w.time_in1, H, f->e_time, H, VCB_EPI_BIAS, stream))) return rc;
+    if (c.guidance_embed) {
+        if ((rc = vcb_timestep_embedding(g_scaled, freqs, f->temb_g, B, stream))) return rc;
+        if ((rc = linear(f->temb_g, 256, B, 256, f->w.guidance_in0, H, f->h1, H, VCB_EPI_BIAS, stream))) return rc;
+        if ((rc = vcb_silu(f->h1, f->h1, (int64_t)B * H, stream))) return rc;
+        if ((rc = linear(f->h1, H, B, H, f->w.guidance_in1, H, f->e_guid, H, VCB_EPI_BIAS, stream))) return rc;
+    }
+    if ((rc = linear(y, c.vec_in_dim, B, c.vec_in_dim, f->w.vector_in0, H, f->h1, H, VCB_EPI_BIAS, stream))) return rc;
+    if ((rc = vcb_silu(f->h1, f->h1, (int64_t)B * H, stream))) return rc;
+    if ((rc = linear(f->h1, H, B, H, f->w.vector_in1, H, f->e_vec, H, VCB_EPI_BIAS, stream))) return rc;
+    if ((rc = vcb_add3(f->e_time, c.guidance_embed ? f->e_guid : nullptr, B, f->e_vec, B, f->vec, EB, H, stream))) return rc;
+    if ((rc = vcb_silu(f->vec, f->svec, (int64_t)EB * H, stream))) return rc;
+    // AdaLN modulation vectors of all evaluations: one GEMM per block reads each modulation weight once per image
+    // instead of once per step (layers.py:121 is a GEMV re-reading 6.5 GB per step in the reference)
+    for (int i = 0; i < c.depth; ++i) {
+        if ((rc = linear(f->svec, H, EB, H, f->dbl[i].img.mod, 6 * H, f->mod_dbl[2 * i], 6 * H, VCB_EPI_BIAS, stream))) return rc;
+        if ((rc = linear(f->svec, H, EB, H, f->dbl[i].txt.mod, 6 * H, f->mod_dbl[2 * i + 1], 6 * H, VCB_EPI_BIAS, stream))) return rc;
+    }
+    for (int i = 0; i < c.depth_single; ++i)
+        if ((rc = linear(f->svec, H, EB, H, f->sgl[i].mod, 3 * H, f->mod_sgl[i], 3 * H, VCB_EPI_BIAS, stream))) return rc;
+    if ((rc = linear(f->svec, H, EB, H, f->w.final_mod, 2 * H, f->mod_final, 2 * H, VCB_EPI_BIAS, stream))) return rc;
+    f->prepared = true;
+    return 0;
+}
+
+namespace {
+
+struct StreamView {
+    int rows;      // tokens of this stream per sample
+    int off;       // first row of the stream inside a sample's L rows
+};
+
+// GEMM over one stream of the joint buffers: A rows (b, off + i) of `a_buf`, output rows (b, off + i) of `out`
+int stream_gemm(const vcb_flux* f, const StreamView& sv, const uint16_t* a_buf, int64_t lda, int a_col, int K,
+                const vcb_linear_w& w, int N, int epi, uint16_t* out, int64_t ldo, int out_col, const uint16_t* gate,
+                int64_t gate_stride, const vcb_stream_w* qk, const void* q_scale, const void* k_scale, uint16_t* out2,
+                int64_t ldo2, int out2_col, void* stream) {
+    (void)qk;
+    vcb_gemm_args g{};
+    g.M = f->B * sv.rows; g.N = N; g.K = K;
+    g.A = a_buf + (int64_t)sv.off * lda + a_col; g.lda = lda; g.a_batch_stride = (int64_t)f->L * lda;
+    g.W = w.w; g.ldw = K; g.bias = w.b;
+    g.out = out; g.ldo = ldo; g.out_col_offset = out_col;
+    g.rows_per_batch = sv.rows; g.out_batch_rows = f->L; g.out_row_offset = sv.off;
+    g.epilogue = epi;
+    g.gate = gate; g.gate_stride = gate_stride; g.res = out; g.ld_res = ldo;
+    g.hidden = f->cfg.hidden; g.q_scale = q_scale; g.k_scale = k_scale; g.rope = f->rope;
+    g.out2 = out2; g.ldo2 = ldo2; g.out2_col_offset = out2_col;
+    return vcb_gemm_bf16(&g, stream);
+}
+
+int stream_ln(const vcb_flux* f, const StreamView& sv, const uint16_t* shift, const uint16_t* scale, int64_t mod_stride,
+              void* stream) {
+    const int H = f->cfg.hidden;
+    return vcb_ln_modulate(f->x + (int64_t)sv.off * H, H, f->xm + (int64_t)sv.off * H, H, shift, scale, mod_stride,
+                           f->B * sv.rows, H, sv.rows, f->L, stream);
+}
+
+}  // namespace
+
+extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t ld_img, void* out, int64_t ld_out,
+                                void* stream) {
+    if (!f || !img || !out) return set_error("flux_forward: null argument");
+    if (!f->prepared) return set_error("flux_forward: call vcb_flux_prepare first");
+    if (e < 0 || e >= f->E) return set_error("flux_forward: eval index %d out of range [0, %d)", e, f->E);
+    const vcb_flux_config& c = f->cfg;
+    const int H = c.hidden, mlp = c.mlp_hidden, B = f->B, L = f->L, Li = f->Li, Lt = f->Lt;
+    const int64_t ldc = H + mlp;
+    const StreamView s_img{Li, Lt}, s_txt{Lt, 0}, s_all{L, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    // img_in (model.py:101) straight into the img rows of x; txt rows <- txt0
+    {
+        vcb_gemm_args g{};
+        g.M = B * Li; g.N = H; g.K = c.in_channels;
+        g.A = img; g.lda = ld_img;
+        g.W = f->w.img_in.w; g.ldw = c.in_channels; g.bias = f->w.img_in.b;
+        g.out = f->x; g.ldo = H;
+        g.rows_per_batch = Li; g.out_batch_rows = L; g.out_row_offset = Lt;
+        g.epilogue = VCB_EPI_BIAS;
+        if ((rc = vcb_gemm_bf16(&g, stream))) return rc;
+    }
+    for (int b = 0; b < B; ++b) {
+        cudaError_t ce = cudaMemcpyAsync(f->x + (int64_t)b * L * H, f->txt0 + (int64_t)b * Lt * H, (size_t)Lt * H * 2,
+                                         cudaMemcpyDeviceToDevice, st);
+        if (ce != cudaSuccess) return set_error("flux_forward: txt copy: %s", cudaGetErrorString(ce));
+    }
+    const int64_t erow = (int64_t)e * B;     // first modulation row of this evaluation
+    // ---- double-stream blocks (layers.py:158-196) ----
+    for (int i = 0; i < c.depth; ++i) {
+        const vcb_double_w& w = f->dbl[i];
+        const vcb_stream_w* sw[2] = {&w.img, &w.txt};
+        const StreamView* sv[2] = {&s_img, &s_txt};
+        const uint16_t* mod[2] = {f->mod_dbl[2 * i] + erow * 6 * H, f->mod_dbl[2 * i + 1] + erow * 6 * H};
+        for (int s = 0; s < 2; ++s) {
+            if ((rc = stream_ln(f, *sv[s], mod[s] + 0, mod[s] + H, 6 * H, stream))) return rc;
+            if ((rc = stream_gemm(f, *sv[s], f->xm, H, 0, H, sw[s]->qkv, 3 * H, VCB_EPI_QKV, f->qkv, 3 * H, 0, nullptr, 0,
+                                  nullptr, sw[s]->q_scale, sw[s]->k_scale, nullptr, 0, 0, stream))) return rc;
+        }
+        if ((rc = vcb_attention_fwd(f->qkv, 3 * H, 0, H, 2 * H, f->seqlens, B, L, c.heads, f->cat, ldc, 0, stream))) return rc;
+        for (int s = 0; s < 2; ++s) {
+            if ((rc = stream_gemm(f, *sv[s], f->cat, ldc, 0, H, sw[s]->proj, H, VCB_EPI_GATE_RES, f->x, H, 0, mod[s] + 2 * H,
+                                  6 * H, nullptr, nullptr, nullptr, nullptr, 0, 0, stream))) return rc;
+            if ((rc = stream_ln(f, *sv[s], mod[s] + 3 * H, mod[s] + 4 * H, 6 * H, stream))) return rc;
+            if ((rc = stream_gemm(f, *sv[s], f->xm, H, 0, H, sw[s]->mlp0, mlp, VCB_EPI_BIAS_GELU, f->cat, ldc, H, nullptr, 0,
+                                  nullptr, nullptr, nullptr, nullptr, 0, 0, stream))) return rc;
+            if ((rc = stream_gemm(f, *sv[s], f->cat, ldc, H, mlp, sw[s]->mlp2, H, VCB_EPI_GATE_RES, f->x, H, 0, mod[s] + 5 * H,
+                                  6 * H, nullptr, nullptr, nullptr, nullptr, 0, 0, stream))) return rc;
+        }
+    }
+    // ---- single-stream blocks on the joint sequence (layers.py:232-245) ----
+    for (int i = 0; i < c.depth_single; ++i) {
+        const vcb_single_w& w = f->sgl[i];
+        const uint16_t* mod = f->mod_sgl[i] + erow * 3 * H;
+        if ((rc = stream_ln(f, s_all, mod + 0, mod + H, 3 * H, stream))) return rc;
+        if ((rc = stream_gemm(f, s_all, f->xm, H, 0, H, w.linear1, 3 * H + mlp, VCB_EPI_LINEAR1, f->qkv, 3 * H, 0, nullptr, 0,
+                              nullptr, w.q_scale, w.k_scale, f->cat, ldc, H, stream))) return rc;
+        if ((rc = vcb_attention_fwd(f->qkv, 3 * H, 0, H, 2 * H, f->seqlens, B, L, c.heads, f->cat, ldc, 0, stream))) return rc;
+        if ((rc = stream_gemm(f, s_all, f->cat, ldc, 0, H + mlp, w.linear2, H, VCB_EPI_GATE_RES, f->x, H, 0, mod + 2 * H, 3 * H,
+                              nullptr, nullptr, nullptr, nullptr, 0, 0, stream))) return rc;
+    }
+    // ---- final layer on the img rows (layers.py:255-259; chunk order shift, scale) ----
+    {
+        const uint16_t* mod = f->mod_final + erow * 2 * H;
+        if ((rc = stream_ln(f, s_img, mod + 0, mod + H, 2 * H, stream))) return rc;
+        vcb_gemm_args g{};
+        g.M = B * Li; g.N = c.out_channels; g.K = H;
+        g.A = f->xm + (int64_t)Lt * H; g.lda = H; g.a_batch_stride = (int64_t)L * H;
+        g.W = f->w.final_linear.w; g.ldw = H; g.bias = f->w.final_linear.b;
+        g.out = out; g.ldo = ld_out;
+        g.rows_per_batch = Li; g.out_batch_rows = Li; g.out_row_offset = 0;
+        g.epilogue = VCB_EPI_BIAS;
+        if ((rc = vcb_gemm_bf16(&g, stream))) return rc;
+    }
+    return 0;
+}

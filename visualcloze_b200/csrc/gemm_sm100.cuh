@@ -23,9 +23,11 @@ enum GemmEpilogue : int {
 };
 
 struct GemmParams {
-    int M, N, K;
-    // row mapping: input row r -> sample b = r / rows_per_batch, position i = r % rows_per_batch
-    // output row  = b * out_batch_rows + out_row_offset + i   (lets the txt / img streams write one joint buffer)
+    int N, K;
+    // A is a [batch, rows_per_batch, K] tensor (3-D TMA map; batch == 1 for a plain matrix).  M tiles never
+    // straddle samples.  Row i of sample b is written to output row  b * out_batch_rows + out_row_offset + i,
+    // which lets the txt / img streams read from and write to one joint [B, L, *] buffer without copies.
+    int batch;
     int rows_per_batch;
     int out_batch_rows;
     int out_row_offset;
@@ -87,6 +89,7 @@ VCB_DEVICE void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int n0, 
 
 VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, int n0, int N, float (&v)[32]) {
     uint32_t r[32];
+    __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge after predicated stores
     tmem_ld_x32(taddr, r);
     tmem_wait_ld();
 #pragma unroll
@@ -143,7 +146,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const uint32_t tmem_base = *tmem_slot;
 
     const int tile_m = kBlockM * kCtaGroup;
-    const int num_m = (p.M + tile_m - 1) / tile_m;
+    const int m_per_sample = (p.rows_per_batch + tile_m - 1) / tile_m;
+    const int num_m = m_per_sample * p.batch;
     const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = num_m * num_n;
     const int num_kb = (p.K + kBlockK - 1) / kBlockK;
@@ -156,19 +160,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             int stage = 0;
             uint32_t phase = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-                const int m0 = (t % num_m) * tile_m + (int)cta_rank * kBlockM;
+                const int mt = t % num_m;
+                const int bi = mt / m_per_sample;
+                const int m0 = (mt % m_per_sample) * tile_m + (int)cta_rank * kBlockM;
                 const int n0 = (t / num_m) * BLOCK_N + (int)cta_rank * Cfg::kBRows;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (is_leader) mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes * kCtaGroup);
-                    tma_load_2d<kCtaGroup == 2>(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBlockK,
-                                                m0, kEvictNormal);
+                    tma_load_3d<kCtaGroup == 2>(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBlockK,
+                                                m0, bi, kEvictNormal);
                     tma_load_2d<kCtaGroup == 2>(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBlockK,
                                                 n0, kEvictNormal);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA) =====================
         if (is_leader && lane == 0) {
@@ -199,6 +206,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
+        __syncwarp();
     } else {
         // ===================== epilogue warps =====================
         const uint32_t quarter = warp & 3;                  // TMEM lane quarter this warp may access
@@ -206,13 +214,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-            const int m0 = (t % num_m) * tile_m + (int)cta_rank * kBlockM;
+            const int mt = t % num_m;
+            const int b = mt / m_per_sample;
             const int n_tile0 = (t / num_m) * BLOCK_N;
-            const int r = m0 + row_in_tile;
-            const bool row_ok = r < p.M;
-            const int b = row_ok ? r / p.rows_per_batch : 0;
-            const int i = row_ok ? r % p.rows_per_batch : 0;
-            const long long orow = (long long)b * p.out_batch_rows + p.out_row_offset + i;
+            const int i = (mt % m_per_sample) * tile_m + (int)cta_rank * kBlockM + row_in_tile;
+            const bool row_ok = i < p.rows_per_batch;
+            const long long orow = (long long)b * p.out_batch_rows + p.out_row_offset + (row_ok ? i : 0);
 
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -225,7 +232,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     if (n0 >= p.N) break;
                     float v[32];
                     load_acc_bias(taddr + c * 32, p.bias, n0, p.N, v);
-                    if (!row_ok) continue;
+                    if (row_ok) {
                     if constexpr (kEpi == EPI_BIAS_GELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
@@ -253,6 +260,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         }
                     }
                     store_bf16x32(p.out + orow * p.ldo + p.out_col_offset + n0, v, n0, p.N);
+                    }
                 }
             } else {
                 // EPI_QKV / EPI_LINEAR1: the tile is processed in 128-column groups (one head each)
@@ -269,8 +277,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             const int n0 = ng + c * 32;
                             float v[32];
                             load_acc_bias(tg + c * 32, p.bias, n0, p.N, v);
-                            if (!row_ok) continue;
-                            if (kEpi == EPI_LINEAR1 && region >= 3) {
+                            if (!row_ok) {
+                            } else if (kEpi == EPI_LINEAR1 && region >= 3) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
                                 store_bf16x32(p.out2 + orow * p.ldo2 + p.out2_col_offset + (n0 - 3 * p.hidden), v, n0, p.N);
@@ -297,7 +305,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             const int n0 = ng + c * 32;
                             float v[32];
                             load_acc_bias(tg + c * 32, p.bias, n0, p.N, v);
-                            if (!row_ok) continue;
+                            if (row_ok) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) {
                                 const int d = c * 32 + j;       // dim inside the head
@@ -310,6 +318,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                 v[j + 1] = __fadd_rn(__fmul_rn(cs.y, x0), __fmul_rn(cs.x, x1));
                             }
                             store_bf16x32(p.out + orow * p.ldo + p.out_col_offset + n0, v, n0, p.N);
+                            }
                         }
                     }
                 }
@@ -319,6 +328,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             else mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        __syncwarp();
     }
 
     // ===================== teardown =====================

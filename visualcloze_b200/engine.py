@@ -1,0 +1,168 @@
+"""Host-side driver of the FLUX-DiT engine in libvcb200 (vcb_flux_* in include/vcb200.h).
+
+Packs the reference's parameters (LoRA merged), owns the device workspace, and marshals pointers.  Arithmetic
+done here in torch is limited to one-off weight packing (``W + s * B @ A`` at load time) and scalar/host
+bookkeeping (time grids, masks -> sequence lengths); every per-token operation of the path runs in the library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import DoubleW, FluxConfigC, FluxWeightsC, LinearW, SingleW, StreamW, check
+
+BF16 = torch.bfloat16
+
+
+def _freqs() -> Tensor:
+    """frequency table of timestep_embedding (layers.py:39), computed exactly like the reference does."""
+    half = 128
+    return torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+
+
+class FluxEngine:
+    def __init__(self, params, named_params: dict[str, Tensor], lora_scale: float = 1.0):
+        some = next(iter(named_params.values()))
+        if not some.is_cuda:
+            raise _lib.VcbError("FluxEngine needs the model on a CUDA device: the hot path has no CPU fallback")
+        self.params = params
+        self.device = some.device
+        self.lib = _lib.lib()
+        self._keep: list[Tensor] = []          # packed tensors referenced by the C structs
+        self._p = named_params
+        self._scale = float(lora_scale)
+        self.H = params.hidden_size
+        self.mlp = int(params.hidden_size * params.mlp_ratio)
+        with torch.no_grad():
+            self._build()
+        self._ws = None
+        self._shape = None
+        self._freqs = _freqs().to(self.device)
+
+    # ---- weight packing -----------------------------------------------------------------------
+    def _linear(self, name: str) -> LinearW:
+        p = self._p
+        w = p[name + ".weight"]
+        a = p.get(name + ".lora_A.weight")
+        b = p.get(name + ".bias")
+        if a is not None:
+            # merged LoRA (lora.py:92-98): W' = W + s * B A in fp32, rounded once to bf16
+            w = (w.float() + self._scale * (p[name + ".lora_B.weight"].float() @ a.float())).to(BF16)
+        else:
+            w = w.to(BF16)
+        w = w.contiguous()
+        bias = torch.zeros(w.shape[0], dtype=torch.float32, device=w.device) if b is None else b.float()
+        bb = p.get(name + ".lora_B.bias")
+        if bb is not None:
+            bias = bias + self._scale * bb.float()
+        bias = bias.contiguous()
+        self._keep += [w, bias]
+        return LinearW(w.data_ptr(), bias.data_ptr())
+
+    def _scale_vec(self, name: str) -> int:
+        t = self._p[name].to(BF16).contiguous()
+        self._keep.append(t)
+        return t.data_ptr()
+
+    def _build(self):
+        P = self.params
+        cfg = FluxConfigC()
+        cfg.in_channels, cfg.out_channels = P.in_channels, P.out_channels
+        cfg.vec_in_dim, cfg.context_in_dim = P.vec_in_dim, P.context_in_dim
+        cfg.hidden, cfg.mlp_hidden, cfg.heads = self.H, self.mlp, P.num_heads
+        cfg.depth, cfg.depth_single = P.depth, P.depth_single_blocks
+        cfg.axes_dim[0], cfg.axes_dim[1], cfg.axes_dim[2] = P.axes_dim
+        cfg.guidance_embed, cfg.theta = int(P.guidance_embed), float(P.theta)
+        w = FluxWeightsC()
+        w.img_in, w.txt_in = self._linear("img_in"), self._linear("txt_in")
+        w.time_in0, w.time_in1 = self._linear("time_in.in_layer"), self._linear("time_in.out_layer")
+        w.vector_in0, w.vector_in1 = self._linear("vector_in.in_layer"), self._linear("vector_in.out_layer")
+        if P.guidance_embed:
+            w.guidance_in0, w.guidance_in1 = self._linear("guidance_in.in_layer"), self._linear("guidance_in.out_layer")
+        w.final_mod, w.final_linear = self._linear("final_layer.adaLN_modulation.1"), self._linear("final_layer.linear")
+        dbl = (DoubleW * max(1, P.depth))()
+        for i in range(P.depth):
+            for s, dst in (("img", dbl[i].img), ("txt", dbl[i].txt)):
+                b = f"double_blocks.{i}.{s}"
+                dst.mod, dst.qkv, dst.proj = self._linear(b + "_mod.lin"), self._linear(b + "_attn.qkv"), self._linear(b + "_attn.proj")
+                dst.mlp0, dst.mlp2 = self._linear(b + "_mlp.0"), self._linear(b + "_mlp.2")
+                dst.q_scale = self._scale_vec(b + "_attn.norm.query_norm.scale")
+                dst.k_scale = self._scale_vec(b + "_attn.norm.key_norm.scale")
+        sgl = (SingleW * max(1, P.depth_single_blocks))()
+        for i in range(P.depth_single_blocks):
+            b = f"single_blocks.{i}"
+            sgl[i].mod, sgl[i].linear1, sgl[i].linear2 = self._linear(b + ".modulation.lin"), self._linear(b + ".linear1"), self._linear(b + ".linear2")
+            sgl[i].q_scale = self._scale_vec(b + ".norm.query_norm.scale")
+            sgl[i].k_scale = self._scale_vec(b + ".norm.key_norm.scale")
+        w.dbl, w.sgl = C.cast(dbl, C.POINTER(DoubleW)), C.cast(sgl, C.POINTER(SingleW))
+        self._cfg, self._w, self._dbl, self._sgl = cfg, w, dbl, sgl
+        h = C.c_void_p()
+        check(self.lib.vcb_flux_create(C.byref(cfg), C.byref(w), C.byref(h)), "vcb_flux_create")
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self.lib.vcb_flux_destroy(h)
+            self._h = None
+
+    # ---- per-image state ------------------------------------------------------------------------
+    def prepare(self, *, txt: Tensor, y: Tensor, img_ids: Tensor, txt_ids: Tensor, timesteps: Tensor,
+                guidance: Tensor | None, txt_mask: Tensor | None, img_mask: Tensor | None, n_img_tokens: int) -> None:
+        """Step-invariant work for ``E = timesteps.shape[0]`` evaluations (timesteps [E, B], FLUX time)."""
+        if txt.ndim != 3:
+            raise ValueError("Input img and txt tensors must have 3 dimensions.")
+        B, Lt, _ = txt.shape
+        Li = int(n_img_tokens)
+        E = int(timesteps.shape[0])
+        dev = self.device
+        st = torch.cuda.current_stream().cuda_stream
+        need = self.lib.vcb_flux_workspace_bytes(self._h, B, Li, Lt, E)
+        if need < 0:
+            raise _lib.VcbError("vcb_flux_workspace_bytes: bad shape")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
+        # `time_factor * t` in the dtype the reference computes it in (layers.py:37): fp32 timesteps stay fp32,
+        # the bf16 guidance is scaled in bf16 (30 -> 29952)
+        ts = (1000.0 * timesteps.to(dev)).float().reshape(E * B).contiguous()
+        gs = None
+        if self.params.guidance_embed:
+            if guidance is None:
+                raise ValueError("Didn't get guidance strength for guidance distilled model.")
+            gs = (1000.0 * guidance.to(dev)).float().reshape(B).contiguous()
+        ids = torch.cat((txt_ids.to(dev), img_ids.to(dev)), dim=1).float().contiguous()
+        if ids.shape != (B, Lt + Li, 3):
+            raise ValueError(f"ids must be [B, Lt+Li, 3], got {tuple(ids.shape)}")
+        seqlens = None
+        if img_mask is not None:
+            tm = txt_mask if txt_mask is not None else torch.ones(B, Lt, dtype=torch.int32, device=dev)
+            seqlens = (tm.to(dev).sum(dim=-1, dtype=torch.int32) + img_mask.to(dev).sum(dim=-1, dtype=torch.int32)).contiguous()
+        txt_c = txt.to(dev, BF16).contiguous()
+        y_c = y.to(dev, BF16).contiguous()
+        self._hold = (ts, gs, ids, seqlens, txt_c, y_c)      # keep alive until the next prepare
+        check(self.lib.vcb_flux_prepare(self._h, self._ws.data_ptr(), self._ws.numel(), B, Li, Lt, E, txt_c.data_ptr(),
+                                        y_c.data_ptr(), ids.data_ptr(), ts.data_ptr(), None if gs is None else gs.data_ptr(),
+                                        self._freqs.data_ptr(), None if seqlens is None else seqlens.data_ptr(), st),
+              "vcb_flux_prepare")
+        self._shape = (B, Li, Lt, E)
+
+    def forward(self, eval_idx: int, img: Tensor, out: Tensor | None = None) -> Tensor:
+        """One Flux.forward with the tables of evaluation ``eval_idx``: img [B, Li, in_channels] -> [B, Li, out_channels]."""
+        if self._shape is None:
+            raise _lib.VcbError("FluxEngine.forward called before prepare")
+        B, Li, Lt, E = self._shape
+        if img.ndim != 3:
+            raise ValueError("Input img and txt tensors must have 3 dimensions.")
+        if tuple(img.shape) != (B, Li, self.params.in_channels):
+            raise ValueError(f"img must be {(B, Li, self.params.in_channels)}, got {tuple(img.shape)}")
+        if img.dtype != BF16 or not img.is_cuda or img.stride(2) != 1 or img.stride(0) != Li * img.stride(1):
+            img = img.to(self.device, BF16).contiguous()
+        if out is None:
+            out = torch.empty(B, Li, self.params.out_channels, dtype=BF16, device=self.device)
+        check(self.lib.vcb_flux_forward(self._h, eval_idx, img.data_ptr(), img.stride(1), out.data_ptr(), out.stride(1),
+                                        torch.cuda.current_stream().cuda_stream), "vcb_flux_forward")
+        return out

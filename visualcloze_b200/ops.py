@@ -33,14 +33,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: torch
          out_col_offset: int = 0, rows_per_batch: int | None = None, out_batch_rows: int | None = None,
          out_row_offset: int = 0, gate: torch.Tensor | None = None, res: torch.Tensor | None = None,
          hidden: int = 0, q_scale=None, k_scale=None, rope=None, out2=None, out2_col_offset: int = 0,
-         block_n: int = 0, cta_group: int = 0) -> torch.Tensor:
-    """out[...] = epilogue(a @ w.T).  a [M,K], w [N,K], out 2-D (rows, ld); see include/vcb200.h."""
+         block_n: int = 0, cta_group: int = 0, a_batch_stride: int = 0, m: int | None = None) -> torch.Tensor:
+    """out[...] = epilogue(a @ w.T).  a [M,K], w [N,K], out 2-D (rows, ld); see include/vcb200.h.
+    With batching (rows_per_batch < M) sample b's rows start at a + b * a_batch_stride (elements)."""
     _req(a, BF16, "a"); _req(w, BF16, "w"); _req(out, BF16, "out")
     M, K = a.shape
+    if m is not None:
+        M = m
     N = w.shape[0]
     g = GemmArgs()
     g.M, g.N, g.K = M, N, K
-    g.A, g.lda = a.data_ptr(), a.stride(0)
+    g.A, g.lda, g.a_batch_stride = a.data_ptr(), a.stride(0), a_batch_stride
     g.W, g.ldw = w.data_ptr(), w.stride(0)
     if bias is not None:
         _req(bias, torch.float32, "bias")
@@ -76,13 +79,14 @@ def attention(qkv: torch.Tensor, B: int, L: int, heads: int, out: torch.Tensor, 
 
 
 def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: torch.Tensor, rows_per_batch: int,
-                mod_stride: int | None = None) -> torch.Tensor:
+                mod_stride: int | None = None, rows: int | None = None, batch_rows: int = 0) -> torch.Tensor:
     """out = bf16((1 + scale[b]) * LayerNorm(x) + shift[b]); x/out [rows, H]; shift/scale rows per sample."""
     _req(x, BF16, "x"); _req(out, BF16, "out"); _req(shift, BF16, "shift"); _req(scale, BF16, "scale")
-    rows, H = x.shape
+    H = x.shape[1]
+    rows = rows if rows is not None else x.shape[0]
     ms = mod_stride if mod_stride is not None else (shift.stride(0) if shift.dim() > 1 else 0)
     check(_lib.lib().vcb_ln_modulate(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), shift.data_ptr(),
-                                     scale.data_ptr(), ms, rows, H, rows_per_batch, _stream()), "vcb_ln_modulate")
+                                     scale.data_ptr(), ms, rows, H, rows_per_batch, batch_rows, _stream()), "vcb_ln_modulate")
     return out
 
 
