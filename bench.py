@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the VisualCloze denoising hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload B|A|Bp|D|E]
+
+One "step" = one image of the workload: the flow-matching Euler loop over the FLUX-DiT (30 time points = 29 model
+evaluations for the 384 grid 2x3 layout) plus the VAE decode of the query row, on synthetic
+inputs of the reference's shapes with random-init weights of the reference's geometry (no checkpoints offline).
+
+  value   images/sec with the inputs already resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e     the same through the public API with HOST (pinned) buffers: H2D of the step's inputs and D2H of the
+          result inside the timed region
+  roofline / roofline_attention   achieved TFLOP/s of the GEMM / attention kernels (algorithmic FLOPs over the sum of
+          their launch durations, CUDA events around every launch of one instrumented image) vs the measured peak
+  cpu_baseline   the CPU oracle port (the reference's algorithm, un-merged LoRA, bf16 autocast semantics) timed on
+          the host cores on a bounded sample (1 double + 1 single block at full width and full token count),
+          extrapolated to images/sec -- a reported baseline, not the target.
+
+`--impl reference` times that CPU port as the reference arm (the reference itself is pure PyTorch+flash-attn and
+cannot run on CPU as shipped, nor travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+BF16 = torch.bfloat16
+WORKLOADS = {  # key: (grid_h, grid_w, res, num_steps, do_shift, strength, description)
+    "A": (1, 1, 384, 4, True, None, "single 384x384 1x1 grid, 4 Euler time points (3 NFE)"),
+    "B": (2, 3, 384, 30, True, None, "384 grid 2x3 in-context, 30 Euler time points (29 NFE), batch 1 per GPU"),
+    "Bp": (3, 3, 384, 30, True, None, "384 grid 3x3 (2 demos + query), 30 time points (29 NFE)"),
+    "C": (2, 3, 512, 30, True, None, "512 grid 2x3, 30 time points (29 NFE), batch 1 per GPU"),
+    "D": (3, 4, 384, 30, True, None, "384 grid 3x4 multi-task layout, 30 time points (29 NFE)"),
+    "E": (1, 1, 1024, 20, False, 0.4, "SDEdit upsampling 1024^2, 20 time points (19 NFE), strength 0.4"),
+}
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------------
+# synthetic inputs: generated on CPU from a seeded generator, identical bits on every rank/run
+# ------------------------------------------------------------------------------------------------------
+def make_inputs(workload: str, seed: int):
+    gh, gw, res, *_ = WORKLOADS[workload]
+    g = torch.Generator().manual_seed(seed)
+    h, w = res // 16, gw * res // 16
+    ids = []
+    for j in range(gh):
+        t = torch.zeros(h, w, 3)
+        t[..., 0] = j + 1
+        t[..., 1] += torch.arange(h)[:, None]
+        t[..., 2] += torch.arange(w)[None, :]
+        ids.append(t.reshape(-1, 3))
+    img_ids = torch.cat(ids)[None]
+    Li, Lt = img_ids.shape[1], 512
+    x = torch.randn(1, Li, 64, generator=g).to(BF16)                       # packed noise rows (visualcloze.py:394-403)
+    fill_cond = torch.randn(1, Li, 64, generator=g).to(BF16)
+    fill_mask = torch.zeros(1, gh, h, gw, res // 16, 256)
+    fill_mask[:, -1, :, -1] = 1.0                                            # target = last cell of the query row
+    cond = torch.cat((fill_cond, fill_mask.reshape(1, Li, 256).to(BF16)), dim=-1)
+    kw = dict(txt=(0.1 * torch.randn(1, Lt, 4096, generator=g)).to(BF16), txt_ids=torch.zeros(1, Lt, 3),
+              txt_mask=torch.ones(1, Lt, dtype=torch.int32), y=torch.randn(1, 768, generator=g).to(BF16),
+              img_ids=img_ids, img_mask=torch.ones(1, Li, dtype=torch.int32), cond=cond,
+              guidance=torch.full((1,), 30.0, dtype=BF16))
+    return x, kw, Li, Lt
+
+
+def flops_per_image(Li, Lt, nfe, H=3072, mlp=12288, heads=24, in_ch=384, out_ch=64, depth=19, depth_single=38):
+    """Algorithmic FLOPs of the launched GEMMs / attention calls (merged LoRA), SURVEY.md 8d."""
+    L = Li + Lt
+    per_eval = 2 * Li * in_ch * H + depth * 24 * L * H * H + depth_single * 24 * L * H * H + 2 * Li * H * out_ch
+    prep = 2 * Lt * 4096 * H + 2 * nfe * H * H * (depth * 12 + depth_single * 3 + 2) + 2 * nfe * (256 * H + H * H) \
+        + 2 * (256 * H + H * H) + 2 * (768 * H + H * H)
+    attn = (depth + depth_single) * 4 * L * L * H
+    return nfe * per_eval + prep, nfe * attn
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU port of the reference (oracle) on a bounded sample
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(workload: str, threads: int):
+    """Times 1 DoubleStreamBlock + 1 SingleStreamBlock of the reference's algorithm (oracle/flux_oracle.py, un-merged LoRA
+    r=256, CUDA-autocast bf16 semantics) at full width on the workload's token count; extrapolates to one image."""
+    from oracle import flux_oracle as fo
+    torch.set_num_threads(threads)
+    gh, gw, res, num_steps, *_ = WORKLOADS[workload]
+    cfg = fo.FluxConfig(depth=1, depth_single_blocks=1, lora_rank=256)
+    H = cfg.hidden_size
+    g = torch.Generator().manual_seed(0)
+    shapes = fo.param_shapes(cfg)
+    p = {}
+    for k, shp in shapes.items():
+        if k.startswith("double_blocks.") or k.startswith("single_blocks."):
+            std = 0.02 if (k.endswith(".bias") or "lora_B" in k) else 1.0 / math.sqrt(shp[-1])
+            p[k] = (torch.randn(shp, generator=g) * std).to(BF16) if not k.endswith(".scale") else torch.ones(shp, dtype=BF16)
+    Li, Lt = gh * gw * (res // 16) ** 2, 512
+    L = Li + Lt
+    img = torch.randn(1, Li, H, generator=g).to(BF16)
+    txt = torch.randn(1, Lt, H, generator=g).to(BF16)
+    vec = torch.randn(1, H, generator=g).to(BF16)
+    ids = torch.zeros(1, L, 3)
+    ids[0, Lt:, 1] = torch.arange(Li) // 72
+    ids[0, Lt:, 2] = torch.arange(Li) % 72
+    cos, sin = fo.rope_table(ids, cfg.axes_dim, cfg.theta)
+    mask = torch.ones(1, L, dtype=torch.int32)
+    nm = fo.Numerics("cuda_bf16")
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        img2, txt2 = fo.double_block(p, 0, cfg, img, txt, vec, cos, sin, mask, nm, 1.0)
+        t1 = time.perf_counter()
+        fo.single_block(p, 0, cfg, torch.cat((txt2, img2), 1), vec, cos, sin, mask, nm, 1.0)
+        t2 = time.perf_counter()
+    nfe = num_steps - 1
+    sec_per_image = nfe * (19 * (t1 - t0) + 38 * (t2 - t1))
+    return 1.0 / sec_per_image, dict(double_block_s=t1 - t0, single_block_s=t2 - t1, tokens=L)
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="B", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    gh, gw, res, num_steps, do_shift, strength, desc = WORKLOADS[args.workload]
+    nfe = num_steps - 1
+    config = {"workload": f"{args.workload}: {desc}", "grid": f"{gh}x{gw}", "resolution": res, "num_steps": num_steps,
+              "nfe": nfe, "batch_per_gpu": 1, "parallelism": f"replicas x{world} (no per-step collective; all_gather of result tiles)",
+              "lora": "merged r=256", "l2": "per-evaluation working set is 24 GB of weights >> 126 MB L2 (no flush needed)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        vals = []
+        for _ in range(max(1, args.warmup)):
+            cpu_reference_sample(args.workload, cores)
+        for _ in range(max(1, args.steps)):
+            v, info = cpu_reference_sample(args.workload, cores)
+            vals.append(v)
+        v = sum(vals) / len(vals)
+        sample = "1 DoubleStreamBlock + 1 SingleStreamBlock of the reference algorithm (CPU oracle port, un-merged LoRA r=256) at " \
+                 f"hidden 3072 on {info['tokens']} tokens, extrapolated x(19,38) blocks x {nfe} evaluations; VAE decode excluded"
+        print(json.dumps({"impl": "reference", "metric": "images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ---------------- our arm ----------------
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a B200: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from visualcloze_b200 import _lib, model as M, transport as T
+    lib = _lib.lib()
+    with torch.device(dev):
+        model = M.FluxLoraWrapper(lora_rank=256, params=M.flux_dev_fill_params())
+    model.init_synthetic(0)
+    model.engine()
+    decoder = None
+    try:
+        from visualcloze_b200 import vae as V
+        decoder = V.AutoEncoderDecoder(device=dev).init_synthetic(0)
+    except ImportError:
+        config["vae_decode"] = "NOT INCLUDED (kernel not built yet): value covers the denoise loop only"
+    sampler = T.Sampler(T.create_transport("Linear", "velocity", do_shift=True))
+    fn = sampler.sample_ode(sampling_method="euler", num_steps=num_steps, atol=1e-6, rtol=1e-3, reverse=False,
+                            do_shift=do_shift, time_shifting_factor=1, strength=strength)
+    x_h, kw_h, Li, Lt = make_inputs(args.workload, 1234 + rank)
+    pin = lambda t: t.pin_memory()
+    x_h, kw_h = pin(x_h), {k: pin(v) for k, v in kw_h.items()}
+    x_d, kw_d = x_h.to(dev), {k: v.to(dev) for k, v in kw_h.items()}
+    row_tokens = Li // gh
+
+    def finish(latent):
+        """query row -> decoded image tile (uint8) -> gathered across replicas"""
+        q = latent[:, Li - row_tokens:, :]
+        if decoder is not None:
+            tile = decoder.decode_packed(q, res // 16, gw * res // 16)
+        else:
+            tile = q
+        if world > 1:
+            out = torch.empty((world,) + tuple(tile.shape), dtype=tile.dtype, device=dev)
+            dist.all_gather_into_tensor(out, tile.contiguous())
+            return out
+        return tile
+
+    def step_resident():
+        return finish(fn(x_d, model.forward, kw_d)[-1])
+
+    def step_e2e():
+        x = x_h.to(dev, non_blocking=True)
+        kw = {k: v.to(dev, non_blocking=True) for k, v in kw_h.items()}
+        return finish(fn(x, model.forward, kw)[-1]).cpu()
+
+    def timed(step, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms)
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local) if rank == 0 else None
+    lib.vcb_reset_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = lib.vcb_launch_count()
+    clk = clocks.stop() if clocks else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    h2d = x_h.numel() * x_h.element_size() + sum(v.numel() * v.element_size() for v in kw_h.values())
+    d2h_t = finish(fn(x_d, model.forward, kw_d)[-1])
+    d2h = d2h_t.numel() * d2h_t.element_size()
+
+    # one instrumented image: CUDA events around every launch, per kernel category
+    import ctypes as C
+    lib.vcb_profile_begin()
+    step_resident()
+    pms, pl = (C.c_double * 4)(), (C.c_longlong * 4)()
+    lib.vcb_profile_end(pms, pl)
+    if rank != 0:
+        return
+    pk = peaks()
+    gemm_fl, attn_fl = flops_per_image(Li, Lt, nfe)
+    value = world * args.steps / (ms / 1000.0)
+    out = {
+        "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": config, "clocks": clk, "gpu_launches": int(launches),
+        "e2e": {"value": world * args.steps / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h)},
+        "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all fused-epilogue GEMMs of one image)", "bound": "tensor",
+                     "achieved": gemm_fl / (pms[0] / 1000.0) / 1e12, "peak": pk["tf"], "unit": "TFLOP/s",
+                     "frac": gemm_fl / (pms[0] / 1000.0) / 1e12 / pk["tf"], "traffic": None, "peak_source": pk["src"] + " sustained",
+                     "launches": int(pl[0]), "avg_launch_ms": pms[0] / max(1, pl[0]), "flops_per_image": gemm_fl},
+        "roofline_attention": {"kernel": "attn_fwd_tcgen05_kernel", "bound": "tensor", "achieved": attn_fl / (pms[1] / 1000.0) / 1e12,
+                               "peak": pk["tf"], "unit": "TFLOP/s", "frac": attn_fl / (pms[1] / 1000.0) / 1e12 / pk["tf"],
+                               "launches": int(pl[1]), "avg_launch_ms": pms[1] / max(1, pl[1])},
+        "roofline_ln_modulate": {"kernel": "ln_modulate_kernel", "bound": "hbm", "unit": "GB/s", "peak": pk["hbm"],
+                                 "launches": int(pl[2]), "avg_launch_ms": pms[2] / max(1, pl[2])},
+        "kernel_time_share": {"gemm_ms": pms[0], "attention_ms": pms[1], "ln_modulate_ms": pms[2], "other_ms": pms[3]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, info = cpu_reference_sample(args.workload, cores)
+        out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                               "sample": "1 double + 1 single block of the reference algorithm (CPU oracle, un-merged LoRA) at hidden "
+                                         f"3072 on {info['tokens']} tokens: {info['double_block_s']:.2f}s + {info['single_block_s']:.2f}s, "
+                                         f"extrapolated x(19,38) blocks x {nfe} evaluations; VAE decode excluded"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

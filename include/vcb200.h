@@ -30,6 +30,11 @@ const char* vcb_last_error(void);
 /* number of kernels this library has launched since load / since the last reset (bench.py gpu_launches) */
 long long   vcb_launch_count(void);
 void        vcb_reset_launch_count(void);
+/* Device time per kernel category, measured with CUDA events around every launch between begin and end
+ * (categories: 0 GEMM, 1 attention, 2 AdaLN LayerNorm, 3 other).  end synchronises the device.
+ * For measurement runs only; not to be used while a CUDA graph is being captured. */
+int         vcb_profile_begin(void);
+int         vcb_profile_end(double ms[4], long long launches[4]);
 
 /* ---- fused-epilogue GEMM:  D = epilogue(A[M,K] * W[N,K]^T)   (bf16 x bf16 -> fp32 -> bf16) --------------
  * Replaces every nn.Linear on the path (models/modules/layers.py:165,172,190-195,235,244; model.py:101,108;

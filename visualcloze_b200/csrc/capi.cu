@@ -67,7 +67,7 @@ int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const
     return set_error("gemm: epilogue %d not available for block_n %d", epi, BN);
 }
 
-int default_cta_group() {
+int forced_cta_group() {
     static int v = [] {
         const char* e = getenv("VCB_GEMM_CTA_GROUP");
         return e ? atoi(e) : 0;
@@ -75,25 +75,30 @@ int default_cta_group() {
     return v;
 }
 
-// pick the N tile that minimises (waves x tile width); ties go to the wider tile
-int pick_block_n(int batch, int rows, int N, int cg, bool head_structured) {
-    const int cands_simple[] = {256, 192, 128};
-    const int cands_head[] = {256, 128};
-    const int* cands = head_structured ? cands_head : cands_simple;
-    const int nc = head_structured ? 2 : 3;
-    const int slots = num_sms() / cg;
-    const int mt = batch * ((rows + kBlockM * cg - 1) / (kBlockM * cg));
-    long best_cost = -1;
-    int best = 256;
-    for (int i = 0; i < nc; ++i) {
-        const int bn = cands[i];
-        const long tiles = (long)mt * ((N + bn - 1) / bn);
+// Tile selection.  Cost of a configuration = (tiles per CTA slot, rounded up) x (tile width) / (measured per-SM
+// rate of that configuration, TFLOP/s on B200 at full waves: profiles/r01_gemm_configs.md).  cta_group 2 pairs two
+// SMs on a 256 x BLOCK_N tile, halving B-operand smem traffic; narrow tiles win when they remove a partial wave.
+struct TileCfg { int cg, bn; float rate; };
+constexpr TileCfg kTileCfgs[] = {{2, 256, 1630.f}, {1, 256, 1445.f}, {1, 192, 1355.f}, {2, 192, 1250.f},
+                                 {1, 128, 970.f},  {2, 128, 950.f}};
+
+void pick_tile(int batch, int rows, int N, bool head_structured, int want_cg, int want_bn, int* cg_out, int* bn_out) {
+    float best_cost = -1.f;
+    int best_cg = 1, best_bn = 256;
+    for (const TileCfg& c : kTileCfgs) {
+        if (want_cg && c.cg != want_cg) continue;
+        if (want_bn && c.bn != want_bn) continue;
+        if (head_structured && c.bn % 128) continue;
+        const int slots = num_sms() / c.cg;
+        const long mt = (long)batch * ((rows + kBlockM * c.cg - 1) / (kBlockM * c.cg));
+        const long tiles = mt * ((N + c.bn - 1) / c.bn);
         const long waves = (tiles + slots - 1) / slots;
-        const long cost = waves * bn;
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+        const float cost = (float)waves * (float)c.bn / c.rate;
+        if (best_cost < 0.f || cost < best_cost) { best_cost = cost; best_cg = c.cg; best_bn = c.bn; }
     }
-    if (N <= 64 && !head_structured && cg == 1) best = 64;
-    return best;
+    if (best_cost < 0.f) { best_cg = want_cg ? want_cg : 1; best_bn = want_bn ? want_bn : 256; }   // e.g. block_n 64
+    *cg_out = best_cg;
+    *bn_out = best_bn;
 }
 
 }  // namespace
@@ -120,10 +125,9 @@ extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
     if (a_bstride % 8) return set_error("gemm: a_batch_stride must be a multiple of 8");
     if (int rc = ensure_device()) return rc;
 
-    int cg = a->cta_group ? a->cta_group : default_cta_group();
-    if (cg == 0) cg = 1;
-    if (cg != 1 && cg != 2) return set_error("gemm: cta_group must be 1 or 2");
-    int bn = a->block_n ? a->block_n : pick_block_n(batch, a->rows_per_batch, a->N, cg, head);
+    if (a->cta_group < 0 || a->cta_group > 2) return set_error("gemm: cta_group must be 0 (auto), 1 or 2");
+    int cg, bn;
+    pick_tile(batch, a->rows_per_batch, a->N, head, a->cta_group ? a->cta_group : forced_cta_group(), a->block_n, &cg, &bn);
 
     GemmParams p{};
     p.N = a->N; p.K = a->K; p.batch = batch;
@@ -136,6 +140,7 @@ extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
     p.rope = (const float2*)a->rope;
     p.out2 = (__nv_bfloat16*)a->out2; p.ldo2 = a->ldo2; p.out2_col_offset = a->out2_col_offset;
 
+    ProfScope prof(PROF_GEMM, stream);
     CUtensorMap ta, tb;
     if (int rc = make_tmap_3d(&ta, a->A, (uint64_t)a->K, (uint64_t)a->rows_per_batch, (uint64_t)batch, (uint64_t)a->lda,
                               (uint64_t)a_bstride, 64, 128)) return rc;
@@ -177,6 +182,7 @@ extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col,
     p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.out_col_offset = out_col_offset;
     p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
     p.scale_log2 = 0.08838834764831845f * 1.4426950408889634f;     // 128^-0.5 * log2(e)
+    ProfScope prof(PROF_ATTN, stream);
     dim3 grid((L + kAttnTile - 1) / kAttnTile, heads, B);
     attn_fwd_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmemBytes, (cudaStream_t)stream>>>(tm, p);
     return check_launch("attention");
@@ -192,6 +198,7 @@ extern "C" int vcb_ln_modulate(const void* x, int64_t ldx, void* y, int64_t ldy,
     if (hidden % 256 || hidden > 256 * kLnMaxChunks) return set_error("ln_modulate: hidden must be a multiple of 256, <= %d", 256 * kLnMaxChunks);
     if (ldx % 8 || ldy % 8 || mod_stride % 8 || rows_per_batch <= 0) return set_error("ln_modulate: strides must be multiples of 8");
     if (int rc = ensure_device()) return rc;
+    ProfScope prof(PROF_LN, stream);
     ln_modulate_kernel<<<(rows + kLnWarps - 1) / kLnWarps, kLnWarps * 32, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const __nv_bfloat16*)shift, (const __nv_bfloat16*)scale,
         mod_stride, rows, hidden, rows_per_batch, batch_rows > 0 ? batch_rows : rows_per_batch);
@@ -201,6 +208,7 @@ extern "C" int vcb_ln_modulate(const void* x, int64_t ldx, void* y, int64_t ldy,
 extern "C" int vcb_timestep_embedding(const float* t_scaled, const float* freqs, void* out, int32_t n, void* stream) {
     if (!t_scaled || !freqs || !out || n <= 0) return set_error("timestep_embedding: bad arguments");
     if (int rc = ensure_device()) return rc;
+    ProfScope prof(PROF_OTHER, stream);
     timestep_embedding_kernel<<<(n * 128 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t_scaled, freqs, (__nv_bfloat16*)out, n);
     return check_launch("timestep_embedding");
 }
@@ -209,6 +217,7 @@ extern "C" int vcb_silu(const void* x, void* y, int64_t n, void* stream) {
     if (!x || !y || n <= 0 || n % 2) return set_error("silu: bad arguments");
     if (int rc = ensure_device()) return rc;
     const long long thr = n / 2;
+    ProfScope prof(PROF_OTHER, stream);
     silu_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n);
     return check_launch("silu");
 }
@@ -219,6 +228,7 @@ extern "C" int vcb_add3(const void* a, const void* b, int32_t b_rows, const void
     if ((b && b_rows <= 0) || (c && c_rows <= 0)) return set_error("add3: bad row counts");
     if (int rc = ensure_device()) return rc;
     const long long n = (long long)rows * hidden;
+    ProfScope prof(PROF_OTHER, stream);
     add3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, b_rows > 0 ? b_rows : 1, (const __nv_bfloat16*)c,
         c_rows > 0 ? c_rows : 1, (__nv_bfloat16*)out, rows, hidden);
@@ -231,6 +241,7 @@ extern "C" int vcb_rope_table(const float* ids, void* out, int32_t rows, int32_t
     if (d0 + d1 + d2 != 128 || d0 % 2 || d1 % 2 || d2 % 2) return set_error("rope_table: axes must be even and sum to 128");
     if (int rc = ensure_device()) return rc;
     const int n = rows * 64;
+    ProfScope prof(PROF_OTHER, stream);
     rope_table_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ids, (float2*)out, rows, d0, d1, d2, theta);
     return check_launch("rope_table");
 }
@@ -240,6 +251,7 @@ extern "C" int vcb_euler_update(const void* x, const void* v, float dt_bf16, voi
     if (!x || !v || !x_new || rows <= 0 || C <= 0) return set_error("euler_update: bad arguments");
     if (int rc = ensure_device()) return rc;
     const long long n = rows * C;
+    ProfScope prof(PROF_OTHER, stream);
     euler_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, (const __nv_bfloat16*)v, dt_bf16, (__nv_bfloat16*)x_new, (__nv_bfloat16*)model_in, ld_in, rows, C);
     return check_launch("euler_update");
@@ -250,6 +262,7 @@ extern "C" int vcb_copy_cols(const void* src, int64_t lds, void* dst, int64_t ld
     if (!src || !dst || rows <= 0 || C <= 0) return set_error("copy_cols: bad arguments");
     if (int rc = ensure_device()) return rc;
     const long long n = rows * C;
+    ProfScope prof(PROF_OTHER, stream);
     copy_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, col0, rows, C);
     return check_launch("copy_cols");
@@ -281,6 +294,30 @@ extern "C" int vcb_debug_umma_probe(const void* a, const void* b, float* out, in
 // ------------------------------------------------------------------------------------------------
 // library
 // ------------------------------------------------------------------------------------------------
+extern "C" int vcb_profile_begin(void) {
+    Profiler& p = profiler();
+    for (auto& r : p.recs) { p.pool.push_back(r.a); p.pool.push_back(r.b); }
+    p.recs.clear();
+    p.on = true;
+    return 0;
+}
+extern "C" int vcb_profile_end(double* ms, long long* launches) {
+    Profiler& p = profiler();
+    p.on = false;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return set_error("profile_end: %s", cudaGetErrorString(e));
+    for (int i = 0; i < PROF_NCAT; ++i) { ms[i] = 0.0; launches[i] = 0; }
+    for (auto& r : p.recs) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms[r.cat] += t;
+        launches[r.cat] += 1;
+        p.pool.push_back(r.a);
+        p.pool.push_back(r.b);
+    }
+    p.recs.clear();
+    return 0;
+}
 extern "C" int vcb_abi_version(void) { return VCB_ABI_VERSION; }
 extern "C" const char* vcb_last_error(void) { return error_buf(); }
 extern "C" long long vcb_launch_count(void) { return launch_counter().load(); }

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
+#include <vector>
 
 namespace vcb {
 
@@ -34,6 +35,40 @@ inline int check_launch(const char* what) {
     count_launch();
     return 0;
 }
+
+// ---- optional per-category device timing (bench.py roofline numbers): CUDA events around every launch ------------
+enum ProfCat : int { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_OTHER = 3, PROF_NCAT = 4 };
+struct ProfRec { int cat; cudaEvent_t a, b; };
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+inline Profiler& profiler() {
+    static Profiler p;
+    return p;
+}
+struct ProfScope {
+    cudaStream_t st;
+    cudaEvent_t b = nullptr;
+    ProfScope(int cat, void* stream) : st((cudaStream_t)stream) {
+        Profiler& p = profiler();
+        if (!p.on) return;
+        cudaEvent_t a = p.get();
+        b = p.get();
+        cudaEventRecord(a, st);
+        p.recs.push_back({cat, a, b});
+    }
+    ~ProfScope() {
+        if (b) cudaEventRecord(b, st);
+    }
+};
 
 struct DeviceInfo {
     int ok = 0;
