@@ -44,8 +44,10 @@ enum vcb_epilogue {
     VCB_EPI_BIAS_GELU = 1, /* out = bf16(gelu_tanh(bf16(acc + bias)))                    layers.py:143,154 */
     VCB_EPI_GATE_RES = 2,  /* out = bf16(res + bf16(gate * bf16(acc + bias)))             layers.py:190-195,245 */
     VCB_EPI_QKV = 3,       /* bias; q,k: RMSNorm(128) * scale then RoPE; v: bias only     layers.py:165-174, math.py:112-117 */
-    VCB_EPI_LINEAR1 = 4    /* cols < 3H as QKV -> out; cols >= 3H as BIAS_GELU -> out2     layers.py:235-244 */
+    VCB_EPI_LINEAR1 = 4,   /* cols < 3H as QKV -> out; cols >= 3H as BIAS_GELU -> out2     layers.py:235-244 */
+    VCB_EPI_BIAS_F32 = 5   /* out is FP32 [.., ldo]: acc + bias (VAE attention scores, autoencoder.py:47) */
 };
+/* VCB_EPI_GATE_RES with gate == NULL is the ungated residual out = bf16(res + bf16(acc + bias)). */
 
 typedef struct vcb_gemm_args {
     int32_t M, N, K;
@@ -74,6 +76,13 @@ typedef struct vcb_gemm_args {
 } vcb_gemm_args;
 
 int vcb_gemm_bf16(const vcb_gemm_args* args, void* stream);
+
+/* ---- 3x3 convolution, stride 1, zero padding 1, NHWC bf16 (models/modules/autoencoder.py:63,65,101,239,258) ------
+ * Implicit GEMM on the tcgen05 kernel without im2col: each k-block is one 4-D TMA box of a 16x8 pixel patch at the
+ * filter tap's shift, zero-filled outside the image.  x [n,H,W,cin], w [cout, 3,3,cin] (tap-major, channels last),
+ * out [n,H,W,cout]; res (optional, same shape as out): out = bf16(res + bf16(conv + bias)).  cin % 64 == 0, cout % 8 == 0. */
+int vcb_conv3x3_nhwc(const void* x, const void* w, const float* bias, const void* res, void* out, int32_t n,
+                     int32_t H, int32_t W, int32_t cin, int32_t cout, void* stream);
 
 /* ---- joint attention (models/math.py:63-99: attention/_upad_input/flash_attn_varlen_func/pad_input) ------
  * qkv: [B, L, ld_qkv] bf16, head h of q/k/v at columns {q,k,v}_col + 128*h, RoPE + QK-norm already applied.
@@ -154,6 +163,43 @@ int vcb_flux_prepare(vcb_flux* f, void* workspace, int64_t workspace_bytes, int3
  * img [B*Li, in_channels] bf16 (latent || cond) -> out [B*Li, out_channels] bf16. */
 int vcb_flux_forward(vcb_flux* f, int32_t eval_idx, const void* img, int64_t ld_img, void* out, int64_t ld_out,
                      void* stream);
+
+/* ---- VAE decoder (models/modules/autoencoder.py:183-259, 307-309; the pipeline's AutoencoderKL.decode, visualcloze.py:430)
+ * NHWC bf16 activations; 3x3 convs as implicit tcgen05 GEMMs, GroupNorm(32)+swish, nearest-2x upsampling and the
+ * single-head mid-block attention as HBM-bound kernels.  Conv weights are [cout, 3, 3, cin_padded] bf16 (tap-major,
+ * channels last, cin padded to a multiple of 64, cout of conv_out padded to 8), 1x1 convs [cout, cin]; biases and
+ * GroupNorm affine parameters fp32. */
+typedef struct vcb_conv_w { const void* w; const float* b; int32_t cin, cout; } vcb_conv_w;
+typedef struct vcb_gn_w { const float* gamma; const float* beta; } vcb_gn_w;
+typedef struct vcb_resblock_w {            /* ResnetBlock, autoencoder.py:55-82 */
+    vcb_gn_w norm1; vcb_conv_w conv1; vcb_gn_w norm2; vcb_conv_w conv2;
+    vcb_conv_w shortcut;                   /* 1x1 nin_shortcut; w == NULL when cin == cout */
+} vcb_resblock_w;
+typedef struct vcb_vae_config {
+    int32_t ch, out_ch, z_channels, num_res_blocks, n_levels;
+    int32_t ch_mult[8];
+    float scale_factor, shift_factor;
+} vcb_vae_config;
+typedef struct vcb_vae_weights {
+    vcb_conv_w conv_in;
+    vcb_resblock_w mid1, mid2;
+    vcb_gn_w attn_norm;
+    vcb_conv_w attn_q, attn_k, attn_v, attn_proj;          /* 1x1 convs == linear layers over channels */
+    const vcb_resblock_w* up_blocks;       /* host array, execution order: level n-1 .. 0, num_res_blocks+1 each */
+    const vcb_conv_w* upsample;            /* host array, execution order: one per level except level 0 */
+    vcb_gn_w norm_out;
+    vcb_conv_w conv_out;
+} vcb_vae_weights;
+typedef struct vcb_vae vcb_vae;
+
+int  vcb_vae_create(const vcb_vae_config* cfg, const vcb_vae_weights* w, vcb_vae** out);
+void vcb_vae_destroy(vcb_vae* v);
+/* workspace for n latents of h x w packed tokens (latent 2h x 2w, image 16h x 16w for the 4-level FLUX VAE) */
+int64_t vcb_vae_workspace_bytes(const vcb_vae* v, int32_t n, int32_t h, int32_t w);
+/* tokens [n, h*w, 4*z_channels] bf16 -> raw [n, out_ch, H, W] fp32 (decoder output, may be NULL) and/or
+ * img [n, out_ch, H, W] uint8 = to_pil(clamp((x + 1) / 2, 0, 1)) (may be NULL) */
+int vcb_vae_decode(vcb_vae* v, void* workspace, int64_t workspace_bytes, const void* tokens, int32_t n, int32_t h,
+                   int32_t w, float* raw, uint8_t* img, void* stream);
 
 /* ---- test hook: one 128x128x(16*ksteps) tcgen05 MMA with caller-chosen descriptor fields -------------------
  * Used by tests/ to pin the smem/TMEM operand layouts the kernels rely on.  a: [128, K] bf16 (K-major),

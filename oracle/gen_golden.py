@@ -180,7 +180,7 @@ def gen_sampler():
 @torch.no_grad()
 def gen_vae():
     from models.modules.autoencoder import AutoEncoder, AutoEncoderParams
-    small = dict(ch=32, out_ch=3, ch_mult=[1, 2, 2], num_res_blocks=1, z_channels=16)
+    small = dict(ch=64, out_ch=3, ch_mult=[1, 2], num_res_blocks=1, z_channels=16)   # level widths multiples of 64
     cfg = vo.VaeConfig(**small)
     ae = AutoEncoder(AutoEncoderParams(resolution=32, in_channels=3, scale_factor=0.3611,
                                        shift_factor=0.1159, **small)).eval()
@@ -190,7 +190,7 @@ def gen_vae():
     assert sorted(dec_keys) == sorted(p), (set(dec_keys) ^ set(p))
     ae.load_state_dict({**sd, **p}, strict=True)
     g = torch.Generator().manual_seed(9)
-    z = torch.randn(1, 16, 6, 10, generator=g)
+    z = torch.randn(1, 16, 12, 20, generator=g)
     out = ae.decode(z)
     torch.save({"cfg": small, "param_seed": 3, "z": z, "out_fp32": out}, os.path.join(OUT, "vae_small.pt"))
     print("vae", out.shape, out.abs().mean().item())

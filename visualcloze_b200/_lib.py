@@ -44,6 +44,8 @@ _SIGNATURES = {
     "vcb_profile_begin": (C.c_int, []),
     "vcb_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "vcb_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "vcb_conv3x3_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vcb_attention_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "vcb_ln_modulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
@@ -94,7 +96,35 @@ class FluxWeightsC(C.Structure):
                 ("dbl", C.POINTER(DoubleW)), ("sgl", C.POINTER(SingleW))]
 
 
+class ConvW(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("cin", C.c_int32), ("cout", C.c_int32)]
+
+
+class GnW(C.Structure):
+    _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p)]
+
+
+class ResblockW(C.Structure):
+    _fields_ = [("norm1", GnW), ("conv1", ConvW), ("norm2", GnW), ("conv2", ConvW), ("shortcut", ConvW)]
+
+
+class VaeConfigC(C.Structure):
+    _fields_ = [("ch", C.c_int32), ("out_ch", C.c_int32), ("z_channels", C.c_int32), ("num_res_blocks", C.c_int32),
+                ("n_levels", C.c_int32), ("ch_mult", C.c_int32 * 8), ("scale_factor", C.c_float), ("shift_factor", C.c_float)]
+
+
+class VaeWeightsC(C.Structure):
+    _fields_ = [("conv_in", ConvW), ("mid1", ResblockW), ("mid2", ResblockW), ("attn_norm", GnW),
+                ("attn_q", ConvW), ("attn_k", ConvW), ("attn_v", ConvW), ("attn_proj", ConvW),
+                ("up_blocks", C.POINTER(ResblockW)), ("upsample", C.POINTER(ConvW)), ("norm_out", GnW), ("conv_out", ConvW)]
+
+
 _OPTIONAL: dict = {
+    "vcb_vae_create": (C.c_int, [C.POINTER(VaeConfigC), C.POINTER(VaeWeightsC), C.POINTER(C.c_void_p)]),
+    "vcb_vae_destroy": (None, [C.c_void_p]),
+    "vcb_vae_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "vcb_vae_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "vcb_flux_create": (C.c_int, [C.POINTER(FluxConfigC), C.POINTER(FluxWeightsC), C.POINTER(C.c_void_p)]),
     "vcb_flux_destroy": (None, [C.c_void_p]),
     "vcb_flux_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

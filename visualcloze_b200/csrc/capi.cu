@@ -58,6 +58,7 @@ int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const
         case EPI_BIAS: return launch_gemm_inst<BN, CG, EPI_BIAS>(ta, tb, p, st);
         case EPI_BIAS_GELU: return launch_gemm_inst<BN, CG, EPI_BIAS_GELU>(ta, tb, p, st);
         case EPI_GATE_RES: return launch_gemm_inst<BN, CG, EPI_GATE_RES>(ta, tb, p, st);
+        case EPI_BIAS_F32: return launch_gemm_inst<BN, CG, EPI_BIAS_F32>(ta, tb, p, st);
         default: break;
     }
     if constexpr (BN % 128 == 0) {
@@ -117,8 +118,9 @@ extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
             return set_error("gemm: LINEAR1 epilogue needs out2");
         if (a->epilogue == VCB_EPI_QKV && a->N != 3 * a->hidden) return set_error("gemm: QKV epilogue needs N == 3*hidden");
     }
-    if (a->epilogue == VCB_EPI_GATE_RES && (!a->gate || !a->res || a->ld_res % 8 || a->gate_stride % 8))
-        return set_error("gemm: GATE_RES epilogue needs gate and res");
+    if (a->epilogue == VCB_EPI_GATE_RES && (!a->res || a->ld_res % 8 || a->gate_stride % 8))
+        return set_error("gemm: GATE_RES epilogue needs res (gate may be NULL = ungated residual)");
+    if (a->epilogue < 0 || a->epilogue > VCB_EPI_BIAS_F32) return set_error("gemm: unknown epilogue %d", a->epilogue);
     if (a->rows_per_batch <= 0 || a->M % a->rows_per_batch) return set_error("gemm: M must be a multiple of rows_per_batch");
     const int batch = a->M / a->rows_per_batch;
     const int64_t a_bstride = a->a_batch_stride ? a->a_batch_stride : (int64_t)a->rows_per_batch * a->lda;
@@ -157,6 +159,55 @@ extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
     VCB_GEMM_CASE(256, 2)
 #undef VCB_GEMM_CASE
     return set_error("gemm: unsupported (block_n=%d, cta_group=%d)", bn, cg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 convolution, NHWC, stride 1, zero padding 1: implicit GEMM on the same tcgen05 kernel (A_CONV3X3)
+// ------------------------------------------------------------------------------------------------
+namespace {
+template <int BN, int EPI>
+int launch_conv_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    using Cfg = GemmCfg<BN, 1>;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, 1, EPI, A_CONV3X3>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    });
+    if (attr_err != cudaSuccess) return set_error("cudaFuncSetAttribute(conv): %s", cudaGetErrorString(attr_err));
+    const int tiles = p.batch * ((p.conv_W + kConvTileW - 1) / kConvTileW) * ((p.conv_H + kConvTileH - 1) / kConvTileH) *
+                      ((p.N + BN - 1) / BN);
+    int grid = num_sms();
+    if (tiles < grid) grid = tiles;
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+    return check_launch("conv3x3");
+}
+}  // namespace
+
+extern "C" int vcb_conv3x3_nhwc(const void* x, const void* w, const float* bias, const void* res, void* out, int32_t n,
+                                int32_t H, int32_t W, int32_t cin, int32_t cout, void* stream) {
+    if (!x || !w || !out || n <= 0 || H <= 0 || W <= 0) return set_error("conv3x3: bad arguments");
+    if (cin % 64 || cout % 8) return set_error("conv3x3: Cin must be a multiple of 64 and Cout of 8 (pad the weights)");
+    if (int rc = ensure_device()) return rc;
+    ProfScope prof(PROF_GEMM, stream);
+    GemmParams p{};
+    p.N = cout; p.K = 9 * cin; p.batch = n;
+    p.rows_per_batch = H * W; p.out_batch_rows = H * W; p.out_row_offset = 0;
+    p.bias = bias; p.out = (__nv_bfloat16*)out; p.ldo = cout;
+    p.res = (const __nv_bfloat16*)res; p.ld_res = cout;
+    p.conv_H = H; p.conv_W = W; p.conv_C = cin;
+    const int bn = cout >= 256 ? 256 : (cout >= 128 ? 128 : 64);
+    CUtensorMap ta, tb;
+    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)cin, (uint64_t)W * cin, (uint64_t)H * W * cin};
+    const uint32_t box[4] = {64, kConvTileW, kConvTileH, 1};
+    if (int rc = make_tmap_4d(&ta, x, dims, str, box)) return rc;
+    if (int rc = make_tmap_2d(&tb, w, (uint64_t)9 * cin, (uint64_t)cout, (uint64_t)9 * cin, 64, (uint32_t)bn)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool r = res != nullptr;
+    if (bn == 256) return r ? launch_conv_inst<256, EPI_GATE_RES>(ta, tb, p, st) : launch_conv_inst<256, EPI_BIAS>(ta, tb, p, st);
+    if (bn == 128) return r ? launch_conv_inst<128, EPI_GATE_RES>(ta, tb, p, st) : launch_conv_inst<128, EPI_BIAS>(ta, tb, p, st);
+    return r ? launch_conv_inst<64, EPI_GATE_RES>(ta, tb, p, st) : launch_conv_inst<64, EPI_BIAS>(ta, tb, p, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -20,7 +20,17 @@ enum GemmEpilogue : int {
     EPI_GATE_RES = 2,   // out = bf16(res + bf16(gate * bf16(acc + bias)))                  layers.py:190-195,245
     EPI_QKV = 3,        // q,k: bias -> QK-RMSNorm -> RoPE ; v: bias                        layers.py:165-174, math.py:112
     EPI_LINEAR1 = 4,    // cols < 3H as EPI_QKV into out ; cols >= 3H as EPI_BIAS_GELU into out2   layers.py:235-244
+    EPI_BIAS_F32 = 5,   // out(fp32) = acc + bias   (VAE mid-block attention scores, autoencoder.py:47)
 };
+// EPI_GATE_RES with gate == nullptr is the plain residual epilogue out = bf16(res + bf16(acc + bias))
+// (ResnetBlock / AttnBlock skip connections, autoencoder.py:52,82).
+
+// A-operand addressing: a [batch, rows, K] matrix, or the 3x3 neighbourhood of an NHWC image (implicit GEMM, no im2col):
+// k-block kb covers filter tap kb / (Cin/64) and channels 64*(kb % (Cin/64)); the tile's 128 rows are a 16 x 8 pixel
+// patch loaded by ONE 4-D TMA box at the tap's (dx, dy) shift -- out-of-image pixels are zero-filled by the TMA unit,
+// which is exactly the conv's zero padding.
+enum GemmAMode : int { A_MATRIX = 0, A_CONV3X3 = 1 };
+constexpr int kConvTileW = 16, kConvTileH = 8;
 
 struct GemmParams {
     int N, K;
@@ -48,6 +58,8 @@ struct GemmParams {
     __nv_bfloat16* out2;         // EPI_LINEAR1: gelu(mlp) destination
     long long ldo2;
     int out2_col_offset;
+    // A_CONV3X3: image height / width / input channels (K == 9 * conv_C); batch = images; rows_per_batch = H * W
+    int conv_H, conv_W, conv_C;
 };
 
 constexpr int kBlockM = 128;
@@ -102,7 +114,7 @@ VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, in
 // ----------------------------------------------------------------------------------------------
 // the kernel
 // ----------------------------------------------------------------------------------------------
-template <int BLOCK_N, int kCtaGroup, int kEpi>
+template <int BLOCK_N, int kCtaGroup, int kEpi, int kAMode = A_MATRIX>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
@@ -145,8 +157,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    static_assert(kAMode == A_MATRIX || kCtaGroup == 1, "conv mode is single-CTA");
     const int tile_m = kBlockM * kCtaGroup;
-    const int m_per_sample = (p.rows_per_batch + tile_m - 1) / tile_m;
+    const int conv_tx = (kAMode == A_CONV3X3) ? (p.conv_W + kConvTileW - 1) / kConvTileW : 1;
+    const int m_per_sample = (kAMode == A_CONV3X3) ? conv_tx * ((p.conv_H + kConvTileH - 1) / kConvTileH)
+                                                   : (p.rows_per_batch + tile_m - 1) / tile_m;
     const int num_m = m_per_sample * p.batch;
     const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = num_m * num_n;
@@ -167,8 +182,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (is_leader) mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes * kCtaGroup);
-                    tma_load_3d<kCtaGroup == 2>(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBlockK,
-                                                m0, bi, kEvictNormal);
+                    if constexpr (kAMode == A_CONV3X3) {
+                        const int cpb = p.conv_C / kBlockK;
+                        const int tap = kb / cpb, cb = kb - tap * cpb;
+                        const int mi = mt % m_per_sample;
+                        const int x0 = (mi % conv_tx) * kConvTileW + (tap % 3) - 1;
+                        const int y0 = (mi / conv_tx) * kConvTileH + (tap / 3) - 1;
+                        tma_load_4d<false>(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, cb * kBlockK, x0, y0, bi,
+                                           kEvictNormal);
+                    } else {
+                        tma_load_3d<kCtaGroup == 2>(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBlockK,
+                                                    m0, bi, kEvictNormal);
+                    }
                     tma_load_2d<kCtaGroup == 2>(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBlockK,
                                                 n0, kEvictNormal);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -217,15 +242,49 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int mt = t % num_m;
             const int b = mt / m_per_sample;
             const int n_tile0 = (t / num_m) * BLOCK_N;
-            const int i = (mt % m_per_sample) * tile_m + (int)cta_rank * kBlockM + row_in_tile;
-            const bool row_ok = i < p.rows_per_batch;
+            int i;
+            bool row_ok;
+            if constexpr (kAMode == A_CONV3X3) {
+                const int mi = mt % m_per_sample;
+                const int px = (mi % conv_tx) * kConvTileW + (row_in_tile % kConvTileW);
+                const int py = (mi / conv_tx) * kConvTileH + (row_in_tile / kConvTileW);
+                row_ok = px < p.conv_W && py < p.conv_H;
+                i = py * p.conv_W + px;
+            } else {
+                i = (mt % m_per_sample) * tile_m + (int)cta_rank * kBlockM + row_in_tile;
+                row_ok = i < p.rows_per_batch;
+            }
             const long long orow = (long long)b * p.out_batch_rows + p.out_row_offset + (row_ok ? i : 0);
 
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * Cfg::kAccStride;
 
-            if constexpr (kEpi == EPI_BIAS || kEpi == EPI_BIAS_GELU || kEpi == EPI_GATE_RES) {
+            if constexpr (kEpi == EPI_BIAS_F32) {
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    const int n0 = n_tile0 + c * 32;
+                    if (n0 >= p.N) break;
+                    uint32_t r[32];
+                    __syncwarp();
+                    tmem_ld_x32(taddr + c * 32, r);
+                    tmem_wait_ld();
+                    if (row_ok) {
+                        float* dst = reinterpret_cast<float*>(p.out) + orow * p.ldo + p.out_col_offset + n0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (n0 + q * 4 < p.N) {
+                                float4 f;
+                                f.x = __uint_as_float(r[q * 4 + 0]) + (p.bias ? __ldg(p.bias + n0 + q * 4 + 0) : 0.f);
+                                f.y = __uint_as_float(r[q * 4 + 1]) + (p.bias ? __ldg(p.bias + n0 + q * 4 + 1) : 0.f);
+                                f.z = __uint_as_float(r[q * 4 + 2]) + (p.bias ? __ldg(p.bias + n0 + q * 4 + 2) : 0.f);
+                                f.w = __uint_as_float(r[q * 4 + 3]) + (p.bias ? __ldg(p.bias + n0 + q * 4 + 3) : 0.f);
+                                *reinterpret_cast<float4*>(dst + q * 4) = f;
+                            }
+                        }
+                    }
+                }
+            } else if constexpr (kEpi == EPI_BIAS || kEpi == EPI_BIAS_GELU || kEpi == EPI_GATE_RES) {
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N / 32; ++c) {
                     const int n0 = n_tile0 + c * 32;
@@ -238,12 +297,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
                     }
                     if constexpr (kEpi == EPI_GATE_RES) {
-                        const __nv_bfloat16* g = p.gate + (long long)b * p.gate_stride + n0;
+                        const __nv_bfloat16* g = p.gate ? p.gate + (long long)b * p.gate_stride + n0 : nullptr;
                         const __nv_bfloat16* rs = p.res + orow * p.ld_res + n0;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             if (n0 + q * 8 < p.N) {
-                                uint4 gu = __ldg(reinterpret_cast<const uint4*>(g + q * 8));
+                                const uint32_t one2 = 0x3F803F80u;          // bf16 (1.0, 1.0)
+                                uint4 gu = g ? __ldg(reinterpret_cast<const uint4*>(g + q * 8)) : make_uint4(one2, one2, one2, one2);
                                 uint4 ru = *reinterpret_cast<const uint4*>(rs + q * 8);
                                 const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
                                 const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
