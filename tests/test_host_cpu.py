@@ -136,3 +136,31 @@ def test_gather_tiles_world2_gloo(tmp_path):
     assert all(p.returncode == 0 for p in procs), outs
     from visualcloze_b200.parallel import gather_tiles, shard_samples
     assert shard_samples(5, 1, 2) == [1, 3] and gather_tiles([torch.zeros(1, 2, 2)], 1)[0].shape == (1, 2, 2)
+
+
+def test_pipeline_host_helpers_match_einops_and_reference_rules():
+    from einops import rearrange
+    from PIL import Image
+    from visualcloze_b200 import pipeline as P
+    m = torch.arange(2 * 32 * 48, dtype=torch.float32).reshape(2, 1, 32, 48)
+    ref = rearrange(rearrange(m, "b c (h ph) (w pw) -> b (c ph pw) h w", ph=8, pw=8), "b c (h ph) (w pw) -> b (h w) (c ph pw)", ph=2, pw=2)
+    assert torch.equal(P._pack_mask(m), ref)
+    lat = torch.arange(16 * 4 * 6, dtype=torch.float32).reshape(1, 16, 4, 6)
+    assert torch.equal(P._patchify(lat), rearrange(lat, "b c (h ph) (w pw) -> b (h w) (c ph pw)", ph=2, pw=2))
+    # area ~ res^2, sides multiples of 16, square stays res x res
+    assert P.resize_with_aspect_ratio(Image.new("RGB", (500, 500)), 384).size == (384, 384)
+    w, h = P.resize_with_aspect_ratio(Image.new("RGB", (800, 400)), 384).size
+    assert w % 16 == 0 and h % 16 == 0 and abs(w * h - 384 * 384) / (384 * 384) < 0.12
+    rgba = Image.new("RGBA", (4, 4), (10, 20, 30, 0))
+    assert P.to_rgb_if_rgba(rgba).getpixel((0, 0)) == (255, 255, 255)
+    t = P.image_transform(Image.new("RGB", (4, 2), (255, 0, 127)))
+    assert t.shape == (3, 2, 4) and float(t[0].max()) == 1.0 and float(t[1].min()) == -1.0
+    pm = object.__new__(P.VisualClozeModel)
+    pm.grid_h, pm.grid_w, pm.resolution = 2, 3, 64
+    imgs = [[Image.new("RGB", (100, 100), (i, j, 0)) for j in range(3)] for i in range(2)]
+    imgs[1][2] = None
+    proc, mask_pos, up = pm._prepare_grid(imgs)
+    assert len(proc) == 6 and mask_pos == [0, 0, 1] and up == (100, 100) and all(p.size == (64, 64) for p in proc)
+    imgs[0][1] = None
+    with pytest.raises(ValueError, match="in-context"):
+        pm._prepare_grid(imgs)
