@@ -68,7 +68,8 @@ typedef struct vcb_gemm_args {
     /* VCB_EPI_QKV / VCB_EPI_LINEAR1 (head_dim is 128) */
     int32_t hidden;
     const void* q_scale; const void* k_scale;   /* [128] bf16 */
-    const void* rope;                            /* [out rows, 64] float2 (cos, sin) */
+    const void* rope;                            /* pair-major [64][rope_rows] float2 (cos, sin); row = mapped output row */
+    int64_t rope_rows;
     void* out2; int64_t ldo2; int32_t out2_col_offset;
     /* tuning: 0 = library heuristic */
     int32_t block_n;                 /* 64 / 128 / 192 / 256 */
@@ -106,7 +107,7 @@ int vcb_silu(const void* x, void* y, int64_t n, void* stream);
 /* out[r] = bf16(bf16(a[r] + b[r % b_rows]) + c[r % c_rows]); b, c may be NULL   (model.py:102-107) */
 int vcb_add3(const void* a, const void* b, int32_t b_rows, const void* c, int32_t c_rows, void* out,
              int32_t rows, int32_t hidden, void* stream);
-/* layers.py:11-25 + math.py:102-109: ids [rows,3] fp32 -> (cos,sin) [rows,64] fp32 pairs */
+/* layers.py:11-25 + math.py:102-109: ids [rows,3] fp32 -> (cos,sin) float2, PAIR-MAJOR [64][rows] */
 int vcb_rope_table(const float* ids, void* out, int32_t rows, int32_t d0, int32_t d1, int32_t d2, double theta,
                    void* stream);
 /* torchdiffeq euler step as used by transport/integrators.py:119 (bf16 state, dt rounded to bf16, v negated);

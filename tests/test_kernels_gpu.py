@@ -154,7 +154,7 @@ def test_gemm_qkv_epilogue(ops, block_n, cta_group):
     qs, ks = (1 + 0.1 * _randn(128, seed=4, dtype=torch.float32)).to(BF16), (1 + 0.1 * _randn(128, seed=5, dtype=torch.float32)).to(BF16)
     ang = _randn(Ltot, 64, seed=6, dtype=torch.float32) * 3
     cos, sin = torch.cos(ang), torch.sin(ang)
-    rope = torch.stack([cos, sin], -1).contiguous()
+    rope = torch.stack([cos, sin], -1).permute(1, 0, 2).contiguous()      # pair-major [64, rows, 2]
     out = torch.zeros(Ltot, 3 * H, dtype=BF16, device="cuda")
     ops.gemm(a.cuda(), w.cuda(), bias.cuda(), out, epilogue=ops.EPI_QKV, hidden=H, q_scale=qs.cuda(), k_scale=ks.cuda(),
              rope=rope.cuda(), rows_per_batch=L, out_batch_rows=Ltot, out_row_offset=row_off, block_n=block_n,
@@ -174,7 +174,7 @@ def test_gemm_linear1_epilogue(ops, cta_group):
     qs, ks = (1 + 0.1 * _randn(128, seed=4, dtype=torch.float32)).to(BF16), (1 + 0.1 * _randn(128, seed=5, dtype=torch.float32)).to(BF16)
     ang = _randn(L, 64, seed=6, dtype=torch.float32) * 3
     cos, sin = torch.cos(ang), torch.sin(ang)
-    rope = torch.stack([cos, sin], -1).contiguous()
+    rope = torch.stack([cos, sin], -1).permute(1, 0, 2).contiguous()
     qkv = torch.zeros(L, 3 * H, dtype=BF16, device="cuda")
     cat = torch.zeros(L, H + mlp, dtype=BF16, device="cuda")
     ops.gemm(a.cuda(), w.cuda(), bias.cuda(), qkv, epilogue=ops.EPI_LINEAR1, hidden=H, q_scale=qs.cuda(), k_scale=ks.cuda(),
@@ -286,10 +286,10 @@ def test_rope_table_and_euler(ops):
     ids[:, 0] = torch.arange(300) % 3 + 1
     ids[:, 1] = torch.arange(300) // 24
     ids[:, 2] = torch.arange(300) % 72
-    out = torch.empty(300, 64, 2, dtype=torch.float32, device="cuda")
+    out = torch.empty(64, 300, 2, dtype=torch.float32, device="cuda")
     ops.rope_table(ids.cuda(), [16, 56, 56], 10000, out)
     cos, sin = fo.rope_table(ids[None], [16, 56, 56], 10000)
-    assert (out[..., 0].cpu() - cos[0]).abs().max() < 1e-6 and (out[..., 1].cpu() - sin[0]).abs().max() < 1e-6
+    assert (out[..., 0].cpu().T - cos[0]).abs().max() < 1e-6 and (out[..., 1].cpu().T - sin[0]).abs().max() < 1e-6
     x, v = _randn(500, 64, seed=1), _randn(500, 64, seed=2)
     dt = torch.tensor(1.0 / 29)                                  # 0-dim fp32 like torchdiffeq's dt
     ref = x + dt * (-v)                                          # torch promotion -> bf16(x + bf16(bf16(dt)*f))

@@ -30,7 +30,7 @@ class GemmArgs(C.Structure):
         ("res", C.c_void_p), ("ld_res", C.c_int64),
         ("hidden", C.c_int32),
         ("q_scale", C.c_void_p), ("k_scale", C.c_void_p),
-        ("rope", C.c_void_p),
+        ("rope", C.c_void_p), ("rope_rows", C.c_int64),
         ("out2", C.c_void_p), ("ldo2", C.c_int64), ("out2_col_offset", C.c_int32),
         ("block_n", C.c_int32), ("cta_group", C.c_int32),
     ]

@@ -8,6 +8,7 @@
 
 #include "../../include/vcb200.h"
 #include "attn_sm100.cuh"
+#include "attn2_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm_sm100.cuh"
 #include "host_util.cuh"
@@ -112,7 +113,7 @@ extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
     if (!a->A || !a->W || !a->out) return set_error("gemm: null operand");
     const bool head = a->epilogue == VCB_EPI_QKV || a->epilogue == VCB_EPI_LINEAR1;
     if (head) {
-        if (a->hidden <= 0 || a->hidden % 128 || !a->q_scale || !a->k_scale || !a->rope)
+        if (a->hidden <= 0 || a->hidden % 128 || !a->q_scale || !a->k_scale || !a->rope || a->rope_rows <= 0)
             return set_error("gemm: QKV epilogue needs hidden %% 128 == 0, q/k scales and the rope table");
         if (a->epilogue == VCB_EPI_LINEAR1 && (!a->out2 || a->ldo2 % 8 || a->out2_col_offset % 8))
             return set_error("gemm: LINEAR1 epilogue needs out2");
@@ -139,7 +140,7 @@ extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
     p.gate = (const __nv_bfloat16*)a->gate; p.gate_stride = a->gate_stride;
     p.res = (const __nv_bfloat16*)a->res; p.ld_res = a->ld_res;
     p.hidden = a->hidden; p.q_scale = (const __nv_bfloat16*)a->q_scale; p.k_scale = (const __nv_bfloat16*)a->k_scale;
-    p.rope = (const float2*)a->rope;
+    p.rope = (const float2*)a->rope; p.rope_rows = a->rope_rows;
     p.out2 = (__nv_bfloat16*)a->out2; p.ldo2 = a->ldo2; p.out2_col_offset = a->out2_col_offset;
 
     ProfScope prof(PROF_GEMM, stream);
@@ -222,8 +223,13 @@ extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col,
     if (int rc = ensure_device()) return rc;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
+    static int use_v1 = 0;
     std::call_once(once, [&] {
         attr_err = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(attn_fwd2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes);
+        const char* e = getenv("VCB_ATTN_V1");
+        use_v1 = e ? atoi(e) : 0;
     });
     if (attr_err != cudaSuccess) return set_error("cudaFuncSetAttribute(attn): %s", cudaGetErrorString(attr_err));
     CUtensorMap tm;
@@ -234,8 +240,13 @@ extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col,
     p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
     p.scale_log2 = 0.08838834764831845f * 1.4426950408889634f;     // 128^-0.5 * log2(e)
     ProfScope prof(PROF_ATTN, stream);
-    dim3 grid((L + kAttnTile - 1) / kAttnTile, heads, B);
-    attn_fwd_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmemBytes, (cudaStream_t)stream>>>(tm, p);
+    if (use_v1) {
+        dim3 grid((L + kAttnTile - 1) / kAttnTile, heads, B);
+        attn_fwd_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmemBytes, (cudaStream_t)stream>>>(tm, p);
+    } else {
+        dim3 grid((L + 2 * kAttnTile - 1) / (2 * kAttnTile), heads, B);
+        attn_fwd2_tcgen05_kernel<<<grid, kAttn2Threads, kAttn2SmemBytes, (cudaStream_t)stream>>>(tm, p);
+    }
     return check_launch("attention");
 }
 

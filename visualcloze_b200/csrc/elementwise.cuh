@@ -122,8 +122,9 @@ __global__ void add3_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bflo
     out[idx] = __float2bfloat16_rn(s);
 }
 
-// RoPE table (layers.py:11-25, math.py:102-109): ids [rows, 3] fp32 -> (cos, sin) [rows, 64], fp64 math like the
-// reference.  axes (16, 56, 56) -> 8 + 28 + 28 frequency pairs.
+// RoPE table (layers.py:11-25, math.py:102-109): ids [rows, 3] fp32 -> (cos, sin), fp64 math like the reference.
+// axes (16, 56, 56) -> 8 + 28 + 28 frequency pairs.  Output is PAIR-MAJOR [64][rows]: the GEMM epilogue's threads own
+// consecutive rows, so a warp reads 32 consecutive float2 per pair (coalesced) instead of 32 strided cache lines.
 __global__ void rope_table_kernel(const float* __restrict__ ids, float2* __restrict__ out, int rows, int d0, int d1,
                                   int d2, double theta) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,7 +139,7 @@ __global__ void rope_table_kernel(const float* __restrict__ ids, float2* __restr
     const double scale = (double)(2 * i) / (double)dim;
     const double omega = 1.0 / pow(theta, scale);
     const double ang = (double)ids[r * 3 + axis] * omega;
-    out[idx] = make_float2((float)cos(ang), (float)sin(ang));
+    out[(long long)(idx % half) * rows + r] = make_float2((float)cos(ang), (float)sin(ang));
 }
 
 // Euler update (torchdiffeq fixed-grid euler via transport/integrators.py:119):

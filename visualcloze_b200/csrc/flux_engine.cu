@@ -6,7 +6,7 @@
 //   xm   [B, L, H]         AdaLN-modulated LayerNorm output (GEMM A operand)
 //   qkv  [B, L, 3H]        q | k | v after bias, QK-RMSNorm and RoPE (GEMM epilogue) -> attention operand
 //   cat  [B, L, H + mlp]   columns [0,H): attention output; [H,H+mlp): GELU(mlp-up)  == linear2 input (layers.py:244)
-//   rope [B, L, 64] float2, txt0 [B, Lt, H] (txt_in output), modulation tables for all evaluations.
+//   rope [64][B*L] float2 (pair-major), txt0 [B, Lt, H] (txt_in output), modulation tables for all evaluations.
 // Step-invariant work is hoisted into vcb_flux_prepare.
 #include <vector>
 
@@ -187,7 +187,7 @@ int stream_gemm(const vcb_flux* f, const StreamView& sv, const uint16_t* a_buf, 
     g.rows_per_batch = sv.rows; g.out_batch_rows = f->L; g.out_row_offset = sv.off;
     g.epilogue = epi;
     g.gate = gate; g.gate_stride = gate_stride; g.res = out; g.ld_res = ldo;
-    g.hidden = f->cfg.hidden; g.q_scale = q_scale; g.k_scale = k_scale; g.rope = f->rope;
+    g.hidden = f->cfg.hidden; g.q_scale = q_scale; g.k_scale = k_scale; g.rope = f->rope; g.rope_rows = (int64_t)f->B * f->L;
     g.out2 = out2; g.ldo2 = ldo2; g.out2_col_offset = out2_col;
     return vcb_gemm_bf16(&g, stream);
 }

@@ -2,10 +2,11 @@
 //
 //   D[M,N] = epilogue( A[M,K] (bf16, K-major) * W[N,K]^T (bf16, K-major), fp32 accumulate in TMEM )
 //
-// One CTA (or CTA pair, cta_group::2) per SM, 192 threads:
+// One CTA (or CTA pair, cta_group::2) per SM, 320 threads:
 //   warp 0      TMA producer      global -> 128B-swizzled smem ring (mbarrier full/empty)
 //   warp 1      MMA issuer        one thread issues tcgen05.mma; accumulators double-buffered in TMEM
-//   warps 2..5  epilogue          tcgen05.ld (thread == accumulator row) -> fused math -> global
+//   warps 2..9  epilogue          tcgen05.ld (thread == accumulator row, two warps per row block, half the columns
+//                                 each) -> fused math -> global
 //
 // Epilogues replace the reference's un-fused elementwise passes and keep the
 // reference's bf16 rounding points under CUDA autocast (models/modules/layers.py:158-245).
@@ -54,7 +55,8 @@ struct GemmParams {
     int hidden;                  // H (3H = end of the qkv columns); head_dim is 128
     const __nv_bfloat16* q_scale;  // [128] RMSNorm scale for q
     const __nv_bfloat16* k_scale;  // [128]
-    const float2* rope;          // [out rows, 64] (cos, sin), indexed by the mapped output row
+    const float2* rope;          // pair-major [64][rope_rows] (cos, sin); row index = the mapped output row
+    long long rope_rows;
     __nv_bfloat16* out2;         // EPI_LINEAR1: gelu(mlp) destination
     long long ldo2;
     int out2_col_offset;
@@ -65,7 +67,7 @@ struct GemmParams {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;       // TMA warp + MMA warp + 8 epilogue warps
 
 template <int BLOCK_N, int kCtaGroup>
 struct GemmCfg {
@@ -104,10 +106,21 @@ VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, in
     __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge after predicated stores
     tmem_ld_x32(taddr, r);
     tmem_wait_ld();
+    if (bias != nullptr && n0 + 32 <= N) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        float b = (bias != nullptr && n0 + j < N) ? __ldg(bias + n0 + j) : 0.0f;
-        v[j] = bf16_round(__uint_as_float(r[j]) + b);   // Linear output is a bf16 tensor in the reference
+        for (int q = 0; q < 8; ++q) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0) + q);
+            v[q * 4 + 0] = bf16_round(__uint_as_float(r[q * 4 + 0]) + b4.x);   // Linear output is a bf16 tensor in the reference
+            v[q * 4 + 1] = bf16_round(__uint_as_float(r[q * 4 + 1]) + b4.y);
+            v[q * 4 + 2] = bf16_round(__uint_as_float(r[q * 4 + 2]) + b4.z);
+            v[q * 4 + 3] = bf16_round(__uint_as_float(r[q * 4 + 3]) + b4.w);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float b = (bias != nullptr && n0 + j < N) ? __ldg(bias + n0 + j) : 0.0f;
+            v[j] = bf16_round(__uint_as_float(r[j]) + b);
+        }
     }
 }
 
@@ -147,7 +160,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 128 * kCtaGroup);
+            mbar_init(&tmem_empty[s], 256 * kCtaGroup);
         }
         fence_barrier_init();
     }
@@ -233,9 +246,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         __syncwarp();
     } else {
-        // ===================== epilogue warps =====================
+        // ===================== epilogue warps (8: two per TMEM lane quarter, each owning half the tile's columns) ============
         const uint32_t quarter = warp & 3;                  // TMEM lane quarter this warp may access
+        const uint32_t half = (warp - 2) >> 2;              // 0: columns [0, BLOCK_N/2), 1: [BLOCK_N/2, BLOCK_N)
         const int row_in_tile = quarter * 32 + lane;
+        constexpr int kHalfN = BLOCK_N / 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
@@ -262,12 +277,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
             if constexpr (kEpi == EPI_BIAS_F32) {
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
-                    const int n0 = n_tile0 + c * 32;
+                for (int c = 0; c < kHalfN / 32; ++c) {
+                    const int cc = half * (kHalfN / 32) + c;
+                    const int n0 = n_tile0 + cc * 32;
                     if (n0 >= p.N) break;
                     uint32_t r[32];
                     __syncwarp();
-                    tmem_ld_x32(taddr + c * 32, r);
+                    tmem_ld_x32(taddr + cc * 32, r);
                     tmem_wait_ld();
                     if (row_ok) {
                         float* dst = reinterpret_cast<float*>(p.out) + orow * p.ldo + p.out_col_offset + n0;
@@ -286,47 +302,48 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
             } else if constexpr (kEpi == EPI_BIAS || kEpi == EPI_BIAS_GELU || kEpi == EPI_GATE_RES) {
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
-                    const int n0 = n_tile0 + c * 32;
+                for (int c = 0; c < kHalfN / 32; ++c) {
+                    const int cc = half * (kHalfN / 32) + c;
+                    const int n0 = n_tile0 + cc * 32;
                     if (n0 >= p.N) break;
                     float v[32];
-                    load_acc_bias(taddr + c * 32, p.bias, n0, p.N, v);
+                    load_acc_bias(taddr + cc * 32, p.bias, n0, p.N, v);
                     if (row_ok) {
-                    if constexpr (kEpi == EPI_BIAS_GELU) {
+                        if constexpr (kEpi == EPI_BIAS_GELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-                    }
-                    if constexpr (kEpi == EPI_GATE_RES) {
-                        const __nv_bfloat16* g = p.gate ? p.gate + (long long)b * p.gate_stride + n0 : nullptr;
-                        const __nv_bfloat16* rs = p.res + orow * p.ld_res + n0;
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+                        }
+                        if constexpr (kEpi == EPI_GATE_RES) {
+                            const __nv_bfloat16* g = p.gate ? p.gate + (long long)b * p.gate_stride + n0 : nullptr;
+                            const __nv_bfloat16* rs = p.res + orow * p.ld_res + n0;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (n0 + q * 8 < p.N) {
-                                const uint32_t one2 = 0x3F803F80u;          // bf16 (1.0, 1.0)
-                                uint4 gu = g ? __ldg(reinterpret_cast<const uint4*>(g + q * 8)) : make_uint4(one2, one2, one2, one2);
-                                uint4 ru = *reinterpret_cast<const uint4*>(rs + q * 8);
-                                const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
-                                const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
+                            for (int q = 0; q < 4; ++q) {
+                                if (n0 + q * 8 < p.N) {
+                                    const uint32_t one2 = 0x3F803F80u;          // bf16 (1.0, 1.0)
+                                    uint4 gu = g ? __ldg(reinterpret_cast<const uint4*>(g + q * 8)) : make_uint4(one2, one2, one2, one2);
+                                    uint4 ru = *reinterpret_cast<const uint4*>(rs + q * 8);
+                                    const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
+                                    const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    float2 gf = unpack_bf16x2(gw[e]);
-                                    float2 rf = unpack_bf16x2(rw[e]);
-                                    float a0 = bf16_round(gf.x * v[q * 8 + 2 * e]);
-                                    float a1 = bf16_round(gf.y * v[q * 8 + 2 * e + 1]);
-                                    v[q * 8 + 2 * e] = rf.x + a0;
-                                    v[q * 8 + 2 * e + 1] = rf.y + a1;
+                                    for (int e = 0; e < 4; ++e) {
+                                        float2 gf = unpack_bf16x2(gw[e]);
+                                        float2 rf = unpack_bf16x2(rw[e]);
+                                        float a0 = bf16_round(gf.x * v[q * 8 + 2 * e]);
+                                        float a1 = bf16_round(gf.y * v[q * 8 + 2 * e + 1]);
+                                        v[q * 8 + 2 * e] = rf.x + a0;
+                                        v[q * 8 + 2 * e + 1] = rf.y + a1;
+                                    }
                                 }
                             }
                         }
-                    }
-                    store_bf16x32(p.out + orow * p.ldo + p.out_col_offset + n0, v, n0, p.N);
+                        store_bf16x32(p.out + orow * p.ldo + p.out_col_offset + n0, v, n0, p.N);
                     }
                 }
             } else {
-                // EPI_QKV / EPI_LINEAR1: the tile is processed in 128-column groups (one head each)
+                // EPI_QKV / EPI_LINEAR1: 128-column groups (one head each); group hg is handled by column-half hg % 2
                 static_assert(kEpi != EPI_QKV && kEpi != EPI_LINEAR1 || BLOCK_N % 128 == 0, "head-structured epilogue");
 #pragma unroll 1
-                for (int hg = 0; hg < BLOCK_N / 128; ++hg) {
+                for (int hg = (int)half; hg < BLOCK_N / 128; hg += 2) {
                     const int ng = n_tile0 + hg * 128;           // first column of this 128-group
                     if (ng >= p.N) break;
                     const uint32_t tg = taddr + hg * 128;
@@ -358,7 +375,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         }
                         const float rrms = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
                         const __nv_bfloat16* sc = region == 0 ? p.q_scale : p.k_scale;
-                        const float2* rp = p.rope + orow * 64;
+                        // rope table is stored pair-major [64][rope_rows]: consecutive lanes (rows) read consecutive float2
+                        const float2* rp = p.rope + orow;
                         // pass 2: normalise, scale, rotate, store
 #pragma unroll 1
                         for (int c = 0; c < 4; ++c) {
@@ -366,18 +384,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             float v[32];
                             load_acc_bias(tg + c * 32, p.bias, n0, p.N, v);
                             if (row_ok) {
+                                uint32_t sw[16];
 #pragma unroll
-                            for (int j = 0; j < 32; j += 2) {
-                                const int d = c * 32 + j;       // dim inside the head
-                                float s0 = __bfloat162float(sc[d]), s1 = __bfloat162float(sc[d + 1]);
-                                float x0 = bf16_round(bf16_round(v[j] * rrms) * s0);
-                                float x1 = bf16_round(bf16_round(v[j + 1] * rrms) * s1);
-                                float2 cs = __ldg(rp + (d >> 1));
-                                // math.py:112-117: two fp32 products, one fp32 add (no contraction)
-                                v[j] = __fadd_rn(__fmul_rn(cs.x, x0), __fmul_rn(-cs.y, x1));
-                                v[j + 1] = __fadd_rn(__fmul_rn(cs.y, x0), __fmul_rn(cs.x, x1));
-                            }
-                            store_bf16x32(p.out + orow * p.ldo + p.out_col_offset + n0, v, n0, p.N);
+                                for (int q = 0; q < 4; ++q) {
+                                    uint4 su = __ldg(reinterpret_cast<const uint4*>(sc + c * 32 + q * 8));
+                                    sw[q * 4 + 0] = su.x; sw[q * 4 + 1] = su.y; sw[q * 4 + 2] = su.z; sw[q * 4 + 3] = su.w;
+                                }
+#pragma unroll
+                                for (int j = 0; j < 32; j += 2) {
+                                    const int pr = (c * 32 + j) >> 1;               // pair index inside the head
+                                    const float2 s2 = unpack_bf16x2(sw[j >> 1]);
+                                    float x0 = bf16_round(bf16_round(v[j] * rrms) * s2.x);
+                                    float x1 = bf16_round(bf16_round(v[j + 1] * rrms) * s2.y);
+                                    float2 cs = __ldg(rp + (long long)pr * p.rope_rows);
+                                    // math.py:112-117: two fp32 products, one fp32 add (no contraction)
+                                    v[j] = __fadd_rn(__fmul_rn(cs.x, x0), __fmul_rn(-cs.y, x1));
+                                    v[j + 1] = __fadd_rn(__fmul_rn(cs.y, x0), __fmul_rn(cs.x, x1));
+                                }
+                                store_bf16x32(p.out + orow * p.ldo + p.out_col_offset + n0, v, n0, p.N);
                             }
                         }
                     }

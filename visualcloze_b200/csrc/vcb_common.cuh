@@ -297,9 +297,10 @@ VCB_DEVICE void named_bar_sync(uint32_t id, uint32_t nthreads) {
 // activations (fp32 in/out)
 VCB_DEVICE float gelu_tanh(float x) {
     // torch GELU(approximate="tanh"): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+    // 0.5 (1 + tanh(u)) == sigmoid(2u): one ex2 + one fast divide instead of tanhf
     const float kBeta = 0.7978845608028654f, kKappa = 0.044715f;
     float inner = kBeta * (x + kKappa * x * x * x);
-    return 0.5f * x * (1.0f + tanhf(inner));
+    return __fdividef(x, 1.0f + __expf(-2.0f * inner));
 }
 VCB_DEVICE float silu(float x) { return x / (1.0f + __expf(-x)); }
 

@@ -59,6 +59,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: torch
         g.res, g.ld_res = res.data_ptr(), res.stride(0)
     g.hidden = hidden
     g.q_scale, g.k_scale, g.rope = _p(q_scale), _p(k_scale), _p(rope)
+    g.rope_rows = 0 if rope is None else rope.shape[1]            # rope is pair-major [64, rows, 2] fp32
     if out2 is not None:
         _req(out2, BF16, "out2")
         g.out2, g.ldo2, g.out2_col_offset = out2.data_ptr(), out2.stride(0), out2_col_offset
@@ -112,7 +113,7 @@ def add3(a, b, c, out) -> torch.Tensor:
 
 
 def rope_table(ids: torch.Tensor, axes_dim, theta: float, out: torch.Tensor) -> torch.Tensor:
-    """ids [rows, 3] fp32 -> out [rows, 64, 2] fp32 (cos, sin)."""
+    """ids [rows, 3] fp32 -> out [64, rows, 2] fp32 (cos, sin), pair-major."""
     _req(ids, torch.float32, "ids"); _req(out, torch.float32, "out")
     check(_lib.lib().vcb_rope_table(ids.data_ptr(), out.data_ptr(), ids.shape[0], axes_dim[0], axes_dim[1], axes_dim[2],
                                     float(theta), _stream()), "vcb_rope_table")
