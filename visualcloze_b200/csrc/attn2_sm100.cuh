@@ -186,7 +186,7 @@ attn_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 m_tile *= sc;                                     // scaled log2 units (scale > 0 commutes with max)
                 const bool grow = (m_tile - m_run) > kRescaleThreshold;
                 const float m_new = grow ? m_tile : m_run;
-                const float alpha = grow ? exp2f(m_run - m_new) : 1.0f;
+                const float alpha = grow ? ex2_approx(m_run - m_new) : 1.0f;
                 if (j > 0 && __any_sync(0xffffffffu, grow)) {
                     mbar_wait(&o_done[t], (uint32_t)(j - 1) & 1u);
                     tc_fence_after();
@@ -202,19 +202,32 @@ attn_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 }
                 l_run *= alpha;
                 m_run = m_new;
-                float l0 = 0.f, l1 = 0.f;
+                float l0, l1;
+                {
+                    const uint64_t sc2 = pack_f32x2(sc, sc), nm2 = pack_f32x2(-m_new, -m_new);
+                    uint64_t acc_a = pack_f32x2(0.f, 0.f), acc_b = acc_a;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t pk[16];
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t pk[16];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = exp2f(fmaf(__uint_as_float(sr[c][i]), sc, -m_new));
-                        const float p1 = exp2f(fmaf(__uint_as_float(sr[c][i + 1]), sc, -m_new));
-                        l0 += p0;
-                        l1 += p1;
-                        pk[i >> 1] = pack_bf16x2(p0, p1);
+                        for (int i = 0; i < 32; i += 2) {
+                            // (s * scale - m) for two columns in one FFMA2, one MUFU.EX2 each, row sum in FADD2
+                            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sc2, nm2);
+                            float p0, p1;
+                            unpack_f32x2(x2, p0, p1);
+                            p0 = ex2_approx(p0);
+                            p1 = ex2_approx(p1);
+                            if ((i >> 1) & 1) acc_b = add_f32x2(acc_b, pack_f32x2(p0, p1));
+                            else acc_a = add_f32x2(acc_a, pack_f32x2(p0, p1));
+                            pk[i >> 1] = pack_bf16x2(p0, p1);
+                        }
+                        tmem_st_x16(s_addr + c * 16, pk);
                     }
-                    tmem_st_x16(s_addr + c * 16, pk);
+                    float a0, a1, b0, b1;
+                    unpack_f32x2(acc_a, a0, a1);
+                    unpack_f32x2(acc_b, b0, b1);
+                    l0 = a0 + b0;
+                    l1 = a1 + b1;
                 }
                 l_run += l0 + l1;
                 tmem_wait_st();

@@ -108,8 +108,14 @@ void pick_tile(int batch, int rows, int N, bool head_structured, int want_cg, in
 extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
     if (!a) return set_error("gemm: null args");
     if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error("gemm: bad shape %d %d %d", a->M, a->N, a->K);
-    if (a->K % 8 || a->lda % 8 || a->ldw % 8 || a->ldo % 8 || a->N % 8 || a->out_col_offset % 8)
-        return set_error("gemm: K, N, leading dims and column offsets must be multiples of 8 (16-byte rows)");
+    if (a->lda % 8 || a->ldw % 8 || a->ldo % 8 || a->out_col_offset % 8)
+        return set_error("gemm: leading dims and column offsets must be multiples of 8 (16-byte rows)");
+    // N need not be a multiple of 8 when the output row has room for the rounded-up width: the extra columns receive the
+    // epilogue of TMA-zero-filled weight rows.  K is arbitrary (the TMA unit zero-fills the k tail of both operands).
+    if (a->N % 8 && (a->epilogue != VCB_EPI_BIAS && a->epilogue != VCB_EPI_BIAS_F32))
+        return set_error("gemm: N must be a multiple of 8 for this epilogue");
+    if (a->N % 8 && a->out_col_offset + (a->N + 7) / 8 * 8 > a->ldo)
+        return set_error("gemm: N %% 8 != 0 needs ldo >= out_col_offset + round_up(N, 8)");
     if (!a->A || !a->W || !a->out) return set_error("gemm: null operand");
     const bool head = a->epilogue == VCB_EPI_QKV || a->epilogue == VCB_EPI_LINEAR1;
     if (head) {

@@ -180,7 +180,6 @@ extern "C" int vcb_vae_decode(vcb_vae* v, void* workspace, int64_t workspace_byt
                 g.M = C; g.N = (int32_t)P; g.K = C;
                 g.A = v->w.attn_v.w; g.lda = C; g.W = hb; g.ldw = C; g.bias = nullptr;
                 g.out = ws.vT; g.ldo = Ppad; g.rows_per_batch = C; g.out_batch_rows = C; g.epilogue = VCB_EPI_BIAS;
-                if (P % 8) return set_error("vae_decode: latent pixel count must be a multiple of 8");
                 if ((rc = vcb_gemm_bf16(&g, stream))) return rc;
             }
             // scores fp32 [P, P] = q k^T

@@ -289,6 +289,29 @@ VCB_DEVICE void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
         : "memory");
 }
 
+// fast math used by the softmax inner loop: single-instruction ex2, packed fp32x2 FMA / ADD (FFMA2 / FADD2 on sm_100)
+VCB_DEVICE float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+VCB_DEVICE uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+VCB_DEVICE void unpack_f32x2(uint64_t r, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r)); }
+VCB_DEVICE uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+VCB_DEVICE uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // named barrier among `nthreads` threads (ids 1..15; 0 is __syncthreads)
 VCB_DEVICE void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
