@@ -267,7 +267,7 @@ extern "C" int vcb_ln_modulate(const void* x, int64_t ldx, void* y, int64_t ldy,
     if (ldx % 8 || ldy % 8 || mod_stride % 8 || rows_per_batch <= 0) return set_error("ln_modulate: strides must be multiples of 8");
     if (int rc = ensure_device()) return rc;
     ProfScope prof(PROF_LN, stream);
-    ln_modulate_kernel<<<(rows + kLnWarps - 1) / kLnWarps, kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+    ln_modulate_kernel<<<(rows + kLnWarps - 1) / kLnWarps, kLnWarps * 32, (size_t)hidden * 4, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const __nv_bfloat16*)shift, (const __nv_bfloat16*)scale,
         mod_stride, rows, hidden, rows_per_batch, batch_rows > 0 ? batch_rows : rows_per_batch);
     return check_launch("ln_modulate");

@@ -11,74 +11,84 @@ namespace vcb {
 // Algorithmic bytes: read + write of [rows, H] bf16 = 4*rows*H bytes.
 // ------------------------------------------------------------------------------------------------
 constexpr int kLnMaxChunks = 16;      // 16 * 256 = up to H = 4096 per row
-constexpr int kLnWarps = 4;
+constexpr int kLnWarps = 8;           // rows per block iteration
 
+// One warp per row, 8 rows per block.  The block's modulation vectors (shift, 1 + scale) are staged once in shared
+// memory as bf16 pairs; a row is read once (16-byte loads, kept packed in registers), statistics are taken in one pass
+// (sum and sum of squares in fp32), and the modulated row is written once.
 __global__ void __launch_bounds__(kLnWarps * 32)
 ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
                    const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
                    long long mod_stride, int rows, int H, int rows_per_batch, int batch_rows) {
-    const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    extern __shared__ uint4 ln_smem[];                 // [2][H / 8] : shift, scale of sample b0
+    const int row0 = blockIdx.x * kLnWarps;
+    const int b0 = row0 / rows_per_batch;
+    const int nvec = H >> 3;
+    for (int i = threadIdx.x; i < 2 * nvec; i += blockDim.x) {
+        const __nv_bfloat16* src = (i < nvec ? shift : scale) + (long long)b0 * mod_stride;
+        ln_smem[i] = __ldg(reinterpret_cast<const uint4*>(src) + (i < nvec ? i : i - nvec));
+    }
+    const int row = row0 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int nchunks = H >> 8;                    // H % 256 == 0
-    const int b = row / rows_per_batch;
+    const bool active = row < rows;
+    const int b = active ? row / rows_per_batch : b0;
     // logical row (b, i) lives at physical row b * batch_rows + i of x and y (a stream inside a joint [B, L, H] buffer)
     const long long prow = (long long)b * batch_rows + (row - b * rows_per_batch);
-    const __nv_bfloat16* xr = x + prow * ldx;
-    float v[kLnMaxChunks][8];
-    float sum = 0.f;
+    uint4 v[kLnMaxChunks];
+    float sum = 0.f, sq = 0.f;
+    if (active) {
+        const __nv_bfloat16* xr = x + prow * ldx;
 #pragma unroll
-    for (int c = 0; c < kLnMaxChunks; ++c) {
-        if (c < nchunks) {
-            uint4 u = *reinterpret_cast<const uint4*>(xr + c * 256 + lane * 8);
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        for (int c = 0; c < kLnMaxChunks; ++c)
+            if (c < nchunks) v[c] = *reinterpret_cast<const uint4*>(xr + c * 256 + lane * 8);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float2 f = unpack_bf16x2(w[e]);
-                v[c][2 * e] = f.x;
-                v[c][2 * e + 1] = f.y;
-                sum += f.x + f.y;
+        for (int c = 0; c < kLnMaxChunks; ++c)
+            if (c < nchunks) {
+                const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float2 f = unpack_bf16x2(w[e]);
+                    sum += f.x + f.y;
+                    sq = fmaf(f.x, f.x, fmaf(f.y, f.y, sq));
+                }
             }
-        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    __syncthreads();                                // modulation vectors staged
+    if (!active) return;
     const float mean = sum / (float)H;
-    float sq = 0.f;
-#pragma unroll
-    for (int c = 0; c < kLnMaxChunks; ++c)
-        if (c < nchunks) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float d = v[c][e] - mean;
-                sq = fmaf(d, d, sq);
-            }
-        }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq / (float)H + 1e-6f);
-    const __nv_bfloat16* sh = shift + (long long)b * mod_stride;
-    const __nv_bfloat16* sc = scale + (long long)b * mod_stride;
+    const float var = fmaxf(sq / (float)H - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + 1e-6f);
+    const bool staged = (b == b0);
+    const uint4* sh_g = reinterpret_cast<const uint4*>(shift + (long long)b * mod_stride);
+    const uint4* sc_g = reinterpret_cast<const uint4*>(scale + (long long)b * mod_stride);
     __nv_bfloat16* yr = y + prow * ldy;
 #pragma unroll
     for (int c = 0; c < kLnMaxChunks; ++c)
         if (c < nchunks) {
-            const int col = c * 256 + lane * 8;
-            uint4 su = __ldg(reinterpret_cast<const uint4*>(sc + col));
-            uint4 hu = __ldg(reinterpret_cast<const uint4*>(sh + col));
+            const int vi = c * 32 + lane;
+            const uint4 hu = staged ? ln_smem[vi] : __ldg(sh_g + vi);
+            const uint4 su = staged ? ln_smem[nvec + vi] : __ldg(sc_g + vi);
+            const uint32_t xw[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
             const uint32_t sw[4] = {su.x, su.y, su.z, su.w};
             const uint32_t hw[4] = {hu.x, hu.y, hu.z, hu.w};
             uint32_t ow[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
+                float2 xf = unpack_bf16x2(xw[e]);
                 float2 s2 = unpack_bf16x2(sw[e]);
                 float2 h2 = unpack_bf16x2(hw[e]);
                 // `1 + scale` is a bf16 op in the reference; the product and sum are fp32 (LayerNorm returns fp32)
                 float a0 = bf16_round(1.0f + s2.x), a1 = bf16_round(1.0f + s2.y);
-                float n0 = (v[c][2 * e] - mean) * rstd, n1 = (v[c][2 * e + 1] - mean) * rstd;
+                float n0 = (xf.x - mean) * rstd, n1 = (xf.y - mean) * rstd;
                 ow[e] = pack_bf16x2(__fadd_rn(__fmul_rn(a0, n0), h2.x), __fadd_rn(__fmul_rn(a1, n1), h2.y));
             }
-            *reinterpret_cast<uint4*>(yr + col) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            *reinterpret_cast<uint4*>(yr + c * 256 + lane * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
 }
 
