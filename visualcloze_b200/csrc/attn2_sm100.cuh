@@ -205,42 +205,18 @@ attn_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 float l0, l1;
                 {
                     const uint64_t sc2 = pack_f32x2(sc, sc), nm2 = pack_f32x2(-m_new, -m_new);
-                    const uint64_t magic2 = pack_f32x2(12582912.f, 12582912.f), nmagic2 = pack_f32x2(-12582912.f, -12582912.f);
-                    const uint64_t neg1_2 = pack_f32x2(-1.f, -1.f);
-                    const uint64_t c0_2 = pack_f32x2(0.99992895f, 0.99992895f), c1_2 = pack_f32x2(0.6932762f, 0.6932762f);
-                    const uint64_t c2_2 = pack_f32x2(0.24260405f, 0.24260405f), c3_2 = pack_f32x2(0.055088684f, 0.055088684f);
                     uint64_t acc_a = pack_f32x2(0.f, 0.f), acc_b = acc_a;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint32_t pk[16];
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
-                            // (s * scale - m) for two columns in one FFMA2
+                            // (s * scale - m) for two columns in one FFMA2, one MUFU.EX2 each, row sum in FADD2
                             const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sc2, nm2);
                             float p0, p1;
-                            if ((i >> 1) & 1) {
-                                // every other pair: 2^x on the FMA pipe instead of the (saturated) MUFU pipe.
-                                // x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (rel. err 8e-5,
-                                // far below the bf16 rounding of P), 2^n by adding n to the exponent field.
-                                float x0, x1;
-                                unpack_f32x2(x2, x0, x1);
-                                const uint64_t xc = pack_f32x2(fmaxf(x0, -127.f), fmaxf(x1, -127.f));
-                                const uint64_t t2 = add_f32x2(xc, magic2);                 // 1.5 * 2^23 + n
-                                const uint64_t n2 = add_f32x2(t2, nmagic2);
-                                const uint64_t f2 = fma_f32x2(n2, neg1_2, xc);
-                                uint64_t q2 = fma_f32x2(c3_2, f2, c2_2);
-                                q2 = fma_f32x2(q2, f2, c1_2);
-                                q2 = fma_f32x2(q2, f2, c0_2);
-                                float t0, t1, q0, q1;
-                                unpack_f32x2(t2, t0, t1);
-                                unpack_f32x2(q2, q0, q1);
-                                p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
-                                p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
-                            } else {
-                                unpack_f32x2(x2, p0, p1);
-                                p0 = ex2_approx(p0);
-                                p1 = ex2_approx(p1);
-                            }
+                            unpack_f32x2(x2, p0, p1);
+                            p0 = ex2_approx(p0);
+                            p1 = ex2_approx(p1);
                             if ((i >> 1) & 1) acc_b = add_f32x2(acc_b, pack_f32x2(p0, p1));
                             else acc_a = add_f32x2(acc_a, pack_f32x2(p0, p1));
                             pk[i >> 1] = pack_bf16x2(p0, p1);
