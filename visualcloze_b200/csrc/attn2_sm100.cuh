@@ -26,9 +26,11 @@ attn_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     const uint32_t warp = warp_id_uniform();
     const uint32_t lane = lane_id();
     const bool tile1 = (q0 + kAttnTile) < seqlen;              // second tile has at least one valid query
+    pdl_launch_dependents();
 
     if (q0 >= seqlen) {
         // both tiles are padding: zero rows (pad_input)
+        pdl_wait();
         if (warp >= 2) {
             const int row = q0 + (int)(warp - 2) * 32 + (int)lane;
             if (row < p.L) {
@@ -66,6 +68,7 @@ attn_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n_kv = (seqlen + kAttnTile - 1) / kAttnTile;
+    pdl_wait();
 
     if (warp == 0) {
         // ===================== TMA producer =====================

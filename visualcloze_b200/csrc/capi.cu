@@ -35,19 +35,7 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     const int tiles = p.batch * ((p.rows_per_batch + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
     int clusters = num_sms() / CG;
     if (tiles < clusters) clusters = tiles;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(clusters * CG);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    cudaError_t e = launch_pdl(kern, dim3(clusters * CG), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, st, CG, ta, tb, p);
     if (e != cudaSuccess) return set_error("gemm launch (BN=%d CG=%d EPI=%d): %s", BN, CG, EPI, cudaGetErrorString(e));
     count_launch();
     return 0;
@@ -186,8 +174,10 @@ int launch_conv_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
                       ((p.N + BN - 1) / BN);
     int grid = num_sms();
     if (tiles < grid) grid = tiles;
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
-    return check_launch("conv3x3");
+    cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, st, 1, ta, tb, p);
+    if (e != cudaSuccess) return set_error("conv3x3 launch: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
 }
 }  // namespace
 
@@ -251,7 +241,10 @@ extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col,
         attn_fwd_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmemBytes, (cudaStream_t)stream>>>(tm, p);
     } else {
         dim3 grid((L + 2 * kAttnTile - 1) / (2 * kAttnTile), heads, B);
-        attn_fwd2_tcgen05_kernel<<<grid, kAttn2Threads, kAttn2SmemBytes, (cudaStream_t)stream>>>(tm, p);
+        cudaError_t e = launch_pdl(attn_fwd2_tcgen05_kernel, grid, dim3(kAttn2Threads), (size_t)kAttn2SmemBytes, (cudaStream_t)stream, 1, tm, p);
+        if (e != cudaSuccess) return set_error("attention launch: %s", cudaGetErrorString(e));
+        count_launch();
+        return 0;
     }
     return check_launch("attention");
 }
@@ -267,10 +260,13 @@ extern "C" int vcb_ln_modulate(const void* x, int64_t ldx, void* y, int64_t ldy,
     if (ldx % 8 || ldy % 8 || mod_stride % 8 || rows_per_batch <= 0) return set_error("ln_modulate: strides must be multiples of 8");
     if (int rc = ensure_device()) return rc;
     ProfScope prof(PROF_LN, stream);
-    ln_modulate_kernel<<<(rows + kLnWarps - 1) / kLnWarps, kLnWarps * 32, (size_t)hidden * 4, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const __nv_bfloat16*)shift, (const __nv_bfloat16*)scale,
-        mod_stride, rows, hidden, rows_per_batch, batch_rows > 0 ? batch_rows : rows_per_batch);
-    return check_launch("ln_modulate");
+    cudaError_t e = launch_pdl(ln_modulate_kernel, dim3((rows + kLnWarps - 1) / kLnWarps), dim3(kLnWarps * 32), (size_t)hidden * 4,
+                               (cudaStream_t)stream, 1, (const __nv_bfloat16*)x, (long long)ldx, (__nv_bfloat16*)y, (long long)ldy,
+                               (const __nv_bfloat16*)shift, (const __nv_bfloat16*)scale, (long long)mod_stride, (int)rows, (int)hidden,
+                               (int)rows_per_batch, (int)(batch_rows > 0 ? batch_rows : rows_per_batch));
+    if (e != cudaSuccess) return set_error("ln_modulate launch: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
 }
 
 extern "C" int vcb_timestep_embedding(const float* t_scaled, const float* freqs, void* out, int32_t n, void* stream) {

@@ -21,6 +21,8 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bflo
                    const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
                    long long mod_stride, int rows, int H, int rows_per_batch, int batch_rows) {
     extern __shared__ uint4 ln_smem[];                 // [2][H / 8] : shift, scale of sample b0
+    pdl_launch_dependents();
+    pdl_wait();
     const int row0 = blockIdx.x * kLnWarps;
     const int b0 = row0 / rows_per_batch;
     const int nvec = H >> 3;

@@ -149,6 +149,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
     const bool is_leader = (cta_rank == 0);
 
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
@@ -169,6 +170,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if constexpr (kCtaGroup == 2) cluster_sync(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                     // everything above overlapped the previous kernel's tail
 
     static_assert(kAMode == A_MATRIX || kCtaGroup == 1, "conv mode is single-CTA");
     const int tile_m = kBlockM * kCtaGroup;

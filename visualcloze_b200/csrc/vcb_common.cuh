@@ -312,6 +312,11 @@ VCB_DEVICE uint64_t add_f32x2(uint64_t a, uint64_t b) {
     return r;
 }
 
+// Programmatic dependent launch: let the next kernel's CTAs start (and run their prologue) while this grid drains;
+// `pdl_wait` blocks until the preceding grid has completed and its writes are visible.
+VCB_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+VCB_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // named barrier among `nthreads` threads (ids 1..15; 0 is __syncthreads)
 VCB_DEVICE void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
