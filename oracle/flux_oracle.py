@@ -181,7 +181,7 @@ def timestep_embedding(t: torch.Tensor, dim: int = 256, max_period: int = 10000,
     """layers.py:28-49.  Result has t's dtype (fp32 timesteps, bf16 guidance)."""
     t = time_factor * t
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=F32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=F32) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     return emb.to(t.dtype) if torch.is_floating_point(t) else emb
@@ -199,7 +199,7 @@ def rope_table(ids: torch.Tensor, axes_dim, theta: int) -> tuple[torch.Tensor, t
     """
     cs, sn = [], []
     for i, d in enumerate(axes_dim):
-        scale = torch.arange(0, d, 2, dtype=torch.float64) / d
+        scale = torch.arange(0, d, 2, dtype=torch.float64, device=ids.device) / d
         omega = 1.0 / (theta ** scale)
         ang = ids[..., i].double()[..., None] * omega
         cs.append(torch.cos(ang).float())
