@@ -9,6 +9,7 @@
 #include "../../include/vcb200.h"
 #include "attn_sm100.cuh"
 #include "attn2_sm100.cuh"
+#include "attn3_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm_sm100.cuh"
 #include "host_util.cuh"
@@ -219,13 +220,17 @@ extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col,
     if (int rc = ensure_device()) return rc;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    static int use_v1 = 0;
+    static int use_v1 = 0, use_v2 = 0;
     std::call_once(once, [&] {
         attr_err = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(attn_fwd2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
         const char* e = getenv("VCB_ATTN_V1");
         use_v1 = e ? atoi(e) : 0;
+        e = getenv("VCB_ATTN_V2");
+        use_v2 = e ? atoi(e) : 0;
     });
     if (attr_err != cudaSuccess) return set_error("cudaFuncSetAttribute(attn): %s", cudaGetErrorString(attr_err));
     CUtensorMap tm;
@@ -241,7 +246,8 @@ extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col,
         attn_fwd_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmemBytes, (cudaStream_t)stream>>>(tm, p);
     } else {
         dim3 grid((L + 2 * kAttnTile - 1) / (2 * kAttnTile), heads, B);
-        cudaError_t e = launch_pdl(attn_fwd2_tcgen05_kernel, grid, dim3(kAttn2Threads), (size_t)kAttn2SmemBytes, (cudaStream_t)stream, 1, tm, p);
+        cudaError_t e = use_v2 ? launch_pdl(attn_fwd2_tcgen05_kernel, grid, dim3(kAttn2Threads), (size_t)kAttn2SmemBytes, (cudaStream_t)stream, 1, tm, p)
+                               : launch_pdl(attn_fwd3_tcgen05_kernel, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p);
         if (e != cudaSuccess) return set_error("attention launch: %s", cudaGetErrorString(e));
         count_launch();
         return 0;
