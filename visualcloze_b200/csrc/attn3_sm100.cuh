@@ -20,7 +20,8 @@
 namespace vcb {
 
 constexpr int kAttn3Threads = 576;          // TMA warp + MMA warp + 2 tiles x 8 softmax warps
-constexpr int kAttn3SmemBytes = (2 + kAttn2Slots) * kSlotBytes + 1024 + 256;   // row-max exchange (4 KB) reuses the alignment slack? no: see xch below
+constexpr int kAttn3Slots = 4;              // K/V ring (one slot less than attn2: room for the exchange buffer)
+constexpr int kAttn3SmemBytes = (2 + kAttn3Slots) * kSlotBytes + 1024 + 256 + 4096;
 
 __global__ void __launch_bounds__(kAttn3Threads, 1)
 attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p) {
@@ -47,24 +48,25 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         return;
     }
 
-    __shared__ float xch[2][2][2][128];             // [parity][tile][column half][row]: row-max / row-sum exchange
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_q = smem;                                  // 2 x 32 KB
     uint8_t* smem_kv = smem + 2 * kSlotBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + kAttn2Slots) * kSlotBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + kAttn3Slots) * kSlotBytes);
     uint64_t* q_full = bars;                       // [1]
     uint64_t* kv_full = bars + 1;                  // [slots]
-    uint64_t* kv_empty = kv_full + kAttn2Slots;    // [slots]
-    uint64_t* s_full = kv_empty + kAttn2Slots;     // [2] per tile
+    uint64_t* kv_empty = kv_full + kAttn3Slots;    // [slots]
+    uint64_t* s_full = kv_empty + kAttn3Slots;     // [2] per tile
     uint64_t* p_full = s_full + 2;                 // [2]
     uint64_t* o_done = p_full + 2;                 // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+    // [parity][tile][column half][row]: row-max / row-sum exchange between the two threads of a row
+    float (*xch)[2][2][128] = reinterpret_cast<float (*)[2][2][128]>(smem + (2 + kAttn3Slots) * kSlotBytes + 256);
 
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_qkv);
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
-        for (int s = 0; s < kAttn2Slots; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < kAttn3Slots; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 256); mbar_init(&o_done[t], 1); }
         fence_barrier_init();
     }
@@ -87,8 +89,8 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                                    q0 + t * kAttnTile, b, kEvictFirst);
             }
             for (int seq = 0; seq < 2 * n_kv; ++seq) {           // K0 V0 K1 V1 ...
-                const int slot = seq % kAttn2Slots;
-                const uint32_t ph = (uint32_t)(seq / kAttn2Slots) & 1u;
+                const int slot = seq % kAttn3Slots;
+                const uint32_t ph = (uint32_t)(seq / kAttn3Slots) & 1u;
                 const int j = seq >> 1;
                 const int col = ((seq & 1) ? p.v_col : p.k_col) + head * 128;
                 mbar_wait(&kv_empty[slot], ph ^ 1);
@@ -104,9 +106,9 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         if (lane == 0) {
             constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
             constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);
-            auto slot_of = [](int seq) { return seq % kAttn2Slots; };
+            auto slot_of = [](int seq) { return seq % kAttn3Slots; };
             auto wait_kv = [&](int seq) {
-                mbar_wait(&kv_full[slot_of(seq)], (uint32_t)(seq / kAttn2Slots) & 1u);
+                mbar_wait(&kv_full[slot_of(seq)], (uint32_t)(seq / kAttn3Slots) & 1u);
                 tc_fence_after();
             };
             auto issue_qk = [&](int t, int j) {                  // S_t = Q_t K_j^T
