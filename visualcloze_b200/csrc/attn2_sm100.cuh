@@ -95,7 +95,8 @@ attn_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The whole warp runs this loop convergently (descriptors stay in uniform registers); one elected lane issues.
+        {
             constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
             constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);
             auto slot_of = [](int seq) { return seq % kAttn2Slots; };
@@ -105,27 +106,36 @@ attn_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
             };
             auto issue_qk = [&](int t, int j) {                  // S_t = Q_t K_j^T
                 const uint32_t qa = smem_u32(smem_q + t * kSlotBytes), ka = smem_u32(smem_kv + slot_of(2 * j) * kSlotBytes);
+                const uint64_t qd = make_smem_desc(qa, 16, 1024, kSwizzle128B), kd = make_smem_desc(ka, 16, 1024, kSwizzle128B);
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const uint32_t off = (ks >> 2) * (kSlotBytes / 2) + (ks & 3) * 32;
-                    umma_ss<1>(tmem_base + t * 128, make_smem_desc(qa + off, 16, 1024, kSwizzle128B),
-                               make_smem_desc(ka + off, 16, 1024, kSwizzle128B), idesc_qk, ks != 0);
+                    for (int ks = 0; ks < 8; ++ks) {
+                        // +32 B per 16-wide k step inside a 64-wide block, +16 KB for the second block (descriptor units of 16 B)
+                        const uint64_t off = (uint64_t)(((ks >> 2) * (kSlotBytes / 2) + (ks & 3) * 32) >> 4);
+                        umma_ss<1>(tmem_base + t * 128, qd + off, kd + off, idesc_qk, ks != 0);
+                    }
+                    umma_commit<1>(&s_full[t]);
                 }
-                umma_commit<1>(&s_full[t]);
+                __syncwarp();
             };
             auto issue_pv = [&](int t, int j) {                  // O_t += P_t V_j
                 const uint32_t va = smem_u32(smem_kv + slot_of(2 * j + 1) * kSlotBytes);
+                const uint64_t vd = make_smem_desc(va, kSlotBytes / 2, 1024, kSwizzle128B);
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + ks * 8,
-                            make_smem_desc(va + ks * 2048, kSlotBytes / 2, 1024, kSwizzle128B), idesc_pv, (j | ks) != 0);
-                umma_commit<1>(&o_done[t]);
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + ks * 8, vd + (uint64_t)(ks * (2048 >> 4)), idesc_pv,
+                                (j | ks) != 0);
+                    umma_commit<1>(&o_done[t]);
+                }
+                __syncwarp();
             };
             mbar_wait(q_full, 0);
             wait_kv(0);
             issue_qk(0, 0);
             if (tile1) issue_qk(1, 0);
-            umma_commit<1>(&kv_empty[slot_of(0)]);
+            if (elect_one()) umma_commit<1>(&kv_empty[slot_of(0)]);
+            __syncwarp();
             for (int j = 0; j < n_kv; ++j) {
                 const bool more = (j + 1) < n_kv;
                 wait_kv(2 * j + 1);                               // V_j
@@ -138,10 +148,12 @@ attn_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                     tc_fence_after();
                     issue_pv(1, j);
                 }
-                umma_commit<1>(&kv_empty[slot_of(2 * j + 1)]);    // V_j free once both PVs have run
+                if (elect_one()) umma_commit<1>(&kv_empty[slot_of(2 * j + 1)]);    // V_j free once both PVs have run
+                __syncwarp();
                 if (more) {
                     if (tile1) issue_qk(1, j + 1);
-                    umma_commit<1>(&kv_empty[slot_of(2 * j + 2)]);   // K_{j+1} free once both QKs have run
+                    if (elect_one()) umma_commit<1>(&kv_empty[slot_of(2 * j + 2)]);   // K_{j+1} free once both QKs have run
+                    __syncwarp();
                 }
             }
         }

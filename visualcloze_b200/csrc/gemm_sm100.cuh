@@ -218,7 +218,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA) =====================
-        if (is_leader && lane == 0) {
+        // The warp runs the loop convergently (descriptors in uniform registers); one elected lane issues tcgen05 ops.
+        if (is_leader) {
             constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCtaGroup, BLOCK_N, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -233,16 +234,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     tc_fence_after();
                     const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes), 16, 1024, kSwizzle128B);
                     const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024, kSwizzle128B);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        // advance 16 bf16 = 32 B inside the 128B swizzle span: +2 in the (addr >> 4) field
-                        umma_ss<kCtaGroup>(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                                           (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            // advance 16 bf16 = 32 B inside the 128B swizzle span: +2 in the (addr >> 4) field
+                            umma_ss<kCtaGroup>(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                                               (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit<kCtaGroup>(&empty_bar[stage]);
+                        if (kb == num_kb - 1) umma_commit<kCtaGroup>(&tmem_full[acc]);
                     }
-                    umma_commit<kCtaGroup>(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit<kCtaGroup>(&tmem_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
