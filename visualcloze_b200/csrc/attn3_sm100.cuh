@@ -233,9 +233,6 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 m_run = m_new;
                 {
                     const uint64_t sc2 = pack_f32x2(sc, sc), nm2 = pack_f32x2(-m_new, -m_new);
-                    const uint64_t magic2 = pack_f32x2(12582912.f, 12582912.f), nmagic2n = pack_f32x2(12582912.f, 12582912.f);
-                    const uint64_t c0_2 = pack_f32x2(0.99992895f, 0.99992895f), c1_2 = pack_f32x2(0.6932762f, 0.6932762f);
-                    const uint64_t c2_2 = pack_f32x2(0.24260405f, 0.24260405f), c3_2 = pack_f32x2(0.055088684f, 0.055088684f);
                     uint64_t acc_a = pack_f32x2(0.f, 0.f), acc_b = acc_a;
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -253,26 +250,8 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                             const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])), sc2, nm2);
                             float p0, p1;
                             unpack_f32x2(x2, p0, p1);
-                            if ((i >> 1) & 1) {
-                                // Every other column pair: 2^x on the FMA pipe.  The two tiles' softmax phases overlap and share the
-                                // SM's 16/clk MUFU (ncu: XU pipe 58 % == 2 x 128 x 128 ex2 per period, tensor pipe 57 %), so MUFU time
-                                // is on the critical path S -> P -> PV -> QK -> S.  x = n + f, n = round(x), |f| <= 0.5;
-                                // 2^f ~ degree-3 minimax polynomial (rel. err 8e-5 << bf16 rounding of P); 2^n via the exponent field.
-                                const uint64_t xc = pack_f32x2(fmaxf(p0, -125.f), fmaxf(p1, -125.f));
-                                const uint64_t t2 = add_f32x2(xc, magic2);                  // 1.5 * 2^23 + n
-                                const uint64_t f2 = add_f32x2(xc, add_f32x2(nmagic2n, t2 ^ 0x8000000080000000ull));   // x - n
-                                uint64_t q2 = fma_f32x2(c3_2, f2, c2_2);
-                                q2 = fma_f32x2(q2, f2, c1_2);
-                                q2 = fma_f32x2(q2, f2, c0_2);
-                                float t0, t1, q0, q1;
-                                unpack_f32x2(t2, t0, t1);
-                                unpack_f32x2(q2, q0, q1);
-                                p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
-                                p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
-                            } else {
-                                p0 = ex2_approx(p0);
-                                p1 = ex2_approx(p1);
-                            }
+                            p0 = ex2_approx(p0);
+                            p1 = ex2_approx(p1);
                             if ((i >> 1) & 1) acc_b = add_f32x2(acc_b, pack_f32x2(p0, p1));
                             else acc_a = add_f32x2(acc_a, pack_f32x2(p0, p1));
                             pk[i >> 1] = pack_bf16x2(p0, p1);
