@@ -67,7 +67,7 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < kAttn3Slots; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 256); mbar_init(&o_done[t], 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 8 /* one arrive per softmax warp */); mbar_init(&o_done[t], 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
@@ -266,7 +266,8 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 }
                 tmem_wait_st();
                 tc_fence_before();
-                mbar_arrive(&p_full[t]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[t]);       // one mbarrier arrive per warp (not per thread)
             }
             // ---- epilogue: total row sum = my half + partner's half ----
             xch[n_kv & 1][t][half][rit] = l_run;

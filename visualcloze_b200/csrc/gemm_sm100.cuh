@@ -161,7 +161,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 256 * kCtaGroup);
+            mbar_init(&tmem_empty[s], 8 * kCtaGroup);     // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -414,8 +414,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
             }
             tc_fence_before();
-            if constexpr (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
-            else mbar_arrive(&tmem_empty[acc]);
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         __syncwarp();
