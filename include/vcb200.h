@@ -81,9 +81,11 @@ int vcb_gemm_bf16(const vcb_gemm_args* args, void* stream);
 /* ---- 3x3 convolution, stride 1, zero padding 1, NHWC bf16 (models/modules/autoencoder.py:63,65,101,239,258) ------
  * Implicit GEMM on the tcgen05 kernel without im2col: each k-block is one 4-D TMA box of a 16x8 pixel patch at the
  * filter tap's shift, zero-filled outside the image.  x [n,H,W,cin], w [cout, 3,3,cin] (tap-major, channels last),
- * out [n,H,W,cout]; res (optional, same shape as out): out = bf16(res + bf16(conv + bias)).  cin % 64 == 0, cout % 8 == 0. */
+ * out [n,H/stride,W/stride,cout]; res (optional, same shape as out): out = bf16(res + bf16(conv + bias)).
+ * stride 1: zero padding 1 all round.  stride 2: the encoder's Downsample (autoencoder.py:85-95): pad right/bottom by 1,
+ * no padding left/top; the TMA map carries elementStrides = 2.  cin % 64 == 0, cout % 8 == 0. */
 int vcb_conv3x3_nhwc(const void* x, const void* w, const float* bias, const void* res, void* out, int32_t n,
-                     int32_t H, int32_t W, int32_t cin, int32_t cout, void* stream);
+                     int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t stride, void* stream);
 
 /* ---- joint attention (models/math.py:63-99: attention/_upad_input/flash_attn_varlen_func/pad_input) ------
  * qkv: [B, L, ld_qkv] bf16, head h of q/k/v at columns {q,k,v}_col + 128*h, RoPE + QK-norm already applied.
@@ -201,6 +203,29 @@ int64_t vcb_vae_workspace_bytes(const vcb_vae* v, int32_t n, int32_t h, int32_t 
  * img [n, out_ch, H, W] uint8 = to_pil(clamp((x + 1) / 2, 0, 1)) (may be NULL) */
 int vcb_vae_decode(vcb_vae* v, void* workspace, int64_t workspace_bytes, const void* tokens, int32_t n, int32_t h,
                    int32_t w, float* raw, uint8_t* img, void* stream);
+
+/* ---- VAE encoder (models/modules/autoencoder.py:109-180, 262-275, 302-305; the pipeline's ae.encode(...).latent_dist.sample(),
+ * visualcloze.py:377-388) -- "next" row (f)-1 of SURVEY.md section 8: same kernels as the decoder, stride-2 convs through
+ * TMA element strides.  Weights as for the decoder (conv_in cin padded to 64). */
+typedef struct vcb_vae_enc_weights {
+    vcb_conv_w conv_in;
+    const vcb_resblock_w* down_blocks;     /* host array, execution order: level 0 .. n-1, num_res_blocks each */
+    const vcb_conv_w* downsample;          /* host array: one stride-2 conv per level except the last */
+    vcb_resblock_w mid1, mid2;
+    vcb_gn_w attn_norm;
+    vcb_conv_w attn_q, attn_k, attn_v, attn_proj;
+    vcb_gn_w norm_out;
+    vcb_conv_w conv_out;                   /* -> 2 * z_channels (mean | logvar) */
+} vcb_vae_enc_weights;
+typedef struct vcb_vae_enc vcb_vae_enc;
+int  vcb_vae_enc_create(const vcb_vae_config* cfg, const vcb_vae_enc_weights* w, vcb_vae_enc** out);
+void vcb_vae_enc_destroy(vcb_vae_enc* e);
+int64_t vcb_vae_enc_workspace_bytes(const vcb_vae_enc* e, int32_t n, int32_t H, int32_t W);
+/* image [n, 3, H, W] fp32 in [-1, 1] (H, W multiples of 16) -> packed condition tokens [n, (H/16)(W/16), 4*z] bf16 =
+ * patchify((sample - shift) * scale), sample = mean + exp(0.5 logvar) * noise (noise [n, z, H/8, W/8] fp32; NULL = mode);
+ * moments (optional): raw encoder output [n, 2z, H/8, W/8] fp32. */
+int vcb_vae_encode(vcb_vae_enc* e, void* workspace, int64_t workspace_bytes, const float* image, int32_t n, int32_t H,
+                   int32_t W, const float* noise, void* tokens, float* moments, void* stream);
 
 /* ---- test hook: one 128x128x(16*ksteps) tcgen05 MMA with caller-chosen descriptor fields -------------------
  * Used by tests/ to pin the smem/TMEM operand layouts the kernels rely on.  a: [128, K] bf16 (K-major),

@@ -192,8 +192,16 @@ def gen_vae():
     g = torch.Generator().manual_seed(9)
     z = torch.randn(1, 16, 12, 20, generator=g)
     out = ae.decode(z)
-    torch.save({"cfg": small, "param_seed": 3, "z": z, "out_fp32": out}, os.path.join(OUT, "vae_small.pt"))
-    print("vae", out.shape, out.abs().mean().item())
+    # encoder: moments of the reference Encoder on a seeded image, same small geometry
+    pe = vo.make_encoder_params(cfg, seed=4, dtype=torch.float32)
+    enc_keys = [k for k in sd if k.startswith("encoder.")]
+    assert sorted(enc_keys) == sorted(pe), (set(enc_keys) ^ set(pe))
+    ae.load_state_dict({**ae.state_dict(), **pe}, strict=True)
+    img = torch.randn(1, 3, 32, 48, generator=g).clamp(-1, 1)
+    mom = ae.encoder(img)
+    torch.save({"cfg": small, "param_seed": 3, "z": z, "out_fp32": out, "enc_param_seed": 4, "img": img, "moments_fp32": mom},
+               os.path.join(OUT, "vae_small.pt"))
+    print("vae", out.shape, out.abs().mean().item(), "moments", mom.shape, mom.abs().mean().item())
 
 
 if __name__ == "__main__":

@@ -96,3 +96,12 @@ def test_vae_decode_matches_reference():
     out = vo.decode(p, cfg, g["z"])
     assert out.shape == g["out_fp32"].shape
     assert rel_l2(out, g["out_fp32"]) < 2e-5
+
+
+def test_vae_encode_moments_match_reference():
+    g = _load("vae_small.pt")
+    cfg = vo.VaeConfig(**g["cfg"])
+    p = vo.make_encoder_params(cfg, seed=g["enc_param_seed"], dtype=torch.float32)
+    mom = vo.encode_moments(p, cfg, g["img"])
+    assert mom.shape == g["moments_fp32"].shape
+    assert rel_l2(mom, g["moments_fp32"]) < 2e-5

@@ -45,7 +45,7 @@ _SIGNATURES = {
     "vcb_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "vcb_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "vcb_conv3x3_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
-                                   C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vcb_attention_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "vcb_ln_modulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
@@ -119,7 +119,19 @@ class VaeWeightsC(C.Structure):
                 ("up_blocks", C.POINTER(ResblockW)), ("upsample", C.POINTER(ConvW)), ("norm_out", GnW), ("conv_out", ConvW)]
 
 
+class VaeEncWeightsC(C.Structure):
+    _fields_ = [("conv_in", ConvW), ("down_blocks", C.POINTER(ResblockW)), ("downsample", C.POINTER(ConvW)),
+                ("mid1", ResblockW), ("mid2", ResblockW), ("attn_norm", GnW),
+                ("attn_q", ConvW), ("attn_k", ConvW), ("attn_v", ConvW), ("attn_proj", ConvW),
+                ("norm_out", GnW), ("conv_out", ConvW)]
+
+
 _OPTIONAL: dict = {
+    "vcb_vae_enc_create": (C.c_int, [C.POINTER(VaeConfigC), C.POINTER(VaeEncWeightsC), C.POINTER(C.c_void_p)]),
+    "vcb_vae_enc_destroy": (None, [C.c_void_p]),
+    "vcb_vae_enc_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "vcb_vae_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vcb_vae_create": (C.c_int, [C.POINTER(VaeConfigC), C.POINTER(VaeWeightsC), C.POINTER(C.c_void_p)]),
     "vcb_vae_destroy": (None, [C.c_void_p]),
     "vcb_vae_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),

@@ -183,23 +183,27 @@ int launch_conv_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
 }  // namespace
 
 extern "C" int vcb_conv3x3_nhwc(const void* x, const void* w, const float* bias, const void* res, void* out, int32_t n,
-                                int32_t H, int32_t W, int32_t cin, int32_t cout, void* stream) {
+                                int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t stride, void* stream) {
     if (!x || !w || !out || n <= 0 || H <= 0 || W <= 0) return set_error("conv3x3: bad arguments");
+    if (stride != 1 && stride != 2) return set_error("conv3x3: stride must be 1 or 2");
+    if (stride == 2 && ((H | W) & 1)) return set_error("conv3x3: stride 2 needs even H and W");
+    const int Ho = H / stride, Wo = W / stride;
     if (cin % 64 || cout % 8) return set_error("conv3x3: Cin must be a multiple of 64 and Cout of 8 (pad the weights)");
     if (int rc = ensure_device()) return rc;
     ProfScope prof(PROF_GEMM, stream);
     GemmParams p{};
     p.N = cout; p.K = 9 * cin; p.batch = n;
-    p.rows_per_batch = H * W; p.out_batch_rows = H * W; p.out_row_offset = 0;
+    p.rows_per_batch = Ho * Wo; p.out_batch_rows = Ho * Wo; p.out_row_offset = 0;
     p.bias = bias; p.out = (__nv_bfloat16*)out; p.ldo = cout;
     p.res = (const __nv_bfloat16*)res; p.ld_res = cout;
-    p.conv_H = H; p.conv_W = W; p.conv_C = cin;
+    p.conv_H = Ho; p.conv_W = Wo; p.conv_C = cin; p.conv_stride = stride;
     const int bn = cout >= 256 ? 256 : (cout >= 128 ? 128 : 64);
     CUtensorMap ta, tb;
     const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)n};
     const uint64_t str[3] = {(uint64_t)cin, (uint64_t)W * cin, (uint64_t)H * W * cin};
-    const uint32_t box[4] = {64, kConvTileW, kConvTileH, 1};
-    if (int rc = make_tmap_4d(&ta, x, dims, str, box)) return rc;
+    const uint32_t box[4] = {64, (uint32_t)(kConvTileW * stride), (uint32_t)(kConvTileH * stride), 1};
+    const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    if (int rc = make_tmap_4d(&ta, x, dims, str, box, estr)) return rc;
     if (int rc = make_tmap_2d(&tb, w, (uint64_t)9 * cin, (uint64_t)cout, (uint64_t)9 * cin, 64, (uint32_t)bn)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const bool r = res != nullptr;

@@ -60,8 +60,10 @@ struct GemmParams {
     __nv_bfloat16* out2;         // EPI_LINEAR1: gelu(mlp) destination
     long long ldo2;
     int out2_col_offset;
-    // A_CONV3X3: image height / width / input channels (K == 9 * conv_C); batch = images; rows_per_batch = H * W
-    int conv_H, conv_W, conv_C;
+    // A_CONV3X3: OUTPUT height / width, input channels (K == 9 * conv_C); batch = images; rows_per_batch = H * W.
+    // conv_stride 1 (pad 1 all round) or 2 (pad right/bottom only, autoencoder.py:91-95): for stride 2 the tensor map carries
+    // elementStrides = 2, so one box still lands as a dense 16 x 8 pixel patch; coordinates are in input pixels.
+    int conv_H, conv_W, conv_C, conv_stride;
 };
 
 constexpr int kBlockM = 128;
@@ -201,8 +203,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         const int cpb = p.conv_C / kBlockK;
                         const int tap = kb / cpb, cb = kb - tap * cpb;
                         const int mi = mt % m_per_sample;
-                        const int x0 = (mi % conv_tx) * kConvTileW + (tap % 3) - 1;
-                        const int y0 = (mi / conv_tx) * kConvTileH + (tap / 3) - 1;
+                        const int pad = p.conv_stride == 1 ? 1 : 0;
+                        const int x0 = (mi % conv_tx) * kConvTileW * p.conv_stride + (tap % 3) - pad;
+                        const int y0 = (mi / conv_tx) * kConvTileH * p.conv_stride + (tap / 3) - pad;
                         tma_load_4d<false>(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, cb * kBlockK, x0, y0, bi,
                                            kEvictNormal);
                     } else {

@@ -150,7 +150,7 @@ inline PFN_encodeTiled encode_fn() {
 
 // bf16 tensor, dims given innermost-first; strides in ELEMENTS for dims 1.. ; 128-byte swizzle; OOB reads give zeros
 inline int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                     const uint32_t* box) {
+                     const uint32_t* box, const uint32_t* elem_strides = nullptr) {
     PFN_encodeTiled fn = encode_fn();
     if (!fn) return set_error("cuTensorMapEncodeTiled entry point not available");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error("TMA base pointer must be 16-byte aligned");
@@ -160,7 +160,7 @@ inline int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
     for (int i = 0; i < rank; ++i) {
         gdims[i] = dims[i];
         gbox[i] = box[i];
-        estr[i] = 1;
+        estr[i] = elem_strides ? elem_strides[i] : 1;
         if (i > 0) {
             gstr[i - 1] = strides_elems[i - 1] * 2;
             if (gstr[i - 1] % 16) return set_error("TMA stride must be a multiple of 16 bytes");
@@ -188,8 +188,8 @@ inline int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_
     return make_tmap(m, base, 3, dims, str, box);
 }
 inline int make_tmap_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_elems[3],
-                        const uint32_t box[4]) {
-    return make_tmap(m, base, 4, dims, strides_elems, box);
+                        const uint32_t box[4], const uint32_t* elem_strides = nullptr) {
+    return make_tmap(m, base, 4, dims, strides_elems, box, elem_strides);
 }
 
 }  // namespace vcb

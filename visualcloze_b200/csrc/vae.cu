@@ -1,4 +1,5 @@
 // vae.cu -- VAE decoder (models/modules/autoencoder.py:183-259) as a sequence of libvcb200 launches, NHWC bf16.
+#include <algorithm>
 #include <vector>
 
 #include "../../include/vcb200.h"
@@ -46,7 +47,14 @@ Ws carve(const vcb_vae_config& c, uint8_t* base, int n, int lh, int lw) {
     int64_t off = 0;
     auto take = [&](int64_t bytes) { uint8_t* p = base ? base + off : nullptr; off += al(bytes); return p; };
     Ws w{};
-    const int64_t act = max_act_elems(c, n, lh, lw) * 2;
+    // largest activation (the encoder mirrors the decoder's resolutions/widths; its 64-channel padded input image is
+    // 16 H W * 64 <= 16 H W * ch elements); mid-block attention needs q,k = 2 P C in one buffer
+    int64_t act_e = max_act_elems(c, n, lh, lw);
+    int64_t full = (int64_t)n * lh * lw;
+    for (int i = 1; i < c.n_levels; ++i) full *= 4;
+    act_e = std::max<int64_t>(act_e, full * std::max(64, c.ch));
+    act_e = std::max<int64_t>(act_e, 2 * (int64_t)lh * lw * c.ch * c.ch_mult[c.n_levels - 1]);
+    const int64_t act = act_e * 2;
     w.a = (uint16_t*)take(act); w.b = (uint16_t*)take(act); w.c = (uint16_t*)take(act); w.d = (uint16_t*)take(act);
     // GroupNorm partials: the largest pixel count is the final resolution
     int64_t maxP = (int64_t)lh * lw;
@@ -82,7 +90,7 @@ int group_norm(const Ws& ws, const uint16_t* x, uint16_t* y, const vcb_gn_w& g, 
 }
 
 int conv3(const uint16_t* x, const vcb_conv_w& cw, const uint16_t* res, uint16_t* out, int n, int H, int W, void* st) {
-    return vcb_conv3x3_nhwc(x, cw.w, cw.b, res, out, n, H, W, cw.cin, cw.cout, st);
+    return vcb_conv3x3_nhwc(x, cw.w, cw.b, res, out, n, H, W, cw.cin, cw.cout, 1, st);
 }
 
 // 1x1 conv == GEMM over pixels; optional residual
@@ -111,6 +119,56 @@ int resblock(const Ws& ws, const vcb_resblock_w& rb, uint16_t* x, uint16_t* t1, 
         skip = t2;
     }
     return conv3(t1, rb.conv2, skip, out, n, H, W, st);
+}
+
+// AttnBlock (autoencoder.py:25-52): x + proj_out(softmax(q k^T / sqrt(C)) v), single head over the P = H*W pixels.
+int mid_attention(const Ws& ws, const vcb_gn_w& norm, const vcb_conv_w& wq, const vcb_conv_w& wk, const vcb_conv_w& wv,
+                  const vcb_conv_w& wproj, const uint16_t* x, uint16_t* t1, uint16_t* t2, uint16_t* y, int n, int H, int W,
+                  void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    const int C = wq.cin;
+    const int64_t P = (int64_t)H * W, Ppad = (P + 7) / 8 * 8;
+    const float scale = 1.0f / sqrtf((float)C);
+    for (int b = 0; b < n; ++b) {               // attention is per image
+        const uint16_t* xb = x + (int64_t)b * P * C;
+        uint16_t* hb = t1;                       // normed input [P, C]
+        if ((rc = group_norm(ws, xb, hb, norm, 1, P, C, false, st))) return rc;
+        uint16_t* q = t2;                        // [P, C]
+        uint16_t* k = t2 + P * C;                // [P, C]  (activation buffers hold >= 2*P*C elements, see carve)
+        if ((rc = conv1(hb, wq, nullptr, q, P, stream))) return rc;
+        if ((rc = conv1(hb, wk, nullptr, k, P, stream))) return rc;
+        // vT [C, P] = Wv [C, C] x h^T  (bias of v folded into the PV epilogue: softmax rows sum to 1)
+        {
+            vcb_gemm_args g{};
+            g.M = C; g.N = (int32_t)P; g.K = C;
+            g.A = wv.w; g.lda = C; g.W = hb; g.ldw = C; g.bias = nullptr;
+            g.out = ws.vT; g.ldo = Ppad; g.rows_per_batch = C; g.out_batch_rows = C; g.epilogue = VCB_EPI_BIAS;
+            if ((rc = vcb_gemm_bf16(&g, stream))) return rc;
+        }
+        {   // scores fp32 [P, P] = q k^T
+            vcb_gemm_args g{};
+            g.M = (int32_t)P; g.N = (int32_t)P; g.K = C;
+            g.A = q; g.lda = C; g.W = k; g.ldw = C; g.bias = nullptr;
+            g.out = ws.scores; g.ldo = Ppad; g.rows_per_batch = (int32_t)P; g.out_batch_rows = (int32_t)P;
+            g.epilogue = VCB_EPI_BIAS_F32;
+            if ((rc = vcb_gemm_bf16(&g, stream))) return rc;
+        }
+        {
+            ProfScope ps(PROF_OTHER, stream);
+            softmax_rows_kernel<<<(unsigned)P, 256, 0, st>>>(ws.scores, (__nv_bfloat16*)ws.probs, (int)P, Ppad, Ppad, scale);
+            if ((rc = check_launch("softmax_rows"))) return rc;
+        }
+        {   // o [P, C] = probs [P, P] x vT^T + b_v
+            vcb_gemm_args g{};
+            g.M = (int32_t)P; g.N = C; g.K = (int32_t)P;
+            g.A = ws.probs; g.lda = Ppad; g.W = ws.vT; g.ldw = Ppad; g.bias = wv.b;
+            g.out = q; g.ldo = C; g.rows_per_batch = (int32_t)P; g.out_batch_rows = (int32_t)P; g.epilogue = VCB_EPI_BIAS;
+            if ((rc = vcb_gemm_bf16(&g, stream))) return rc;
+        }
+        if ((rc = conv1(q, wproj, xb, y + (int64_t)b * P * C, P, stream))) return rc;   // x + proj_out(o)
+    }
+    return 0;
 }
 
 }  // namespace
@@ -162,53 +220,8 @@ extern "C" int vcb_vae_decode(vcb_vae* v, void* workspace, int64_t workspace_byt
     // ---- middle: ResnetBlock, AttnBlock, ResnetBlock (autoencoder.py:242-244) ----
     if ((rc = resblock(ws, v->w.mid1, x, t1, t2, y, n, H, W, st))) return rc;
     std::swap(x, y);
-    {
-        const int C = v->w.attn_q.cin;
-        const int64_t P = (int64_t)H * W, Ppad = (P + 7) / 8 * 8;
-        const float scale = 1.0f / sqrtf((float)C);
-        for (int b = 0; b < n; ++b) {               // attention is per image
-            const uint16_t* xb = x + (int64_t)b * P * C;
-            uint16_t* hb = t1;                       // normed input [P, C]
-            if ((rc = group_norm(ws, xb, hb, v->w.attn_norm, 1, P, C, false, st))) return rc;
-            uint16_t* q = t2;                        // [P, C]
-            uint16_t* k = t2 + P * C;                // [P, C]  (t2 holds >= 2*P*C elements: activations are >= 4x larger upstream)
-            if ((rc = conv1(hb, v->w.attn_q, nullptr, q, P, stream))) return rc;
-            if ((rc = conv1(hb, v->w.attn_k, nullptr, k, P, stream))) return rc;
-            // vT [C, P] = Wv [C, C] x h^T  (bias of v folded into the PV epilogue: softmax rows sum to 1)
-            {
-                vcb_gemm_args g{};
-                g.M = C; g.N = (int32_t)P; g.K = C;
-                g.A = v->w.attn_v.w; g.lda = C; g.W = hb; g.ldw = C; g.bias = nullptr;
-                g.out = ws.vT; g.ldo = Ppad; g.rows_per_batch = C; g.out_batch_rows = C; g.epilogue = VCB_EPI_BIAS;
-                if ((rc = vcb_gemm_bf16(&g, stream))) return rc;
-            }
-            // scores fp32 [P, P] = q k^T
-            {
-                vcb_gemm_args g{};
-                g.M = (int32_t)P; g.N = (int32_t)P; g.K = C;
-                g.A = q; g.lda = C; g.W = k; g.ldw = C; g.bias = nullptr;
-                g.out = ws.scores; g.ldo = Ppad; g.rows_per_batch = (int32_t)P; g.out_batch_rows = (int32_t)P;
-                g.epilogue = VCB_EPI_BIAS_F32;
-                if ((rc = vcb_gemm_bf16(&g, stream))) return rc;
-            }
-            {
-                ProfScope ps(PROF_OTHER, stream);
-                softmax_rows_kernel<<<(unsigned)P, 256, 0, st>>>(ws.scores, (__nv_bfloat16*)ws.probs, (int)P, Ppad, Ppad, scale);
-                if ((rc = check_launch("softmax_rows"))) return rc;
-            }
-            // o [P, C] = probs [P, P] x vT^T + b_v
-            {
-                vcb_gemm_args g{};
-                g.M = (int32_t)P; g.N = C; g.K = (int32_t)P;
-                g.A = ws.probs; g.lda = Ppad; g.W = ws.vT; g.ldw = Ppad; g.bias = v->w.attn_v.b;
-                g.out = q; g.ldo = C; g.rows_per_batch = (int32_t)P; g.out_batch_rows = (int32_t)P; g.epilogue = VCB_EPI_BIAS;
-                if ((rc = vcb_gemm_bf16(&g, stream))) return rc;
-            }
-            // x + proj_out(o)
-            if ((rc = conv1(q, v->w.attn_proj, xb, y + (int64_t)b * P * C, P, stream))) return rc;
-        }
-        std::swap(x, y);
-    }
+    if ((rc = mid_attention(ws, v->w.attn_norm, v->w.attn_q, v->w.attn_k, v->w.attn_v, v->w.attn_proj, x, t1, t2, y, n, H, W, stream))) return rc;
+    std::swap(x, y);
     if ((rc = resblock(ws, v->w.mid2, x, t1, t2, y, n, H, W, st))) return rc;
     std::swap(x, y);
     // ---- upsampling path (autoencoder.py:247-253) ----
@@ -241,6 +254,92 @@ extern "C" int vcb_vae_decode(vcb_vae* v, void* workspace, int64_t workspace_byt
         nhwc_to_image_kernel<<<dim3((unsigned)((per + 255) / 256), n), 256, 0, st>>>((const __nv_bfloat16*)y, raw, img, H, W,
                                                                                      v->w.conv_out.cout, c.out_ch);
         if ((rc = check_launch("nhwc_to_image"))) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder (autoencoder.py:109-180): conv_in -> [ResnetBlock x R, Downsample]* -> mid -> GN+swish -> conv_out (moments)
+// ------------------------------------------------------------------------------------------------
+struct vcb_vae_enc {
+    vcb_vae_config cfg;
+    vcb_vae_enc_weights w;
+    std::vector<vcb_resblock_w> down;
+    std::vector<vcb_conv_w> dsc;
+};
+
+extern "C" int vcb_vae_enc_create(const vcb_vae_config* cfg, const vcb_vae_enc_weights* w, vcb_vae_enc** out) {
+    if (!cfg || !w || !out) return set_error("vae_enc_create: null argument");
+    if (cfg->n_levels < 1 || cfg->n_levels > 8 || cfg->num_res_blocks < 1) return set_error("vae_enc_create: bad config");
+    for (int i = 0; i < cfg->n_levels; ++i)
+        if ((cfg->ch * cfg->ch_mult[i]) % 64) return set_error("vae_enc_create: every level width must be a multiple of 64");
+    if (cfg->ch % 64 || (2 * cfg->z_channels) % 8) return set_error("vae_enc_create: ch %% 64 and 2 z %% 8 required");
+    vcb_vae_enc* e = new vcb_vae_enc();
+    e->cfg = *cfg;
+    e->w = *w;
+    e->down.assign(w->down_blocks, w->down_blocks + cfg->n_levels * cfg->num_res_blocks);
+    if (cfg->n_levels > 1) e->dsc.assign(w->downsample, w->downsample + cfg->n_levels - 1);
+    e->w.down_blocks = e->down.data();
+    e->w.downsample = e->dsc.data();
+    *out = e;
+    return 0;
+}
+extern "C" void vcb_vae_enc_destroy(vcb_vae_enc* e) { delete e; }
+
+extern "C" int64_t vcb_vae_enc_workspace_bytes(const vcb_vae_enc* e, int32_t n, int32_t H, int32_t W) {
+    if (!e || n <= 0 || H <= 0 || W <= 0) return -1;
+    const int f = 1 << (e->cfg.n_levels - 1);
+    if (H % (2 * f) || W % (2 * f)) return -1;
+    return carve(e->cfg, nullptr, n, H / f, W / f).total;
+}
+
+extern "C" int vcb_vae_encode(vcb_vae_enc* e, void* workspace, int64_t workspace_bytes, const float* image, int32_t n, int32_t H,
+                              int32_t W, const float* noise, void* tokens, float* moments, void* stream) {
+    if (!e || !workspace || !image || !tokens || n <= 0) return set_error("vae_encode: bad arguments");
+    const vcb_vae_config& c = e->cfg;
+    const int f = 1 << (c.n_levels - 1);
+    if (H <= 0 || W <= 0 || H % (2 * f) || W % (2 * f)) return set_error("vae_encode: H and W must be multiples of %d", 2 * f);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return set_error("vae_encode: workspace must be 256-byte aligned");
+    if (int rc = ensure_device()) return rc;
+    const Ws ws = carve(c, static_cast<uint8_t*>(workspace), n, H / f, W / f);
+    if (workspace_bytes < ws.total) return set_error("vae_encode: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)ws.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    {
+        ProfScope ps(PROF_OTHER, stream);
+        const int64_t per = (int64_t)H * W * 64;
+        image_to_nhwc_kernel<<<dim3((unsigned)((per + 255) / 256), n), 256, 0, st>>>(image, (__nv_bfloat16*)ws.a, H, W, 3, 64);
+        if ((rc = check_launch("image_to_nhwc"))) return rc;
+    }
+    uint16_t *x = ws.b, *t1 = ws.c, *t2 = ws.d, *y = ws.a;
+    if ((rc = conv3(ws.a, e->w.conv_in, nullptr, x, n, H, W, stream))) return rc;
+    int h = H, w = W, bi = 0;
+    for (int lvl = 0; lvl < c.n_levels; ++lvl) {
+        for (int r = 0; r < c.num_res_blocks; ++r) {
+            if ((rc = resblock(ws, e->down[bi++], x, t1, t2, y, n, h, w, st))) return rc;
+            std::swap(x, y);
+        }
+        if (lvl != c.n_levels - 1) {
+            const vcb_conv_w& dw = e->dsc[lvl];
+            if ((rc = vcb_conv3x3_nhwc(x, dw.w, dw.b, nullptr, y, n, h, w, dw.cin, dw.cout, 2, stream))) return rc;
+            std::swap(x, y);
+            h /= 2; w /= 2;
+        }
+    }
+    if ((rc = resblock(ws, e->w.mid1, x, t1, t2, y, n, h, w, st))) return rc;
+    std::swap(x, y);
+    if ((rc = mid_attention(ws, e->w.attn_norm, e->w.attn_q, e->w.attn_k, e->w.attn_v, e->w.attn_proj, x, t1, t2, y, n, h, w, stream))) return rc;
+    std::swap(x, y);
+    if ((rc = resblock(ws, e->w.mid2, x, t1, t2, y, n, h, w, st))) return rc;
+    std::swap(x, y);
+    if ((rc = group_norm(ws, x, t1, e->w.norm_out, n, (int64_t)h * w, e->w.conv_out.cin, true, st))) return rc;
+    if ((rc = conv3(t1, e->w.conv_out, nullptr, y, n, h, w, stream))) return rc;
+    {
+        ProfScope ps(PROF_OTHER, stream);
+        const int64_t per = (int64_t)h * w * c.z_channels;
+        moments_to_tokens_kernel<<<dim3((unsigned)((per + 255) / 256), n), 256, 0, st>>>((const __nv_bfloat16*)y, noise, (__nv_bfloat16*)tokens,
+                                                                                         moments, h, w, c.z_channels, c.scale_factor, c.shift_factor);
+        if ((rc = check_launch("moments_to_tokens"))) return rc;
     }
     return 0;
 }

@@ -191,4 +191,49 @@ __global__ void nhwc_to_image_kernel(const __nv_bfloat16* __restrict__ in, float
     }
 }
 
+// image [n, cin, H, W] fp32 (NCHW, values in [-1, 1]) -> NHWC bf16 [n, H, W, cpad], channels >= cin zero (encoder input)
+__global__ void image_to_nhwc_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int H, int W, int cin, int cpad) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over H * W * cpad
+    const int n = blockIdx.y;
+    const long long per = (long long)H * W * cpad;
+    if (idx >= per) return;
+    const int c = (int)(idx % cpad);
+    const long long pix = idx / cpad;
+    float v = 0.f;
+    if (c < cin) v = img[((long long)n * cin + c) * H * W + pix];
+    out[(long long)n * per + idx] = __float2bfloat16_rn(v);
+}
+
+// encoder output moments NHWC [n, h2, w2, 2*zc] bf16 (mean | logvar) -> latent sample mean + exp(0.5 logvar) * noise
+// (DiagonalGaussian, autoencoder.py:262-275; bf16 steps) -> (z - shift) * scale (visualcloze.py:378) -> packed tokens
+// [n, (h2/2)(w2/2), 4*zc] ("c (h 2)(w 2) -> (h w)(c 2 2)", visualcloze.py:385).  noise [n, zc, h2, w2] fp32 or NULL (mode).
+// Optionally also writes the raw moments as fp32 NCHW [n, 2*zc, h2, w2].
+__global__ void moments_to_tokens_kernel(const __nv_bfloat16* __restrict__ mom, const float* __restrict__ noise,
+                                         __nv_bfloat16* __restrict__ tok, float* __restrict__ raw, int h2, int w2, int zc,
+                                         float scale_factor, float shift_factor) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over h2 * w2 * zc
+    const int n = blockIdx.y;
+    const long long per = (long long)h2 * w2 * zc;
+    if (idx >= per) return;
+    const int c = (int)(idx % zc);
+    const long long pix = idx / zc;
+    const int x = (int)(pix % w2), y = (int)(pix / w2);
+    const __nv_bfloat16* m = mom + ((long long)n * h2 * w2 + pix) * (2 * zc);
+    const float mean = __bfloat162float(m[c]), logvar = __bfloat162float(m[zc + c]);
+    if (raw) {
+        raw[(((long long)n * 2 * zc + c) * h2 + y) * w2 + x] = mean;
+        raw[(((long long)n * 2 * zc + zc + c) * h2 + y) * w2 + x] = logvar;
+    }
+    float z = mean;
+    if (noise) {
+        const float stdv = bf16_round(expf(bf16_round(0.5f * logvar)));
+        const float eps = bf16_round(noise[(((long long)n * zc + c) * h2 + y) * w2 + x]);
+        z = bf16_round(mean + bf16_round(stdv * eps));
+    }
+    z = bf16_round(bf16_round(z - shift_factor) * scale_factor);
+    const int w = w2 >> 1;
+    const long long t = (long long)(y >> 1) * w + (x >> 1);
+    tok[((long long)n * (h2 >> 1) * w + t) * (4 * zc) + c * 4 + (y & 1) * 2 + (x & 1)] = __float2bfloat16_rn(z);
+}
+
 }  // namespace vcb

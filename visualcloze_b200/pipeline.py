@@ -8,10 +8,12 @@ row-wise RoPE ids, sampler settings and output cropping.  What differs is where 
     ``visualcloze_b200.transport.Sampler`` -- one ``vcb_flux_forward`` + one ``vcb_euler_update`` per step;
   * only the query (last) row is decoded, fused with un-patchify, scale/shift, ``(x + 1) / 2``, clamp and uint8
     conversion (the reference decodes every row and returns crops of the last one, visualcloze.py:424-453);
-  * text encoders (T5-XXL / CLIP-L) and the VAE *encoder* are outside this path: they are
-    injected as callables -- ``t5(list[str]) -> [B, 512, 4096]``, ``clip(list[str]) -> [B, 768]``,
-    ``encode(image [1, 3, H, W] in [-1, 1]) -> latent [1, 16, H/8, W/8]`` (already sampled, un-scaled) -- e.g. the
-    reference's own ``load_t5`` / ``load_clip`` / ``AutoencoderKL.encode(...).latent_dist.sample()``.
+  * text encoders (T5-XXL / CLIP-L) are outside this path: they are injected as callables --
+    ``t5(list[str]) -> [B, 512, 4096]``, ``clip(list[str]) -> [B, 768]`` -- e.g. the reference's own ``load_t5`` /
+    ``load_clip``;
+  * the VAE *encode* of the condition rows (visualcloze.py:377-388) runs on ``vae.AutoEncoderEncoder`` (libvcb200; the
+    "next" row (f)-1 of SURVEY.md section 8) unless an external ``encode(image [1, 3, H, W]) -> latent [1, 16, H/8, W/8]``
+    callable (sampled, un-scaled -- e.g. ``AutoencoderKL.encode(...).latent_dist.sample()``) is injected.
 """
 from __future__ import annotations
 
@@ -24,7 +26,7 @@ from PIL import Image
 from .model import FluxLoraWrapper, flux_dev_fill_params
 from .sampling import prepare_modified
 from .transport import Sampler, create_transport
-from .vae import AutoEncoderDecoder
+from .vae import AutoEncoderDecoder, AutoEncoderEncoder
 
 _CONTENT_PREFIXES = (
     "The content of the last image in the final row is: ", "The last image of the last row depicts: ",
@@ -88,7 +90,7 @@ def _patchify(lat: torch.Tensor) -> torch.Tensor:
 class VisualClozeModel:
     def __init__(self, model_path=None, model_name="flux-dev-fill-lora", max_length=512, lora_rank=256, atol=1e-6, rtol=1e-3,
                  solver="euler", time_shifting_factor=1, resolution=384, precision="bf16", *, model=None, ae_decoder=None,
-                 t5=None, clip=None, encode=None, device=None):
+                 ae_encoder=None, t5=None, clip=None, encode=None, device=None):
         if precision != "bf16":
             raise NotImplementedError("the sm_100a kernels implement the reference's default bf16 path only")
         if model_name != "flux-dev-fill-lora":
@@ -110,6 +112,10 @@ class VisualClozeModel:
             with torch.device(self.device):
                 ae_decoder = AutoEncoderDecoder()
         self.ae = ae_decoder
+        if ae_encoder is None and encode is None:
+            with torch.device(self.device):
+                ae_encoder = AutoEncoderEncoder()
+        self.ae_encoder = ae_encoder
         self.t5, self.clip, self.encode = t5, clip, encode
         self.sampler = Sampler(create_transport("Linear", "velocity", do_shift=True))
         self.sample_fn = self._make_sample_fn(30, True, self.time_shifting_factor, None)
@@ -131,10 +137,15 @@ class VisualClozeModel:
                                "hot path; pass the reference's own, see the module docstring)")
         return fn
 
-    def _encode_latent(self, image_chw: torch.Tensor) -> torch.Tensor:
-        """(ae.encode(x).latent_dist.sample() - shift) * scale, bf16 (visualcloze.py:377-378,384)."""
-        lat = self._need("encode")(image_chw[None].to(self.device, self.dtype))
-        return ((lat - self.ae.shift_factor) * self.ae.scale_factor).to(self.dtype)
+    def _encode_tokens(self, image_chw: torch.Tensor) -> torch.Tensor:
+        """patchify((ae.encode(x).latent_dist.sample() - shift) * scale) in bf16 (visualcloze.py:377-378,384-385): [1, hw/256, 64].
+        Like the reference, the sampling noise comes from the global (unseeded) RNG."""
+        if self.encode is not None:
+            lat = self.encode(image_chw[None].to(self.device, self.dtype))
+            return _patchify(((lat - self.ae.shift_factor) * self.ae.scale_factor).to(self.dtype))
+        x = image_chw[None].to(self.device)
+        noise = torch.randn(1, self.ae_encoder.params.z_channels, x.shape[2] // 8, x.shape[3] // 8, device=self.device)
+        return self.ae_encoder.encode_packed(x, noise)
 
     # ------------------------------------------------------------------------------------------------
     def _prepare_grid(self, images):
@@ -195,7 +206,7 @@ class VisualClozeModel:
             marks = mask_position if i == grid_h - 1 else [0] * grid_w
             rows.append(torch.cat(cells, dim=2).to(dev))
             fill_mask.append(torch.cat([torch.full((1, 1, h, w), float(m), device=dev) for m in marks], dim=3))
-        fill_cond = torch.cat([_patchify(self._encode_latent(r)) for r in rows], dim=1)
+        fill_cond = torch.cat([self._encode_tokens(r) for r in rows], dim=1)
         fill_mask = torch.cat([_pack_mask(m) for m in fill_mask], dim=1).to(dt)
         img_cond = torch.cat((fill_cond, fill_mask), dim=-1)
 
@@ -250,15 +261,15 @@ class VisualClozeModel:
         self.sample_fn = self._make_sample_fn(int(upsampling_steps), False, 1.0, upsampling_noise)
         dev, dt = self.device, self.dtype
         x = self.image_transform(image).to(dev)
-        latent = self._encode_latent(x)
-        blank = self._encode_latent(torch.zeros_like(x))
-        lh, lw = latent.shape[2:]
+        latent = self._encode_tokens(x)
+        blank = self._encode_tokens(torch.zeros_like(x))
+        lh, lw = x.shape[1] // 8, x.shape[2] // 8
         mask = _pack_mask(torch.ones(1, 1, x.shape[1], x.shape[2], device=dev, dtype=dt))
-        img_cond = torch.cat((_patchify(blank), mask), dim=-1)
+        img_cond = torch.cat((blank, mask), dim=-1)
         noise = torch.randn([1, 16, lh, lw], device=dev, generator=generator).to(dt)
         inp = prepare_modified(t5=self._need("t5"), clip=self._need("clip"), img=[[noise]], prompt=[content_prompt],
                                proportion_empty_prompts=0.0)
-        x_t = (inp["img"] * (1 - upsampling_noise) + _patchify(latent) * upsampling_noise).to(dt)
+        x_t = (inp["img"] * (1 - upsampling_noise) + latent * upsampling_noise).to(dt)
         kw = dict(txt=inp["txt"], txt_ids=inp["txt_ids"], txt_mask=inp["txt_mask"], y=inp["vec"], img_ids=inp["img_ids"],
                   img_mask=inp["img_mask"], cond=img_cond, guidance=torch.full((1,), cfg, device=dev, dtype=dt))
         sample = self.sample_fn(x_t, self.model.forward, kw)[-1][:1]

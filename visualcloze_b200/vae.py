@@ -16,7 +16,7 @@ import torch
 from torch import Tensor, nn
 
 from . import _lib
-from ._lib import ConvW, GnW, ResblockW, VaeConfigC, VaeWeightsC, check
+from ._lib import ConvW, GnW, ResblockW, VaeConfigC, VaeEncWeightsC, VaeWeightsC, check
 
 BF16 = torch.bfloat16
 
@@ -210,3 +210,127 @@ class AutoEncoderDecoder(nn.Module):
         h, w = H2 // 2, W2 // 2
         tok = z.reshape(n, c, h, 2, w, 2).permute(0, 2, 4, 1, 3, 5).reshape(n, h * w, c * 4)
         return self._run(tok, h, w, True, False)[0].to(z.dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# encoder ("next" row (f)-1): models/modules/autoencoder.py:109-180, 262-275, 302-305
+# --------------------------------------------------------------------------------------------------
+def encoder_param_shapes(p: AutoEncoderParams) -> dict[str, tuple]:
+    sh: dict[str, tuple] = {}
+
+    def conv(n, ci, co, k):
+        sh[n + ".weight"], sh[n + ".bias"] = (co, ci, k, k), (co,)
+
+    def norm(n, c):
+        sh[n + ".weight"], sh[n + ".bias"] = (c,), (c,)
+
+    def res(n, ci, co):
+        norm(n + ".norm1", ci); conv(n + ".conv1", ci, co, 3); norm(n + ".norm2", co); conv(n + ".conv2", co, co, 3)
+        if ci != co:
+            conv(n + ".nin_shortcut", ci, co, 1)
+
+    conv("encoder.conv_in", p.in_channels, p.ch, 3)
+    in_mult = (1,) + tuple(p.ch_mult)
+    bi = p.ch
+    for lvl in range(len(p.ch_mult)):
+        bi, bo = p.ch * in_mult[lvl], p.ch * p.ch_mult[lvl]
+        for b in range(p.num_res_blocks):
+            res(f"encoder.down.{lvl}.block.{b}", bi, bo)
+            bi = bo
+        if lvl != len(p.ch_mult) - 1:
+            conv(f"encoder.down.{lvl}.downsample.conv", bi, bi, 3)
+    res("encoder.mid.block_1", bi, bi)
+    norm("encoder.mid.attn_1.norm", bi)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(f"encoder.mid.attn_1.{n}", bi, bi, 1)
+    res("encoder.mid.block_2", bi, bi)
+    norm("encoder.norm_out", bi)
+    conv("encoder.conv_out", bi, 2 * p.z_channels, 3)
+    return sh
+
+
+class AutoEncoderEncoder(AutoEncoderDecoder):
+    """VAE encoder with the reference's ``encoder.*`` keys.  ``encode_packed`` returns what the pipeline needs as
+    ``fill_cond``: patchified ``(sample - shift) * scale`` tokens (visualcloze.py:377-388) in one call."""
+
+    def __init__(self, params: AutoEncoderParams | None = None, device=None, dtype=BF16):
+        nn.Module.__init__(self)
+        self.params = params or AutoEncoderParams()
+        self.scale_factor, self.shift_factor = self.params.scale_factor, self.params.shift_factor
+        for name, shp in encoder_param_shapes(self.params).items():
+            _attach(self, name, nn.Parameter(torch.empty(shp, device=device, dtype=dtype), requires_grad=False))
+        self._h = None
+        self._key = None
+        self._ws = None
+
+    def _engine(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._h is not None and key == self._key:
+            return self._h
+        some = next(self.parameters())
+        if not some.is_cuda:
+            raise _lib.VcbError("the VAE encoder runs on a CUDA device only (no CPU fallback)")
+        lib = _lib.lib()
+        if self._h is not None:
+            lib.vcb_vae_enc_destroy(self._h)
+        P = self.params
+        self._p = dict(self.named_parameters())
+        self._keep = []
+        with torch.no_grad():
+            cfg = VaeConfigC()
+            cfg.ch, cfg.out_ch, cfg.z_channels = P.ch, P.out_ch, P.z_channels
+            cfg.num_res_blocks, cfg.n_levels = P.num_res_blocks, len(P.ch_mult)
+            for i, m in enumerate(P.ch_mult):
+                cfg.ch_mult[i] = m
+            cfg.scale_factor, cfg.shift_factor = P.scale_factor, P.shift_factor
+            w = VaeEncWeightsC()
+            w.conv_in = self._conv("encoder.conv_in")
+            nl = len(P.ch_mult)
+            dn = (ResblockW * (nl * P.num_res_blocks))()
+            dc = (ConvW * max(1, nl - 1))()
+            bi = 0
+            for lvl in range(nl):
+                for b in range(P.num_res_blocks):
+                    dn[bi] = self._res(f"encoder.down.{lvl}.block.{b}")
+                    bi += 1
+                if lvl != nl - 1:
+                    dc[lvl] = self._conv(f"encoder.down.{lvl}.downsample.conv")
+            w.down_blocks, w.downsample = C.cast(dn, C.POINTER(ResblockW)), C.cast(dc, C.POINTER(ConvW))
+            w.mid1, w.mid2 = self._res("encoder.mid.block_1"), self._res("encoder.mid.block_2")
+            w.attn_norm = self._gn("encoder.mid.attn_1.norm")
+            w.attn_q, w.attn_k = self._conv("encoder.mid.attn_1.q"), self._conv("encoder.mid.attn_1.k")
+            w.attn_v, w.attn_proj = self._conv("encoder.mid.attn_1.v"), self._conv("encoder.mid.attn_1.proj_out")
+            w.norm_out, w.conv_out = self._gn("encoder.norm_out"), self._conv("encoder.conv_out")
+        self._cw = (cfg, w, dn, dc)
+        h = C.c_void_p()
+        check(lib.vcb_vae_enc_create(C.byref(cfg), C.byref(w), C.byref(h)), "vcb_vae_enc_create")
+        self._h, self._key = h, key
+        return h
+
+    def encode_packed(self, image: Tensor, noise: Tensor | None = None, return_moments: bool = False):
+        """image [n, 3, H, W] in [-1, 1] -> condition tokens [n, (H/16)(W/16), 64] bf16; ``noise`` [n, 16, H/8, W/8] is the
+        standard-normal draw of ``latent_dist.sample()`` (None = distribution mode)."""
+        hnd = self._engine()
+        lib = _lib.lib()
+        n, _, H, W = image.shape
+        dev = image.device
+        img = image.float().contiguous()
+        f = 2 ** (len(self.params.ch_mult) - 1)
+        need = lib.vcb_vae_enc_workspace_bytes(hnd, n, H, W)
+        if need < 0:
+            raise ValueError(f"image size must be a multiple of {2 * f}, got {(H, W)}")
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
+        zc = self.params.z_channels
+        tok = torch.empty(n, (H // (2 * f)) * (W // (2 * f)), 4 * zc, dtype=BF16, device=dev)
+        mom = torch.empty(n, 2 * zc, H // f, W // f, dtype=torch.float32, device=dev) if return_moments else None
+        nz = None if noise is None else noise.float().contiguous()
+        check(lib.vcb_vae_encode(hnd, self._ws.data_ptr(), self._ws.numel(), img.data_ptr(), n, H, W,
+                                 None if nz is None else nz.data_ptr(), tok.data_ptr(), None if mom is None else mom.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream), "vcb_vae_encode")
+        return (tok, mom) if return_moments else tok
+
+    def decode(self, *a, **k):          # not a decoder
+        raise AttributeError("AutoEncoderEncoder has no decode()")
+
+    decode_packed = decode
