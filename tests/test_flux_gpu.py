@@ -194,3 +194,10 @@ def test_pipeline_process_images_end_to_end(vcb):
     up = pipe.process_images(imgs, ["layout", "task", "The last image of the last row depicts: a cat"], seed=5, cfg=30, steps=4,
                              upsampling_steps=3, upsampling_noise=0.4, is_upsampling=True)
     assert len(up) == 1 and up[0].size == (80, 80)          # resized to the input cell's size, multiples of 16
+    # same pipeline with the library's own VAE encoder for the condition rows instead of an injected one
+    enc = V.AutoEncoderEncoder(V.AutoEncoderParams(ch=64, ch_mult=[1, 2, 2, 2], num_res_blocks=1), device="cuda").init_synthetic(2)
+    pipe2 = P.VisualClozeModel(None, resolution=64, model=model, ae_decoder=dec, ae_encoder=enc, t5=t5, clip=clip)
+    pipe2.set_grid_size(2, 3)
+    imgs = mk(); imgs[1][2] = None
+    out4 = pipe2.process_images(imgs, ["layout", "task", "content"], seed=5, cfg=30, steps=4, is_upsampling=False)
+    assert len(out4) == 1 and out4[0].size == (64, 64)
