@@ -77,6 +77,10 @@ typedef struct vcb_gemm_args {
 } vcb_gemm_args;
 
 int vcb_gemm_bf16(const vcb_gemm_args* args, void* stream);
+/* Two problems with the same N, K and epilogue (their own A, W, bias, outputs, row mapping) in ONE persistent launch:
+ * the txt stream of a DoubleStreamBlock (layers.py:170-175,193-195) rides in the img stream's launch and fills its
+ * partial last wave.  block_n / cta_group are taken from the first problem. */
+int vcb_gemm_bf16_grouped(const vcb_gemm_args* args0, const vcb_gemm_args* args1, void* stream);
 
 /* ---- 3x3 convolution, stride 1, zero padding 1, NHWC bf16 (models/modules/autoencoder.py:63,65,101,239,258) ------
  * Implicit GEMM on the tcgen05 kernel without im2col: each k-block is one 4-D TMA box of a 16x8 pixel patch at the

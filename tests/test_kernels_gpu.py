@@ -133,6 +133,33 @@ def test_gemm_gate_residual_batched(ops, cta_group):
     assert rel_l2(xg.cpu(), ref) < 4e-3, _stats(xg, ref)
 
 
+@pytest.mark.parametrize("cta_group", [0, 1, 2])
+def test_gemm_grouped_two_streams(ops, cta_group):
+    """img + txt streams of a double block in ONE launch: different A rows of a joint buffer, different weights, gates and
+    row offsets; in-place gated residual (layers.py:190-195)."""
+    B, Li, Lt, H, K = 2, 300, 40, 512, 256
+    L = Li + Lt
+    attn = _randn(B * L, K, seed=1)                                  # joint [B, L, K] buffer, txt rows first
+    x = _randn(B * L, H, seed=2)
+    w = [_randn(H, K, seed=3, scale=1 / math.sqrt(K)), _randn(H, K, seed=4, scale=1 / math.sqrt(K))]
+    bias = [_randn(H, seed=5, dtype=torch.float32, scale=0.1), _randn(H, seed=6, dtype=torch.float32, scale=0.1)]
+    gate = [_randn(B, H, seed=7), _randn(B, H, seed=8)]
+    xg, ag = x.cuda().clone(), attn.cuda()
+    probs = []
+    for s, (rows, off) in enumerate(((Li, Lt), (Lt, 0))):           # img then txt
+        probs.append(dict(a=ag[off:], w=w[s].cuda(), bias=bias[s].cuda(), out=xg, epilogue=ops.EPI_GATE_RES, m=B * rows,
+                          rows_per_batch=rows, out_batch_rows=L, out_row_offset=off, a_batch_stride=L * K, gate=gate[s].cuda(),
+                          res=xg, cta_group=cta_group))
+    ops.gemm_grouped(probs[0], probs[1])
+    torch.cuda.synchronize()
+    ref = x.reshape(B, L, H).clone()
+    a3 = attn.reshape(B, L, K)
+    for s, (rows, off) in enumerate(((Li, Lt), (Lt, 0))):
+        lin = (a3[:, off:off + rows].float() @ w[s].float().T + bias[s]).to(BF16)
+        ref[:, off:off + rows] = x.reshape(B, L, H)[:, off:off + rows] + gate[s][:, None, :] * lin
+    assert rel_l2(xg.cpu(), ref.reshape(B * L, H)) < 4e-3, _stats(xg, ref.reshape(B * L, H))
+
+
 def _qkv_reference(a, w, bias, qs, ks, cos, sin, heads):
     from oracle import flux_oracle as fo
     L = a.shape[0]

@@ -22,8 +22,11 @@ using namespace vcb;
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+struct Problem { CUtensorMap ta, tb; GemmParams p; };
+
 template <int BN, int CG, int EPI>
-int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+int launch_gemm_inst(const Problem& g0, const Problem& g1, cudaStream_t st) {
+    const CUtensorMap& ta = g0.ta; const CUtensorMap& tb = g0.tb; const GemmParams& p = g0.p;
     using Cfg = GemmCfg<BN, CG>;
     auto kern = gemm_bf16_tcgen05_kernel<BN, CG, EPI>;
     static std::once_flag once;
@@ -33,27 +36,28 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     });
     if (attr_err != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(attr_err));
     const int tile_m = kBlockM * CG;
-    const int tiles = p.batch * ((p.rows_per_batch + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
+    int tiles = p.batch * ((p.rows_per_batch + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
+    if (g1.p.batch > 0) tiles += g1.p.batch * ((g1.p.rows_per_batch + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
     int clusters = num_sms() / CG;
     if (tiles < clusters) clusters = tiles;
-    cudaError_t e = launch_pdl(kern, dim3(clusters * CG), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, st, CG, ta, tb, p);
+    cudaError_t e = launch_pdl(kern, dim3(clusters * CG), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, st, CG, ta, tb, p, g1.ta, g1.tb, g1.p);
     if (e != cudaSuccess) return set_error("gemm launch (BN=%d CG=%d EPI=%d): %s", BN, CG, EPI, cudaGetErrorString(e));
     count_launch();
     return 0;
 }
 
 template <int BN, int CG>
-int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+int launch_gemm_epi(int epi, const Problem& g0, const Problem& g1, cudaStream_t st) {
     switch (epi) {
-        case EPI_BIAS: return launch_gemm_inst<BN, CG, EPI_BIAS>(ta, tb, p, st);
-        case EPI_BIAS_GELU: return launch_gemm_inst<BN, CG, EPI_BIAS_GELU>(ta, tb, p, st);
-        case EPI_GATE_RES: return launch_gemm_inst<BN, CG, EPI_GATE_RES>(ta, tb, p, st);
-        case EPI_BIAS_F32: return launch_gemm_inst<BN, CG, EPI_BIAS_F32>(ta, tb, p, st);
+        case EPI_BIAS: return launch_gemm_inst<BN, CG, EPI_BIAS>(g0, g1, st);
+        case EPI_BIAS_GELU: return launch_gemm_inst<BN, CG, EPI_BIAS_GELU>(g0, g1, st);
+        case EPI_GATE_RES: return launch_gemm_inst<BN, CG, EPI_GATE_RES>(g0, g1, st);
+        case EPI_BIAS_F32: return launch_gemm_inst<BN, CG, EPI_BIAS_F32>(g0, g1, st);
         default: break;
     }
     if constexpr (BN % 128 == 0) {
-        if (epi == EPI_QKV) return launch_gemm_inst<BN, CG, EPI_QKV>(ta, tb, p, st);
-        if (epi == EPI_LINEAR1) return launch_gemm_inst<BN, CG, EPI_LINEAR1>(ta, tb, p, st);
+        if (epi == EPI_QKV) return launch_gemm_inst<BN, CG, EPI_QKV>(g0, g1, st);
+        if (epi == EPI_LINEAR1) return launch_gemm_inst<BN, CG, EPI_LINEAR1>(g0, g1, st);
     }
     return set_error("gemm: epilogue %d not available for block_n %d", epi, BN);
 }
@@ -94,7 +98,10 @@ void pick_tile(int batch, int rows, int N, bool head_structured, int want_cg, in
 
 }  // namespace
 
-extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
+namespace {
+
+// validate one problem
+int check_gemm_args(const vcb_gemm_args* a) {
     if (!a) return set_error("gemm: null args");
     if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error("gemm: bad shape %d %d %d", a->M, a->N, a->K);
     if (a->lda % 8 || a->ldw % 8 || a->ldo % 8 || a->out_col_offset % 8)
@@ -118,16 +125,17 @@ extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
         return set_error("gemm: GATE_RES epilogue needs res (gate may be NULL = ungated residual)");
     if (a->epilogue < 0 || a->epilogue > VCB_EPI_BIAS_F32) return set_error("gemm: unknown epilogue %d", a->epilogue);
     if (a->rows_per_batch <= 0 || a->M % a->rows_per_batch) return set_error("gemm: M must be a multiple of rows_per_batch");
-    const int batch = a->M / a->rows_per_batch;
     const int64_t a_bstride = a->a_batch_stride ? a->a_batch_stride : (int64_t)a->rows_per_batch * a->lda;
     if (a_bstride % 8) return set_error("gemm: a_batch_stride must be a multiple of 8");
-    if (int rc = ensure_device()) return rc;
-
     if (a->cta_group < 0 || a->cta_group > 2) return set_error("gemm: cta_group must be 0 (auto), 1 or 2");
-    int cg, bn;
-    pick_tile(batch, a->rows_per_batch, a->N, head, a->cta_group ? a->cta_group : forced_cta_group(), a->block_n, &cg, &bn);
+    return 0;
+}
 
-    GemmParams p{};
+int build_problem(const vcb_gemm_args* a, int bn, int cg, Problem* out) {
+    const int batch = a->M / a->rows_per_batch;
+    const int64_t a_bstride = a->a_batch_stride ? a->a_batch_stride : (int64_t)a->rows_per_batch * a->lda;
+    GemmParams& p = out->p;
+    p = GemmParams{};
     p.N = a->N; p.K = a->K; p.batch = batch;
     p.rows_per_batch = a->rows_per_batch; p.out_batch_rows = a->out_batch_rows; p.out_row_offset = a->out_row_offset;
     p.bias = a->bias;
@@ -137,15 +145,38 @@ extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
     p.hidden = a->hidden; p.q_scale = (const __nv_bfloat16*)a->q_scale; p.k_scale = (const __nv_bfloat16*)a->k_scale;
     p.rope = (const float2*)a->rope; p.rope_rows = a->rope_rows;
     p.out2 = (__nv_bfloat16*)a->out2; p.ldo2 = a->ldo2; p.out2_col_offset = a->out2_col_offset;
-
-    ProfScope prof(PROF_GEMM, stream);
-    CUtensorMap ta, tb;
-    if (int rc = make_tmap_3d(&ta, a->A, (uint64_t)a->K, (uint64_t)a->rows_per_batch, (uint64_t)batch, (uint64_t)a->lda,
+    if (int rc = make_tmap_3d(&out->ta, a->A, (uint64_t)a->K, (uint64_t)a->rows_per_batch, (uint64_t)batch, (uint64_t)a->lda,
                               (uint64_t)a_bstride, 64, 128)) return rc;
-    if (int rc = make_tmap_2d(&tb, a->W, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldw, 64, (uint32_t)(bn / cg))) return rc;
+    if (int rc = make_tmap_2d(&out->tb, a->W, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldw, 64, (uint32_t)(bn / cg))) return rc;
+    return 0;
+}
+
+int gemm_dispatch(const vcb_gemm_args* a, const vcb_gemm_args* a1, void* stream) {
+    if (int rc = check_gemm_args(a)) return rc;
+    if (a1) {
+        if (int rc = check_gemm_args(a1)) return rc;
+        if (a1->N != a->N || a1->K != a->K || a1->epilogue != a->epilogue)
+            return set_error("gemm (grouped): both problems need the same N, K and epilogue");
+    }
+    if (int rc = ensure_device()) return rc;
+    const bool head = a->epilogue == VCB_EPI_QKV || a->epilogue == VCB_EPI_LINEAR1;
+    int cg, bn;
+    // tile choice for the combined tile count (the second problem only adds tiles of the same shape)
+    const int batch = a->M / a->rows_per_batch;
+    pick_tile(batch, a->rows_per_batch + (a1 ? a1->M / batch : 0), a->N, head, a->cta_group ? a->cta_group : forced_cta_group(),
+              a->block_n, &cg, &bn);
+    ProfScope prof(PROF_GEMM, stream);
+    Problem g0, g1;
+    if (int rc = build_problem(a, bn, cg, &g0)) return rc;
+    if (a1) {
+        if (int rc = build_problem(a1, bn, cg, &g1)) return rc;
+    } else {
+        g1 = g0;
+        g1.p = GemmParams{};            // batch == 0: no second problem
+    }
     cudaStream_t st = (cudaStream_t)stream;
 #define VCB_GEMM_CASE(BN, CG) \
-    if (bn == BN && cg == CG) return launch_gemm_epi<BN, CG>(a->epilogue, ta, tb, p, st);
+    if (bn == BN && cg == CG) return launch_gemm_epi<BN, CG>(a->epilogue, g0, g1, st);
     VCB_GEMM_CASE(64, 1)
     VCB_GEMM_CASE(128, 1)
     VCB_GEMM_CASE(192, 1)
@@ -155,6 +186,15 @@ extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) {
     VCB_GEMM_CASE(256, 2)
 #undef VCB_GEMM_CASE
     return set_error("gemm: unsupported (block_n=%d, cta_group=%d)", bn, cg);
+}
+
+}  // namespace
+
+extern "C" int vcb_gemm_bf16(const vcb_gemm_args* a, void* stream) { return gemm_dispatch(a, nullptr, stream); }
+
+extern "C" int vcb_gemm_bf16_grouped(const vcb_gemm_args* a0, const vcb_gemm_args* a1, void* stream) {
+    if (!a1) return set_error("gemm (grouped): second problem is null");
+    return gemm_dispatch(a0, a1, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -175,7 +215,8 @@ int launch_conv_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
                       ((p.N + BN - 1) / BN);
     int grid = num_sms();
     if (tiles < grid) grid = tiles;
-    cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, st, 1, ta, tb, p);
+    GemmParams none{};
+    cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, st, 1, ta, tb, p, ta, tb, none);
     if (e != cudaSuccess) return set_error("conv3x3 launch: %s", cudaGetErrorString(e));
     count_launch();
     return 0;

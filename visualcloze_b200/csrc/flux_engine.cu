@@ -174,11 +174,10 @@ struct StreamView {
 };
 
 // GEMM over one stream of the joint buffers: A rows (b, off + i) of `a_buf`, output rows (b, off + i) of `out`
-int stream_gemm(const vcb_flux* f, const StreamView& sv, const uint16_t* a_buf, int64_t lda, int a_col, int K,
-                const vcb_linear_w& w, int N, int epi, uint16_t* out, int64_t ldo, int out_col, const uint16_t* gate,
-                int64_t gate_stride, const vcb_stream_w* qk, const void* q_scale, const void* k_scale, uint16_t* out2,
-                int64_t ldo2, int out2_col, void* stream) {
-    (void)qk;
+vcb_gemm_args stream_args(const vcb_flux* f, const StreamView& sv, const uint16_t* a_buf, int64_t lda, int a_col, int K,
+                          const vcb_linear_w& w, int N, int epi, uint16_t* out, int64_t ldo, int out_col, const uint16_t* gate,
+                          int64_t gate_stride, const void* q_scale, const void* k_scale, uint16_t* out2, int64_t ldo2,
+                          int out2_col) {
     vcb_gemm_args g{};
     g.M = f->B * sv.rows; g.N = N; g.K = K;
     g.A = a_buf + (int64_t)sv.off * lda + a_col; g.lda = lda; g.a_batch_stride = (int64_t)f->L * lda;
@@ -189,6 +188,16 @@ int stream_gemm(const vcb_flux* f, const StreamView& sv, const uint16_t* a_buf, 
     g.gate = gate; g.gate_stride = gate_stride; g.res = out; g.ld_res = ldo;
     g.hidden = f->cfg.hidden; g.q_scale = q_scale; g.k_scale = k_scale; g.rope = f->rope; g.rope_rows = (int64_t)f->B * f->L;
     g.out2 = out2; g.ldo2 = ldo2; g.out2_col_offset = out2_col;
+    return g;
+}
+
+int stream_gemm(const vcb_flux* f, const StreamView& sv, const uint16_t* a_buf, int64_t lda, int a_col, int K,
+                const vcb_linear_w& w, int N, int epi, uint16_t* out, int64_t ldo, int out_col, const uint16_t* gate,
+                int64_t gate_stride, const vcb_stream_w* qk, const void* q_scale, const void* k_scale, uint16_t* out2,
+                int64_t ldo2, int out2_col, void* stream) {
+    (void)qk;
+    vcb_gemm_args g = stream_args(f, sv, a_buf, lda, a_col, K, w, N, epi, out, ldo, out_col, gate, gate_stride, q_scale, k_scale,
+                                  out2, ldo2, out2_col);
     return vcb_gemm_bf16(&g, stream);
 }
 
@@ -235,20 +244,39 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
         const vcb_stream_w* sw[2] = {&w.img, &w.txt};
         const StreamView* sv[2] = {&s_img, &s_txt};
         const uint16_t* mod[2] = {f->mod_dbl[2 * i] + erow * 6 * H, f->mod_dbl[2 * i + 1] + erow * 6 * H};
-        for (int s = 0; s < 2; ++s) {
+        // both streams of a block share each launch (img first, txt fills the img problem's partial last wave)
+        for (int s = 0; s < 2; ++s)
             if ((rc = stream_ln(f, *sv[s], mod[s] + 0, mod[s] + H, 6 * H, stream))) return rc;
-            if ((rc = stream_gemm(f, *sv[s], f->xm, H, 0, H, sw[s]->qkv, 3 * H, VCB_EPI_QKV, f->qkv, 3 * H, 0, nullptr, 0,
-                                  nullptr, sw[s]->q_scale, sw[s]->k_scale, nullptr, 0, 0, stream))) return rc;
+        {
+            vcb_gemm_args g[2];
+            for (int s = 0; s < 2; ++s)
+                g[s] = stream_args(f, *sv[s], f->xm, H, 0, H, sw[s]->qkv, 3 * H, VCB_EPI_QKV, f->qkv, 3 * H, 0, nullptr, 0,
+                                   sw[s]->q_scale, sw[s]->k_scale, nullptr, 0, 0);
+            if ((rc = vcb_gemm_bf16_grouped(&g[0], &g[1], stream))) return rc;
         }
         if ((rc = vcb_attention_fwd(f->qkv, 3 * H, 0, H, 2 * H, f->seqlens, B, L, c.heads, f->cat, ldc, 0, stream))) return rc;
-        for (int s = 0; s < 2; ++s) {
-            if ((rc = stream_gemm(f, *sv[s], f->cat, ldc, 0, H, sw[s]->proj, H, VCB_EPI_GATE_RES, f->x, H, 0, mod[s] + 2 * H,
-                                  6 * H, nullptr, nullptr, nullptr, nullptr, 0, 0, stream))) return rc;
+        {
+            vcb_gemm_args g[2];
+            for (int s = 0; s < 2; ++s)
+                g[s] = stream_args(f, *sv[s], f->cat, ldc, 0, H, sw[s]->proj, H, VCB_EPI_GATE_RES, f->x, H, 0, mod[s] + 2 * H, 6 * H,
+                                   nullptr, nullptr, nullptr, 0, 0);
+            if ((rc = vcb_gemm_bf16_grouped(&g[0], &g[1], stream))) return rc;
+        }
+        for (int s = 0; s < 2; ++s)
             if ((rc = stream_ln(f, *sv[s], mod[s] + 3 * H, mod[s] + 4 * H, 6 * H, stream))) return rc;
-            if ((rc = stream_gemm(f, *sv[s], f->xm, H, 0, H, sw[s]->mlp0, mlp, VCB_EPI_BIAS_GELU, f->cat, ldc, H, nullptr, 0,
-                                  nullptr, nullptr, nullptr, nullptr, 0, 0, stream))) return rc;
-            if ((rc = stream_gemm(f, *sv[s], f->cat, ldc, H, mlp, sw[s]->mlp2, H, VCB_EPI_GATE_RES, f->x, H, 0, mod[s] + 5 * H,
-                                  6 * H, nullptr, nullptr, nullptr, nullptr, 0, 0, stream))) return rc;
+        {
+            vcb_gemm_args g[2];
+            for (int s = 0; s < 2; ++s)
+                g[s] = stream_args(f, *sv[s], f->xm, H, 0, H, sw[s]->mlp0, mlp, VCB_EPI_BIAS_GELU, f->cat, ldc, H, nullptr, 0, nullptr,
+                                   nullptr, nullptr, 0, 0);
+            if ((rc = vcb_gemm_bf16_grouped(&g[0], &g[1], stream))) return rc;
+        }
+        {
+            vcb_gemm_args g[2];
+            for (int s = 0; s < 2; ++s)
+                g[s] = stream_args(f, *sv[s], f->cat, ldc, H, mlp, sw[s]->mlp2, H, VCB_EPI_GATE_RES, f->x, H, 0, mod[s] + 5 * H, 6 * H,
+                                   nullptr, nullptr, nullptr, 0, 0);
+            if ((rc = vcb_gemm_bf16_grouped(&g[0], &g[1], stream))) return rc;
         }
     }
     // ---- single-stream blocks on the joint sequence (layers.py:232-245) ----

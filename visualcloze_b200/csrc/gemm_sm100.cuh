@@ -132,7 +132,10 @@ VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, in
 template <int BLOCK_N, int kCtaGroup, int kEpi, int kAMode = A_MATRIX>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const GemmParams p) {
+                         const GemmParams p, const __grid_constant__ CUtensorMap tmap_a1,
+                         const __grid_constant__ CUtensorMap tmap_b1, const GemmParams p1) {
+    // Grouped launch: an optional second problem (p1.batch > 0) with the same N, K and epilogue but its own operands --
+    // the txt stream of a DoubleStreamBlock rides in the img stream's launch and fills its partial last wave.
     using Cfg = GemmCfg<BLOCK_N, kCtaGroup>;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -155,6 +158,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if (p1.batch > 0) {
+            tma_prefetch_desc(&tmap_a1);
+            tma_prefetch_desc(&tmap_b1);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -181,7 +188,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                                    : (p.rows_per_batch + tile_m - 1) / tile_m;
     const int num_m = m_per_sample * p.batch;
     const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-    const int num_tiles = num_m * num_n;
+    const int tiles0 = num_m * num_n;
+    const int m_per_sample1 = (p1.rows_per_batch + tile_m - 1) / tile_m;
+    const int num_m1 = p1.batch > 0 ? m_per_sample1 * p1.batch : 0;
+    const int num_tiles = tiles0 + num_m1 * num_n;
     const int num_kb = (p.K + kBlockK - 1) / kBlockK;
     const int cluster_id = blockIdx.x / kCtaGroup;
     const int num_clusters = gridDim.x / kCtaGroup;
@@ -192,27 +202,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             int stage = 0;
             uint32_t phase = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-                const int mt = t % num_m;
-                const int bi = mt / m_per_sample;
-                const int m0 = (mt % m_per_sample) * tile_m + (int)cta_rank * kBlockM;
-                const int n0 = (t / num_m) * BLOCK_N + (int)cta_rank * Cfg::kBRows;
+                const bool g1 = t >= tiles0;
+                const int tt = g1 ? t - tiles0 : t, nm = g1 ? num_m1 : num_m, mps = g1 ? m_per_sample1 : m_per_sample;
+                const CUtensorMap* ta = g1 ? &tmap_a1 : &tmap_a;
+                const CUtensorMap* tb = g1 ? &tmap_b1 : &tmap_b;
+                const int mt = tt % nm;
+                const int bi = mt / mps;
+                const int m0 = (mt % mps) * tile_m + (int)cta_rank * kBlockM;
+                const int n0 = (tt / nm) * BLOCK_N + (int)cta_rank * Cfg::kBRows;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (is_leader) mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes * kCtaGroup);
                     if constexpr (kAMode == A_CONV3X3) {
                         const int cpb = p.conv_C / kBlockK;
                         const int tap = kb / cpb, cb = kb - tap * cpb;
-                        const int mi = mt % m_per_sample;
+                        const int mi = mt % mps;
                         const int pad = p.conv_stride == 1 ? 1 : 0;
                         const int x0 = (mi % conv_tx) * kConvTileW * p.conv_stride + (tap % 3) - pad;
                         const int y0 = (mi / conv_tx) * kConvTileH * p.conv_stride + (tap / 3) - pad;
-                        tma_load_4d<false>(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, cb * kBlockK, x0, y0, bi,
+                        tma_load_4d<false>(ta, &full_bar[stage], smem_a + stage * Cfg::kABytes, cb * kBlockK, x0, y0, bi,
                                            kEvictNormal);
                     } else {
-                        tma_load_3d<kCtaGroup == 2>(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBlockK,
+                        tma_load_3d<kCtaGroup == 2>(ta, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBlockK,
                                                     m0, bi, kEvictNormal);
                     }
-                    tma_load_2d<kCtaGroup == 2>(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBlockK,
+                    tma_load_2d<kCtaGroup == 2>(tb, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBlockK,
                                                 n0, kEvictNormal);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -263,22 +277,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-            const int mt = t % num_m;
-            const int b = mt / m_per_sample;
-            const int n_tile0 = (t / num_m) * BLOCK_N;
+            const bool g1 = t >= tiles0;
+            const GemmParams& P = g1 ? p1 : p;
+            const int tt = g1 ? t - tiles0 : t, nm = g1 ? num_m1 : num_m, mps = g1 ? m_per_sample1 : m_per_sample;
+            const int mt = tt % nm;
+            const int b = mt / mps;
+            const int n_tile0 = (tt / nm) * BLOCK_N;
             int i;
             bool row_ok;
             if constexpr (kAMode == A_CONV3X3) {
-                const int mi = mt % m_per_sample;
+                const int mi = mt % mps;
                 const int px = (mi % conv_tx) * kConvTileW + (row_in_tile % kConvTileW);
                 const int py = (mi / conv_tx) * kConvTileH + (row_in_tile / kConvTileW);
-                row_ok = px < p.conv_W && py < p.conv_H;
-                i = py * p.conv_W + px;
+                row_ok = px < P.conv_W && py < P.conv_H;
+                i = py * P.conv_W + px;
             } else {
-                i = (mt % m_per_sample) * tile_m + (int)cta_rank * kBlockM + row_in_tile;
-                row_ok = i < p.rows_per_batch;
+                i = (mt % mps) * tile_m + (int)cta_rank * kBlockM + row_in_tile;
+                row_ok = i < P.rows_per_batch;
             }
-            const long long orow = (long long)b * p.out_batch_rows + p.out_row_offset + (row_ok ? i : 0);
+            const long long orow = (long long)b * P.out_batch_rows + P.out_row_offset + (row_ok ? i : 0);
 
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -289,21 +306,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int c = 0; c < kHalfN / 32; ++c) {
                     const int cc = half * (kHalfN / 32) + c;
                     const int n0 = n_tile0 + cc * 32;
-                    if (n0 >= p.N) break;
+                    if (n0 >= P.N) break;
                     uint32_t r[32];
                     __syncwarp();
                     tmem_ld_x32(taddr + cc * 32, r);
                     tmem_wait_ld();
                     if (row_ok) {
-                        float* dst = reinterpret_cast<float*>(p.out) + orow * p.ldo + p.out_col_offset + n0;
+                        float* dst = reinterpret_cast<float*>(P.out) + orow * P.ldo + P.out_col_offset + n0;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            if (n0 + q * 4 < p.N) {
+                            if (n0 + q * 4 < P.N) {
                                 float4 f;
-                                f.x = __uint_as_float(r[q * 4 + 0]) + (p.bias ? __ldg(p.bias + n0 + q * 4 + 0) : 0.f);
-                                f.y = __uint_as_float(r[q * 4 + 1]) + (p.bias ? __ldg(p.bias + n0 + q * 4 + 1) : 0.f);
-                                f.z = __uint_as_float(r[q * 4 + 2]) + (p.bias ? __ldg(p.bias + n0 + q * 4 + 2) : 0.f);
-                                f.w = __uint_as_float(r[q * 4 + 3]) + (p.bias ? __ldg(p.bias + n0 + q * 4 + 3) : 0.f);
+                                f.x = __uint_as_float(r[q * 4 + 0]) + (P.bias ? __ldg(P.bias + n0 + q * 4 + 0) : 0.f);
+                                f.y = __uint_as_float(r[q * 4 + 1]) + (P.bias ? __ldg(P.bias + n0 + q * 4 + 1) : 0.f);
+                                f.z = __uint_as_float(r[q * 4 + 2]) + (P.bias ? __ldg(P.bias + n0 + q * 4 + 2) : 0.f);
+                                f.w = __uint_as_float(r[q * 4 + 3]) + (P.bias ? __ldg(P.bias + n0 + q * 4 + 3) : 0.f);
                                 *reinterpret_cast<float4*>(dst + q * 4) = f;
                             }
                         }
@@ -314,20 +331,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int c = 0; c < kHalfN / 32; ++c) {
                     const int cc = half * (kHalfN / 32) + c;
                     const int n0 = n_tile0 + cc * 32;
-                    if (n0 >= p.N) break;
+                    if (n0 >= P.N) break;
                     float v[32];
-                    load_acc_bias(taddr + cc * 32, p.bias, n0, p.N, v);
+                    load_acc_bias(taddr + cc * 32, P.bias, n0, P.N, v);
                     if (row_ok) {
                         if constexpr (kEpi == EPI_BIAS_GELU) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
                         }
                         if constexpr (kEpi == EPI_GATE_RES) {
-                            const __nv_bfloat16* g = p.gate ? p.gate + (long long)b * p.gate_stride + n0 : nullptr;
-                            const __nv_bfloat16* rs = p.res + orow * p.ld_res + n0;
+                            const __nv_bfloat16* g = P.gate ? P.gate + (long long)b * P.gate_stride + n0 : nullptr;
+                            const __nv_bfloat16* rs = P.res + orow * P.ld_res + n0;
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                if (n0 + q * 8 < p.N) {
+                                if (n0 + q * 8 < P.N) {
                                     const uint32_t one2 = 0x3F803F80u;          // bf16 (1.0, 1.0)
                                     uint4 gu = g ? __ldg(reinterpret_cast<const uint4*>(g + q * 8)) : make_uint4(one2, one2, one2, one2);
                                     uint4 ru = *reinterpret_cast<const uint4*>(rs + q * 8);
@@ -345,7 +362,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                 }
                             }
                         }
-                        store_bf16x32(p.out + orow * p.ldo + p.out_col_offset + n0, v, n0, p.N);
+                        store_bf16x32(P.out + orow * P.ldo + P.out_col_offset + n0, v, n0, P.N);
                     }
                 }
             } else {
@@ -354,22 +371,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll 1
                 for (int hg = (int)half; hg < BLOCK_N / 128; hg += 2) {
                     const int ng = n_tile0 + hg * 128;           // first column of this 128-group
-                    if (ng >= p.N) break;
+                    if (ng >= P.N) break;
                     const uint32_t tg = taddr + hg * 128;
-                    const int region = ng / p.hidden;            // 0 q, 1 k, 2 v, >= 3 mlp (LINEAR1)
+                    const int region = ng / P.hidden;            // 0 q, 1 k, 2 v, >= 3 mlp (LINEAR1)
                     if (region >= 2) {
 #pragma unroll 1
                         for (int c = 0; c < 4; ++c) {
                             const int n0 = ng + c * 32;
                             float v[32];
-                            load_acc_bias(tg + c * 32, p.bias, n0, p.N, v);
+                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v);
                             if (!row_ok) {
                             } else if (kEpi == EPI_LINEAR1 && region >= 3) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-                                store_bf16x32(p.out2 + orow * p.ldo2 + p.out2_col_offset + (n0 - 3 * p.hidden), v, n0, p.N);
+                                store_bf16x32(P.out2 + orow * P.ldo2 + P.out2_col_offset + (n0 - 3 * P.hidden), v, n0, P.N);
                             } else {
-                                store_bf16x32(p.out + orow * p.ldo + p.out_col_offset + n0, v, n0, p.N);
+                                store_bf16x32(P.out + orow * P.ldo + P.out_col_offset + n0, v, n0, P.N);
                             }
                         }
                     } else {
@@ -378,20 +395,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll 1
                         for (int c = 0; c < 4; ++c) {
                             float v[32];
-                            load_acc_bias(tg + c * 32, p.bias, ng + c * 32, p.N, v);
+                            load_acc_bias(tg + c * 32, P.bias, ng + c * 32, P.N, v);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
                         }
                         const float rrms = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
-                        const __nv_bfloat16* sc = region == 0 ? p.q_scale : p.k_scale;
+                        const __nv_bfloat16* sc = region == 0 ? P.q_scale : P.k_scale;
                         // rope table is stored pair-major [64][rope_rows]: consecutive lanes (rows) read consecutive float2
-                        const float2* rp = p.rope + orow;
+                        const float2* rp = P.rope + orow;
                         // pass 2: normalise, scale, rotate, store
 #pragma unroll 1
                         for (int c = 0; c < 4; ++c) {
                             const int n0 = ng + c * 32;
                             float v[32];
-                            load_acc_bias(tg + c * 32, p.bias, n0, p.N, v);
+                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v);
                             if (row_ok) {
                                 uint32_t sw[16];
 #pragma unroll
@@ -405,12 +422,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                     const float2 s2 = unpack_bf16x2(sw[j >> 1]);
                                     float x0 = bf16_round(bf16_round(v[j] * rrms) * s2.x);
                                     float x1 = bf16_round(bf16_round(v[j + 1] * rrms) * s2.y);
-                                    float2 cs = __ldg(rp + (long long)pr * p.rope_rows);
+                                    float2 cs = __ldg(rp + (long long)pr * P.rope_rows);
                                     // math.py:112-117: two fp32 products, one fp32 add (no contraction)
                                     v[j] = __fadd_rn(__fmul_rn(cs.x, x0), __fmul_rn(-cs.y, x1));
                                     v[j + 1] = __fadd_rn(__fmul_rn(cs.y, x0), __fmul_rn(cs.x, x1));
                                 }
-                                store_bf16x32(p.out + orow * p.ldo + p.out_col_offset + n0, v, n0, p.N);
+                                store_bf16x32(P.out + orow * P.ldo + P.out_col_offset + n0, v, n0, P.N);
                             }
                         }
                     }

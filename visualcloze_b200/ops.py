@@ -29,11 +29,27 @@ def _req(t: torch.Tensor, dtype, name: str):
         raise _lib.VcbError(f"{name} must be contiguous in its last dimension")
 
 
-def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: torch.Tensor, *, epilogue: int = EPI_BIAS,
+def gemm(*args, **kw) -> torch.Tensor:
+    """out[...] = epilogue(a @ w.T); see ``gemm_args`` for the parameters and include/vcb200.h for the semantics."""
+    g, out = gemm_args(*args, **kw)
+    check(_lib.lib().vcb_gemm_bf16(C.byref(g), _stream()), "vcb_gemm_bf16")
+    return out
+
+
+def gemm_grouped(problem0: dict, problem1: dict) -> None:
+    """Two problems (dicts of ``gemm_args`` keyword arguments incl. a, w, bias, out) with equal N, K, epilogue in one launch."""
+    def build(d):
+        d = dict(d)
+        return gemm_args(d.pop("a"), d.pop("w"), d.pop("bias"), d.pop("out"), **d)[0]
+    g0, g1 = build(problem0), build(problem1)
+    check(_lib.lib().vcb_gemm_bf16_grouped(C.byref(g0), C.byref(g1), _stream()), "vcb_gemm_bf16_grouped")
+
+
+def gemm_args(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: torch.Tensor, *, epilogue: int = EPI_BIAS,
          out_col_offset: int = 0, rows_per_batch: int | None = None, out_batch_rows: int | None = None,
          out_row_offset: int = 0, gate: torch.Tensor | None = None, res: torch.Tensor | None = None,
          hidden: int = 0, q_scale=None, k_scale=None, rope=None, out2=None, out2_col_offset: int = 0,
-         block_n: int = 0, cta_group: int = 0, a_batch_stride: int = 0, m: int | None = None) -> torch.Tensor:
+         block_n: int = 0, cta_group: int = 0, a_batch_stride: int = 0, m: int | None = None):
     """out[...] = epilogue(a @ w.T).  a [M,K], w [N,K], out 2-D (rows, ld); see include/vcb200.h.
     With batching (rows_per_batch < M) sample b's rows start at a + b * a_batch_stride (elements)."""
     _req(a, BF16, "a"); _req(w, BF16, "w"); _req(out, BF16, "out")
@@ -64,8 +80,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: torch
         _req(out2, BF16, "out2")
         g.out2, g.ldo2, g.out2_col_offset = out2.data_ptr(), out2.stride(0), out2_col_offset
     g.block_n, g.cta_group = block_n, cta_group
-    check(_lib.lib().vcb_gemm_bf16(C.byref(g), _stream()), "vcb_gemm_bf16")
-    return out
+    g._keepalive = (a, w, bias, out, gate, res, q_scale, k_scale, rope, out2)
+    return g, out
 
 
 def attention(qkv: torch.Tensor, B: int, L: int, heads: int, out: torch.Tensor, *, q_col: int, k_col: int, v_col: int,
