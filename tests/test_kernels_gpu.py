@@ -193,6 +193,44 @@ def test_gemm_qkv_epilogue(ops, block_n, cta_group):
 
 
 @pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("epi", ["qkv", "gelu", "gate"])
+def test_gemm_streamk_multiwave(ops, epi, cta_group):
+    """More tiles than CTA pairs and a non-integral wave count -> stream-K scheduling: tiles split along K between two
+    CTAs (fp32 partials through the workspace) must give the same result as the plain schedule, for every epilogue."""
+    M, K, H, heads = 3000, 512, 1024, 8
+    a = _randn(M, K, seed=1)
+    if epi == "qkv":
+        w = _randn(3 * H, K, seed=2, scale=1 / math.sqrt(K))
+        bias = _randn(3 * H, seed=3, dtype=torch.float32, scale=0.1)
+        qs, ks = (1 + 0.1 * _randn(128, seed=4, dtype=torch.float32)).to(BF16), (1 + 0.1 * _randn(128, seed=5, dtype=torch.float32)).to(BF16)
+        ang = _randn(M, 64, seed=6, dtype=torch.float32) * 3
+        cos, sin = torch.cos(ang), torch.sin(ang)
+        rope = torch.stack([cos, sin], -1).permute(1, 0, 2).contiguous()
+        out = torch.zeros(M, 3 * H, dtype=BF16, device="cuda")
+        ops.gemm(a.cuda(), w.cuda(), bias.cuda(), out, epilogue=ops.EPI_QKV, hidden=H, q_scale=qs.cuda(), k_scale=ks.cuda(),
+                 rope=rope.cuda(), cta_group=cta_group)
+        ref = _qkv_reference(a, w, bias, qs, ks, cos, sin, heads)
+        tol = 6e-3
+    else:
+        N = 3072
+        w = _randn(N, K, seed=2, scale=1 / math.sqrt(K))
+        bias = _randn(N, seed=3, dtype=torch.float32, scale=0.1)
+        lin = (a.float() @ w.float().T + bias).to(BF16)
+        if epi == "gelu":
+            out = torch.empty(M, N, dtype=BF16, device="cuda")
+            ops.gemm(a.cuda(), w.cuda(), bias.cuda(), out, epilogue=ops.EPI_BIAS_GELU, cta_group=cta_group)
+            ref = torch.nn.functional.gelu(lin, approximate="tanh")
+        else:
+            gate, x = _randn(1, N, seed=4), _randn(M, N, seed=5)
+            out = x.cuda().clone()
+            ops.gemm(a.cuda(), w.cuda(), bias.cuda(), out, epilogue=ops.EPI_GATE_RES, gate=gate.cuda(), res=out, cta_group=cta_group)
+            ref = x + gate * lin
+        tol = 4e-3
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu(), ref) < tol, _stats(out, ref)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
 def test_gemm_linear1_epilogue(ops, cta_group):
     """single-stream linear1: qkv columns get norm+rope, mlp columns get GELU into the linear2 input (layers.py:235-244)."""
     L, H, heads, mlp = 160, 256, 2, 512

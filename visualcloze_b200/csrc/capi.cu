@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 
 #include "../../include/vcb200.h"
@@ -24,6 +25,27 @@ namespace {
 
 struct Problem { CUtensorMap ta, tb; GemmParams p; };
 
+// stream-K scratch: one slot of 128 x 256 fp32 per CTA and one flag per CTA, per stream (launches on one stream are
+// ordered, so a single scratch per stream is enough); allocated on first use (call once before CUDA-graph capture)
+struct SkScratch { float* ws = nullptr; int* flags = nullptr; int epoch = 0; };
+inline SkScratch* sk_scratch(cudaStream_t st) {
+    static std::mutex mu;
+    static std::map<cudaStream_t, SkScratch> pool;
+    std::lock_guard<std::mutex> lk(mu);
+    SkScratch& s = pool[st];
+    if (!s.ws) {
+        const size_t n = 160;                                  // >= number of SMs
+        if (cudaMalloc(&s.ws, n * 128 * 256 * sizeof(float)) != cudaSuccess) return nullptr;
+        if (cudaMalloc(&s.flags, n * sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(s.flags, 0, n * sizeof(int));
+    }
+    return &s;
+}
+inline bool streamk_allowed() {
+    static const bool on = [] { const char* e = getenv("VCB_NO_STREAMK"); return !(e && atoi(e)); }();
+    return on;
+}
+
 template <int BN, int CG, int EPI>
 int launch_gemm_inst(const Problem& g0, const Problem& g1, cudaStream_t st) {
     const CUtensorMap& ta = g0.ta; const CUtensorMap& tb = g0.tb; const GemmParams& p = g0.p;
@@ -40,7 +62,15 @@ int launch_gemm_inst(const Problem& g0, const Problem& g1, cudaStream_t st) {
     if (g1.p.batch > 0) tiles += g1.p.batch * ((g1.p.rows_per_batch + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
     int clusters = num_sms() / CG;
     if (tiles < clusters) clusters = tiles;
-    cudaError_t e = launch_pdl(kern, dim3(clusters * CG), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, st, CG, ta, tb, p, g1.ta, g1.tb, g1.p);
+    // stream-K when there is more than one wave and it is not (nearly) integral: every CTA pair gets an equal share of
+    // the (tile, k-block) space; needs >= one tile's worth of k-blocks per pair so a tile is split at most in two
+    StreamKParams skp{nullptr, nullptr, 0, 0};
+    if (streamk_allowed() && tiles > clusters && tiles % clusters != 0 && num_sms() <= 160) {
+        SkScratch* sc = sk_scratch(st);
+        if (!sc) return set_error("gemm: stream-K scratch allocation failed");
+        skp.ws = sc->ws; skp.flags = sc->flags; skp.epoch = ++sc->epoch; skp.enabled = 1;
+    }
+    cudaError_t e = launch_pdl(kern, dim3(clusters * CG), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, st, CG, ta, tb, p, g1.ta, g1.tb, g1.p, skp);
     if (e != cudaSuccess) return set_error("gemm launch (BN=%d CG=%d EPI=%d): %s", BN, CG, EPI, cudaGetErrorString(e));
     count_launch();
     return 0;
@@ -216,7 +246,7 @@ int launch_conv_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     int grid = num_sms();
     if (tiles < grid) grid = tiles;
     GemmParams none{};
-    cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, st, 1, ta, tb, p, ta, tb, none);
+    cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, st, 1, ta, tb, p, ta, tb, none, StreamKParams{nullptr, nullptr, 0, 0});
     if (e != cudaSuccess) return set_error("conv3x3 launch: %s", cudaGetErrorString(e));
     count_launch();
     return 0;

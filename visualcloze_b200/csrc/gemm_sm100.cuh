@@ -66,6 +66,51 @@ struct GemmParams {
     int conv_H, conv_W, conv_C, conv_stride;
 };
 
+// Stream-K scheduling (optional): the (tile, k-block) space is cut into one contiguous, equal range per CTA (pair), so
+// no SM idles in a partial last wave.  A tile whose k range straddles two ranges is produced by two CTAs: the one holding
+// the TAIL part (its first work item) dumps fp32 partials to a workspace slot and raises a flag; the one holding the HEAD
+// part (its last work item) adds them in its epilogue.  The waiter only ever waits on another CTA's FIRST item, which
+// itself waits on nothing: deadlock-free.
+struct StreamKParams {
+    float* ws;              // [gridDim.x][128][BLOCK_N] fp32 partial accumulators (one slot per CTA)
+    int* flags;             // [gridDim.x]
+    int epoch;              // value that marks "partial of this launch is ready"
+    int enabled;
+};
+
+struct WorkIter {
+    bool sk;
+    int t, stride, num_tiles, num_kb;
+    long long u, u1;
+    __device__ __forceinline__ WorkIter(const StreamKParams& skp, int cluster_id, int num_clusters, int num_tiles_, int num_kb_)
+        : sk(skp.enabled != 0), t(cluster_id), stride(num_clusters), num_tiles(num_tiles_), num_kb(num_kb_) {
+        const long long U = (long long)num_tiles_ * num_kb_;
+        u = U * cluster_id / num_clusters;
+        u1 = U * (cluster_id + 1) / num_clusters;
+    }
+    __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
+        if (!sk) {
+            if (t >= num_tiles) return false;
+            tile = t; kb0 = 0; kb1 = num_kb; t += stride;
+            return true;
+        }
+        if (u >= u1) return false;
+        tile = (int)(u / num_kb);
+        kb0 = (int)(u - (long long)tile * num_kb);
+        const long long rem = u1 - u;
+        kb1 = rem < (long long)(num_kb - kb0) ? kb0 + (int)rem : num_kb;
+        u += kb1 - kb0;
+        return true;
+    }
+};
+
+VCB_DEVICE int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+VCB_DEVICE void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
@@ -103,11 +148,22 @@ VCB_DEVICE void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int n0, 
     }
 }
 
-VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, int n0, int N, float (&v)[32]) {
+VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, int n0, int N, float (&v)[32],
+                             const float* part = nullptr) {
     uint32_t r[32];
     __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge after predicated stores
     tmem_ld_x32(taddr, r);
     tmem_wait_ld();
+    if (part != nullptr) {                          // stream-K: add the other CTA's fp32 partial of these 32 columns
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 f = __ldcg(reinterpret_cast<const float4*>(part + q * 4));
+            r[q * 4 + 0] = __float_as_uint(__uint_as_float(r[q * 4 + 0]) + f.x);
+            r[q * 4 + 1] = __float_as_uint(__uint_as_float(r[q * 4 + 1]) + f.y);
+            r[q * 4 + 2] = __float_as_uint(__uint_as_float(r[q * 4 + 2]) + f.z);
+            r[q * 4 + 3] = __float_as_uint(__uint_as_float(r[q * 4 + 3]) + f.w);
+        }
+    }
     if (bias != nullptr && n0 + 32 <= N) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -133,7 +189,7 @@ template <int BLOCK_N, int kCtaGroup, int kEpi, int kAMode = A_MATRIX>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p, const __grid_constant__ CUtensorMap tmap_a1,
-                         const __grid_constant__ CUtensorMap tmap_b1, const GemmParams p1) {
+                         const __grid_constant__ CUtensorMap tmap_b1, const GemmParams p1, const StreamKParams skp) {
     // Grouped launch: an optional second problem (p1.batch > 0) with the same N, K and epilogue but its own operands --
     // the txt stream of a DoubleStreamBlock rides in the img stream's launch and fills its partial last wave.
     using Cfg = GemmCfg<BLOCK_N, kCtaGroup>;
@@ -201,7 +257,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+            WorkIter it(skp, cluster_id, num_clusters, num_tiles, num_kb);
+            int t, kb0, kb1;
+            while (it.next(t, kb0, kb1)) {
                 const bool g1 = t >= tiles0;
                 const int tt = g1 ? t - tiles0 : t, nm = g1 ? num_m1 : num_m, mps = g1 ? m_per_sample1 : m_per_sample;
                 const CUtensorMap* ta = g1 ? &tmap_a1 : &tmap_a;
@@ -210,7 +268,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const int bi = mt / mps;
                 const int m0 = (mt % mps) * tile_m + (int)cta_rank * kBlockM;
                 const int n0 = (tt / nm) * BLOCK_N + (int)cta_rank * Cfg::kBRows;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (is_leader) mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes * kCtaGroup);
                     if constexpr (kAMode == A_CONV3X3) {
@@ -242,11 +300,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+            WorkIter it(skp, cluster_id, num_clusters, num_tiles, num_kb);
+            int t, kb0, kb1;
+            while (it.next(t, kb0, kb1)) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes), 16, 1024, kSwizzle128B);
@@ -256,10 +316,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                             // advance 16 bf16 = 32 B inside the 128B swizzle span: +2 in the (addr >> 4) field
                             umma_ss<kCtaGroup>(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                                               (kb | k) != 0 ? 1u : 0u);
+                                               (kb > kb0 || k != 0) ? 1u : 0u);
                         }
                         umma_commit<kCtaGroup>(&empty_bar[stage]);
-                        if (kb == num_kb - 1) umma_commit<kCtaGroup>(&tmem_full[acc]);
+                        if (kb == kb1 - 1) umma_commit<kCtaGroup>(&tmem_full[acc]);
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -276,9 +336,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         constexpr int kHalfN = BLOCK_N / 2;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        WorkIter it(skp, cluster_id, num_clusters, num_tiles, num_kb);
+        int t, kb0, kb1;
+        const int my_cta = cluster_id * kCtaGroup + (int)cta_rank;
+        while (it.next(t, kb0, kb1)) {
             const bool g1 = t >= tiles0;
             const GemmParams& P = g1 ? p1 : p;
+            const bool sk_contrib = kb0 > 0;                       // tail part of a split tile: dump partials, no epilogue
+            const bool sk_final = !sk_contrib && kb1 < num_kb;     // head part: add the partner's partials, then epilogue
             const int tt = g1 ? t - tiles0 : t, nm = g1 ? num_m1 : num_m, mps = g1 ? m_per_sample1 : m_per_sample;
             const int mt = tt % nm;
             const int b = mt / mps;
@@ -301,6 +366,44 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * Cfg::kAccStride;
 
+            const float* part = nullptr;                            // my row of the partner's partial accumulator
+            if (sk_contrib) {
+                // dump this CTA's raw fp32 accumulator rows into its workspace slot, then publish
+                float* slot = skp.ws + ((long long)my_cta * kBlockM + row_in_tile) * BLOCK_N;
+#pragma unroll 1
+                for (int c = 0; c < kHalfN / 32; ++c) {
+                    const int cc = half * (kHalfN / 32) + c;
+                    uint32_t r[32];
+                    __syncwarp();
+                    tmem_ld_x32(taddr + cc * 32, r);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4)
+                        *reinterpret_cast<uint4*>(slot + cc * 32 + q4 * 4) = make_uint4(r[q4 * 4], r[q4 * 4 + 1], r[q4 * 4 + 2], r[q4 * 4 + 3]);
+                }
+                __threadfence();
+                named_bar_sync(1, 256);                             // all 8 epilogue warps have written and fenced
+                if (warp == 2 && lane == 0) st_release_gpu(skp.flags + my_cta, skp.epoch);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
+                    else mbar_arrive(&tmem_empty[acc]);
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
+            if (sk_final) {
+                // the partner (next CTA pair, same rank) produced its part as its FIRST work item
+                const int partner = my_cta + kCtaGroup;
+                if (lane == 0) {
+                    while (ld_acquire_gpu(skp.flags + partner) != skp.epoch) {
+                    }
+                }
+                __syncwarp();
+                part = skp.ws + ((long long)partner * kBlockM + row_in_tile) * BLOCK_N;
+            }
+
             if constexpr (kEpi == EPI_BIAS_F32) {
 #pragma unroll 1
                 for (int c = 0; c < kHalfN / 32; ++c) {
@@ -311,6 +414,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     __syncwarp();
                     tmem_ld_x32(taddr + cc * 32, r);
                     tmem_wait_ld();
+                    if (part != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldcg(part + cc * 32 + j));
+                    }
                     if (row_ok) {
                         float* dst = reinterpret_cast<float*>(P.out) + orow * P.ldo + P.out_col_offset + n0;
 #pragma unroll
@@ -333,7 +440,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const int n0 = n_tile0 + cc * 32;
                     if (n0 >= P.N) break;
                     float v[32];
-                    load_acc_bias(taddr + cc * 32, P.bias, n0, P.N, v);
+                    load_acc_bias(taddr + cc * 32, P.bias, n0, P.N, v, part ? part + cc * 32 : nullptr);
                     if (row_ok) {
                         if constexpr (kEpi == EPI_BIAS_GELU) {
 #pragma unroll
@@ -379,7 +486,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         for (int c = 0; c < 4; ++c) {
                             const int n0 = ng + c * 32;
                             float v[32];
-                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v);
+                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v, part ? part + hg * 128 + c * 32 : nullptr);
                             if (!row_ok) {
                             } else if (kEpi == EPI_LINEAR1 && region >= 3) {
 #pragma unroll
@@ -395,7 +502,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll 1
                         for (int c = 0; c < 4; ++c) {
                             float v[32];
-                            load_acc_bias(tg + c * 32, P.bias, ng + c * 32, P.N, v);
+                            load_acc_bias(tg + c * 32, P.bias, ng + c * 32, P.N, v, part ? part + hg * 128 + c * 32 : nullptr);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
                         }
@@ -408,7 +515,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         for (int c = 0; c < 4; ++c) {
                             const int n0 = ng + c * 32;
                             float v[32];
-                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v);
+                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v, part ? part + hg * 128 + c * 32 : nullptr);
                             if (row_ok) {
                                 uint32_t sw[16];
 #pragma unroll
