@@ -65,7 +65,9 @@ int launch_gemm_inst(const Problem& g0, const Problem& g1, cudaStream_t st) {
     // stream-K when there is more than one wave and it is not (nearly) integral: every CTA pair gets an equal share of
     // the (tile, k-block) space; needs >= one tile's worth of k-blocks per pair so a tile is split at most in two
     StreamKParams skp{nullptr, nullptr, 0, 0};
-    if (streamk_allowed() && tiles > clusters && tiles % clusters != 0 && num_sms() <= 160) {
+    const int rem = tiles % clusters;
+    // tail tiles are split at most kSkMaxParts ways: needs rem * (kSkMaxParts - 1) >= clusters (else keep the plain tail)
+    if (streamk_allowed() && tiles > clusters && rem != 0 && rem * (kSkMaxParts - 1) >= clusters && num_sms() <= 160) {
         SkScratch* sc = sk_scratch(st);
         if (!sc) return set_error("gemm: stream-K scratch allocation failed");
         skp.ws = sc->ws; skp.flags = sc->flags; skp.epoch = ++sc->epoch; skp.enabled = 1;

@@ -66,11 +66,13 @@ struct GemmParams {
     int conv_H, conv_W, conv_C, conv_stride;
 };
 
-// Stream-K scheduling (optional): the (tile, k-block) space is cut into one contiguous, equal range per CTA (pair), so
-// no SM idles in a partial last wave.  A tile whose k range straddles two ranges is produced by two CTAs: the one holding
-// the TAIL part (its first work item) dumps fp32 partials to a workspace slot and raises a flag; the one holding the HEAD
-// part (its last work item) adds them in its epilogue.  The waiter only ever waits on another CTA's FIRST item, which
-// itself waits on nothing: deadlock-free.
+// Stream-K tail (optional): the tiles of the partial last wave are cut along K into one equal contiguous range per CTA
+// (pair), so no SM idles while a few CTAs finish whole tiles.  A split tile is produced by up to kSkMaxParts CTAs: the one
+// holding the HEAD k range (kb0 == 0) finalises; the others dump fp32 partials to their workspace slot and raise a flag.
+// A waiter only waits on CTAs with a larger index, whose contributing item is their FIRST item of the phase and waits on
+// nothing: deadlock-free.  (A fully contiguous stream-K over ALL tiles was measured 30 % slower: CTAs of one wave no
+// longer share B tiles, and the 100-200 MB operands stop fitting in L2.)
+constexpr int kSkMaxParts = 4;
 struct StreamKParams {
     float* ws;              // [gridDim.x][128][BLOCK_N] fp32 partial accumulators (one slot per CTA)
     int* flags;             // [gridDim.x]
@@ -79,24 +81,28 @@ struct StreamKParams {
 };
 
 struct WorkIter {
+    // phase 1: the full waves with the plain strided schedule (CTA pairs of one wave share B tiles in L2);
+    // phase 2 (stream-K only): the R = tiles % pairs tiles of the partial last wave are cut into equal contiguous
+    // (tile, k-block) ranges, one per CTA pair.
     bool sk;
-    int t, stride, num_tiles, num_kb;
+    int t, stride, full_tiles, num_tiles, num_kb;
     long long u, u1;
     __device__ __forceinline__ WorkIter(const StreamKParams& skp, int cluster_id, int num_clusters, int num_tiles_, int num_kb_)
         : sk(skp.enabled != 0), t(cluster_id), stride(num_clusters), num_tiles(num_tiles_), num_kb(num_kb_) {
-        const long long U = (long long)num_tiles_ * num_kb_;
+        full_tiles = sk ? (num_tiles_ / num_clusters) * num_clusters : num_tiles_;
+        const long long U = (long long)(num_tiles_ - full_tiles) * num_kb_;
         u = U * cluster_id / num_clusters;
         u1 = U * (cluster_id + 1) / num_clusters;
     }
     __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
-        if (!sk) {
-            if (t >= num_tiles) return false;
+        if (t < full_tiles) {
             tile = t; kb0 = 0; kb1 = num_kb; t += stride;
             return true;
         }
-        if (u >= u1) return false;
-        tile = (int)(u / num_kb);
-        kb0 = (int)(u - (long long)tile * num_kb);
+        if (!sk || u >= u1) return false;
+        const int lt = (int)(u / num_kb);
+        tile = full_tiles + lt;
+        kb0 = (int)(u - (long long)lt * num_kb);
         const long long rem = u1 - u;
         kb1 = rem < (long long)(num_kb - kb0) ? kb0 + (int)rem : num_kb;
         u += kb1 - kb0;
@@ -148,22 +154,11 @@ VCB_DEVICE void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int n0, 
     }
 }
 
-VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, int n0, int N, float (&v)[32],
-                             const float* part = nullptr) {
+VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, int n0, int N, float (&v)[32]) {
     uint32_t r[32];
     __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge after predicated stores
     tmem_ld_x32(taddr, r);
     tmem_wait_ld();
-    if (part != nullptr) {                          // stream-K: add the other CTA's fp32 partial of these 32 columns
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 f = __ldcg(reinterpret_cast<const float4*>(part + q * 4));
-            r[q * 4 + 0] = __float_as_uint(__uint_as_float(r[q * 4 + 0]) + f.x);
-            r[q * 4 + 1] = __float_as_uint(__uint_as_float(r[q * 4 + 1]) + f.y);
-            r[q * 4 + 2] = __float_as_uint(__uint_as_float(r[q * 4 + 2]) + f.z);
-            r[q * 4 + 3] = __float_as_uint(__uint_as_float(r[q * 4 + 3]) + f.w);
-        }
-    }
     if (bias != nullptr && n0 + 32 <= N) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -366,7 +361,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * Cfg::kAccStride;
 
-            const float* part = nullptr;                            // my row of the partner's partial accumulator
             if (sk_contrib) {
                 // dump this CTA's raw fp32 accumulator rows into its workspace slot, then publish
                 float* slot = skp.ws + ((long long)my_cta * kBlockM + row_in_tile) * BLOCK_N;
@@ -394,14 +388,38 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 continue;
             }
             if (sk_final) {
-                // the partner (next CTA pair, same rank) produced its part as its FIRST work item
-                const int partner = my_cta + kCtaGroup;
-                if (lane == 0) {
-                    while (ld_acquire_gpu(skp.flags + partner) != skp.epoch) {
+                // partners: the following CTA pairs (same rank) whose range starts inside this tile; each produced its part as
+                // the FIRST item of its phase 2.  Fold their fp32 partials into my TMEM accumulator, then run the normal epilogue.
+                const long long U = (long long)(num_tiles - it.full_tiles) * num_kb;
+                const long long tile_end = (long long)(t - it.full_tiles + 1) * num_kb;
+#pragma unroll 1
+                for (int pc = cluster_id + 1; pc < num_clusters && U * pc / num_clusters < tile_end; ++pc) {
+                    const int partner = pc * kCtaGroup + (int)cta_rank;
+                    if (lane == 0) {
+                        while (ld_acquire_gpu(skp.flags + partner) != skp.epoch) {
+                        }
                     }
+                    __syncwarp();
+                    const float* part = skp.ws + ((long long)partner * kBlockM + row_in_tile) * BLOCK_N;
+#pragma unroll 1
+                    for (int c = 0; c < kHalfN / 32; ++c) {
+                        const int cc = half * (kHalfN / 32) + c;
+                        uint32_t r[32];
+                        __syncwarp();
+                        tmem_ld_x32(taddr + cc * 32, r);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int q4 = 0; q4 < 8; ++q4) {
+                            const float4 f = __ldcg(reinterpret_cast<const float4*>(part + cc * 32 + q4 * 4));
+                            r[q4 * 4 + 0] = __float_as_uint(__uint_as_float(r[q4 * 4 + 0]) + f.x);
+                            r[q4 * 4 + 1] = __float_as_uint(__uint_as_float(r[q4 * 4 + 1]) + f.y);
+                            r[q4 * 4 + 2] = __float_as_uint(__uint_as_float(r[q4 * 4 + 2]) + f.z);
+                            r[q4 * 4 + 3] = __float_as_uint(__uint_as_float(r[q4 * 4 + 3]) + f.w);
+                        }
+                        tmem_st_x32(taddr + cc * 32, r);
+                    }
+                    tmem_wait_st();
                 }
-                __syncwarp();
-                part = skp.ws + ((long long)partner * kBlockM + row_in_tile) * BLOCK_N;
             }
 
             if constexpr (kEpi == EPI_BIAS_F32) {
@@ -414,10 +432,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     __syncwarp();
                     tmem_ld_x32(taddr + cc * 32, r);
                     tmem_wait_ld();
-                    if (part != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldcg(part + cc * 32 + j));
-                    }
                     if (row_ok) {
                         float* dst = reinterpret_cast<float*>(P.out) + orow * P.ldo + P.out_col_offset + n0;
 #pragma unroll
@@ -440,7 +454,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const int n0 = n_tile0 + cc * 32;
                     if (n0 >= P.N) break;
                     float v[32];
-                    load_acc_bias(taddr + cc * 32, P.bias, n0, P.N, v, part ? part + cc * 32 : nullptr);
+                    load_acc_bias(taddr + cc * 32, P.bias, n0, P.N, v);
                     if (row_ok) {
                         if constexpr (kEpi == EPI_BIAS_GELU) {
 #pragma unroll
@@ -486,7 +500,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         for (int c = 0; c < 4; ++c) {
                             const int n0 = ng + c * 32;
                             float v[32];
-                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v, part ? part + hg * 128 + c * 32 : nullptr);
+                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v);
                             if (!row_ok) {
                             } else if (kEpi == EPI_LINEAR1 && region >= 3) {
 #pragma unroll
@@ -502,7 +516,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll 1
                         for (int c = 0; c < 4; ++c) {
                             float v[32];
-                            load_acc_bias(tg + c * 32, P.bias, ng + c * 32, P.N, v, part ? part + hg * 128 + c * 32 : nullptr);
+                            load_acc_bias(tg + c * 32, P.bias, ng + c * 32, P.N, v);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
                         }
@@ -515,7 +529,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         for (int c = 0; c < 4; ++c) {
                             const int n0 = ng + c * 32;
                             float v[32];
-                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v, part ? part + hg * 128 + c * 32 : nullptr);
+                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v);
                             if (row_ok) {
                                 uint32_t sw[16];
 #pragma unroll
