@@ -67,7 +67,12 @@ int launch_gemm_inst(const Problem& g0, const Problem& g1, cudaStream_t st) {
     StreamKParams skp{nullptr, nullptr, 0, 0};
     const int rem = tiles % clusters;
     // tail tiles are split at most kSkMaxParts ways: needs rem * (kSkMaxParts - 1) >= clusters (else keep the plain tail)
-    if (streamk_allowed() && tiles > clusters && rem != 0 && rem * (kSkMaxParts - 1) >= clusters && num_sms() <= 160) {
+    // worth it only when the idle part of the last wave outweighs the partial dump / fold (~15 us): estimated saving =
+    // (1 - rem/pairs) x tile time, tile time ~ 0.31 us per 256-wide k-block at power-capped clocks
+    const int num_kb_h = (p.K + kBlockK - 1) / kBlockK;
+    const float saving_us = rem ? (1.0f - (float)rem / clusters) * num_kb_h * 0.31f * (BN / 256.0f) : 0.f;
+    if (streamk_allowed() && tiles > clusters && rem != 0 && rem * (kSkMaxParts - 1) >= clusters && saving_us > 20.f &&
+        num_sms() <= 160) {
         SkScratch* sc = sk_scratch(st);
         if (!sc) return set_error("gemm: stream-K scratch allocation failed");
         skp.ws = sc->ws; skp.flags = sc->flags; skp.epoch = ++sc->epoch; skp.enabled = 1;
