@@ -195,8 +195,8 @@ def test_gemm_qkv_epilogue(ops, block_n, cta_group):
 @pytest.mark.parametrize("cta_group", [1, 2])
 @pytest.mark.parametrize("epi", ["qkv", "gelu", "gate"])
 def test_gemm_streamk_multiwave(ops, epi, cta_group):
-    """More tiles than CTA pairs and a non-integral wave count -> stream-K scheduling: tiles split along K between two
-    CTAs (fp32 partials through the workspace) must give the same result as the plain schedule, for every epilogue."""
+    """More tiles than CTA pairs and a non-integral wave count.  With VCB_STREAMK=1 in the environment the partial last wave
+    is split along K (fp32 partials through the workspace); results must match the reference either way, for every epilogue."""
     M, K, H, heads = 3000, 512, 1024, 8
     a = _randn(M, K, seed=1)
     if epi == "qkv":
