@@ -363,3 +363,29 @@ def test_rope_table_and_euler(ops):
     ops.euler_update(x.cuda(), v.cuda(), float(dt.to(BF16)), xn, inp)
     assert torch.equal(xn.cpu(), ref), _stats(xn, ref)
     assert torch.equal(inp[:, :64].cpu(), ref) and float(inp[:, 64:].abs().max()) == 0
+
+
+def test_gemm_streamk_enabled_subprocess():
+    """The stream-K tail is off by default; run it explicitly in a child process (the switch is read once
+    per process) on a shape whose last wave is half empty, grouped and plain, and compare with fp32 matmul."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import math, sys, torch
+sys.path.insert(0, %r)
+from visualcloze_b200 import ops
+g = torch.Generator().manual_seed(0)
+M, N, K = 3968, 3072, 4096
+a = torch.randn(M, K, generator=g).bfloat16(); w = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16()
+bias = torch.randn(N, generator=g)
+out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+ops.gemm(a.cuda(), w.cuda(), bias.cuda(), out, cta_group=2, block_n=256)
+torch.cuda.synchronize()
+ref = (a.float() @ w.float().T + bias).bfloat16().float()
+err = float((out.float().cpu() - ref).norm() / ref.norm())
+assert err < 3e-3, err
+print("streamk ok", err)
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, VCB_STREAMK="1"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "streamk ok" in r.stdout, r.stdout + r.stderr
