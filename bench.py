@@ -296,6 +296,10 @@ def main():
         return
     pk = peaks()
     gemm_fl, attn_fl = flops_per_image(Li, Lt, nfe)
+    traffic = {}
+    tp = os.path.join(REPO, "profiles", "r01_ncu_traffic.json")       # committed ncu --set full capture (per-launch DRAM bytes)
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
     value = world * args.steps / (ms / 1000.0)
     out = {
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -305,11 +309,13 @@ def main():
                 "d2h_bytes_per_step": int(d2h)},
         "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all fused-epilogue GEMMs of one image)", "bound": "tensor",
                      "achieved": gemm_fl / (pms[0] / 1000.0) / 1e12, "peak": pk["tf"], "unit": "TFLOP/s",
-                     "frac": gemm_fl / (pms[0] / 1000.0) / 1e12 / pk["tf"], "traffic": None, "peak_source": pk["src"] + " sustained",
+                     "frac": gemm_fl / (pms[0] / 1000.0) / 1e12 / pk["tf"],
+                     "traffic": traffic.get("gemm", {}).get("avg_dram_bytes_per_launch"), "peak_source": pk["src"] + " sustained",
                      "launches": int(pl[0]), "avg_launch_ms": pms[0] / max(1, pl[0]), "flops_per_image": gemm_fl},
         "roofline_attention": {"kernel": "attn_fwd_tcgen05_kernel", "bound": "tensor", "achieved": attn_fl / (pms[1] / 1000.0) / 1e12,
                                "peak": pk["tf"], "unit": "TFLOP/s", "frac": attn_fl / (pms[1] / 1000.0) / 1e12 / pk["tf"],
-                               "launches": int(pl[1]), "avg_launch_ms": pms[1] / max(1, pl[1])},
+                               "launches": int(pl[1]), "avg_launch_ms": pms[1] / max(1, pl[1]),
+                               "traffic": traffic.get("attention", {}).get("avg_dram_bytes_per_launch")},
         "roofline_ln_modulate": {"kernel": "ln_modulate_kernel", "bound": "hbm", "unit": "GB/s", "peak": pk["hbm"],
                                  "launches": int(pl[2]), "avg_launch_ms": pms[2] / max(1, pl[2])},
         "kernel_time_share": {"gemm_ms": pms[0], "attention_ms": pms[1], "ln_modulate_ms": pms[2], "other_ms": pms[3]},
