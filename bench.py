@@ -177,6 +177,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="B", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "sp"],
+                    help="N>1: 'replicas' = one image per GPU (throughput, weak scaling; the default and the contract's line); "
+                         "'sp' = ONE image sharded by token rows over the N GPUs (latency, strong scaling; SURVEY.md 8f-2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -187,6 +190,11 @@ def main():
               "nfe": nfe, "batch_per_gpu": 1, "parallelism": f"replicas x{world} (no per-step collective; all_gather of result tiles)",
               "lora": "merged r=256", "l2": "per-evaluation working set is 24 GB of weights >> 126 MB L2 (no flush needed)"}
 
+    sp_mode = args.mode == "sp" and world > 1
+    if sp_mode:
+        config["parallelism"] = (f"sequence-parallel x{world}: one image, token rows sharded over the GPUs, attention all-to-alls fused "
+                                 "into the QKV-GEMM / attention epilogues as NVLink peer stores (no NCCL on the per-step path)")
+        config["batch_per_gpu"] = f"1/{world}"
     if args.impl == "reference":
         if rank != 0:
             return
@@ -230,7 +238,10 @@ def main():
     sampler = T.Sampler(T.create_transport("Linear", "velocity", do_shift=True))
     fn = sampler.sample_ode(sampling_method="euler", num_steps=num_steps, atol=1e-6, rtol=1e-3, reverse=False,
                             do_shift=do_shift, time_shifting_factor=1, strength=strength)
-    x_h, kw_h, Li, Lt = make_inputs(args.workload, 1234 + rank)
+    if sp_mode:
+        from visualcloze_b200.parallel import SequenceParallel
+        model.enable_sequence_parallel(SequenceParallel(timeout_ms=20000))
+    x_h, kw_h, Li, Lt = make_inputs(args.workload, 1234 + (0 if sp_mode else rank))
     pin = lambda t: t.pin_memory()
     x_h, kw_h = pin(x_h), {k: pin(v) for k, v in kw_h.items()}
     x_d, kw_d = x_h.to(dev), {k: v.to(dev) for k, v in kw_h.items()}
@@ -243,7 +254,7 @@ def main():
             tile = decoder.decode_packed(q, res // 16, gw * res // 16)
         else:
             tile = q
-        if world > 1:
+        if world > 1 and not sp_mode:     # sp: every rank holds the whole latent after the trajectory gather and decodes it
             out = torch.empty((world,) + tuple(tile.shape), dtype=tile.dtype, device=dev)
             dist.all_gather_into_tensor(out, tile.contiguous())
             return out
@@ -296,16 +307,19 @@ def main():
         return
     pk = peaks()
     gemm_fl, attn_fl = flops_per_image(Li, Lt, nfe)
+    if sp_mode:                       # rank 0's kernels did 1/W of the image's GEMM rows and attention heads
+        gemm_fl, attn_fl = gemm_fl / world, attn_fl / world
     traffic = {}
     tp = os.path.join(REPO, "profiles", "r01_ncu_traffic.json")       # committed ncu --set full capture (per-launch DRAM bytes)
     if os.path.exists(tp):
         traffic = json.load(open(tp))
-    value = world * args.steps / (ms / 1000.0)
+    jobs = 1 if sp_mode else world    # images per step over the whole job
+    value = jobs * args.steps / (ms / 1000.0)
     out = {
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic", "config": config, "clocks": clk, "gpu_launches": int(launches),
-        "e2e": {"value": world * args.steps / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sp_mode else "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clk, "gpu_launches": int(launches),
+        "e2e": {"value": jobs * args.steps / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
         "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all fused-epilogue GEMMs of one image)", "bound": "tensor",
                      "achieved": gemm_fl / (pms[0] / 1000.0) / 1e12, "peak": pk["tf"], "unit": "TFLOP/s",

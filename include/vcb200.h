@@ -22,7 +22,8 @@
 extern "C" {
 #endif
 
-#define VCB_ABI_VERSION 1
+#define VCB_ABI_VERSION 2
+#define VCB_SP_MAX 8          /* ranks of one sequence-parallel group (one NVSwitch domain) */
 
 /* ---- library ------------------------------------------------------------------------------ */
 int         vcb_abi_version(void);
@@ -74,6 +75,13 @@ typedef struct vcb_gemm_args {
     /* tuning: 0 = library heuristic */
     int32_t block_n;                 /* 64 / 128 / 192 / 256 */
     int32_t cta_group;               /* 1 or 2 (CTA pair, tcgen05 cta_group::2) */
+    /* sequence-parallel head routing (VCB_EPI_QKV / VCB_EPI_LINEAR1, one sample; sp_world <= 1 = off): token rows are
+       sharded over sp_world ranks and attention heads over the same ranks, so the epilogue stores the q/k/v columns of
+       head h directly into rank h / (heads / sp_world)'s peer-mapped buffer sp_out[rank] -- layout
+       [sp_world * rows, 3 * hidden / sp_world], row sp_row_offset + mapped output row -- over NVLink (fused all-to-all).
+       `out` is then unused for the q/k/v columns. */
+    int32_t sp_world, sp_row_offset;
+    void* sp_out[VCB_SP_MAX];
 } vcb_gemm_args;
 
 int vcb_gemm_bf16(const vcb_gemm_args* args, void* stream);
@@ -97,6 +105,13 @@ int vcb_conv3x3_nhwc(const void* x, const void* w, const float* bias, const void
 int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_col, int32_t v_col,
                       const int32_t* seqlens, int32_t B, int32_t L, int32_t heads,
                       void* out, int64_t ldo, int32_t out_col_offset, void* stream);
+
+/* Sequence-parallel variant (one sample, no padding): this rank attends `heads` heads over the L rows of
+ * ALL ranks held in its qkv buffer and stores query row r into out_peers[r / rows_per_rank] (peer-mapped, row
+ * r % rows_per_rank, columns out_col_offset + 128*h) over NVLink -- the return all-to-all fused into the epilogue. */
+int vcb_attention_fwd_sp(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_col, int32_t v_col, int32_t L,
+                         int32_t heads, void* const* out_peers, int32_t world, int32_t rows_per_rank, int64_t ldo,
+                         int32_t out_col_offset, void* stream);
 
 /* ---- AdaLN modulated LayerNorm (layers.py:163-164,191,195,234,257):
  *      y = bf16( bf16(1 + scale[b]) * LayerNorm(x) + shift[b] ), eps 1e-6, no affine; hidden % 256 == 0.
@@ -170,6 +185,35 @@ int vcb_flux_prepare(vcb_flux* f, void* workspace, int64_t workspace_bytes, int3
  * img [B*Li, in_channels] bf16 (latent || cond) -> out [B*Li, out_channels] bf16. */
 int vcb_flux_forward(vcb_flux* f, int32_t eval_idx, const void* img, int64_t ld_img, void* out, int64_t ld_out,
                      void* stream);
+
+/* ---- single-image sequence parallelism over NVLink peer memory (the reference has no multi-GPU
+ * inference; the join point is the attention call, layers.py:177-187 / 236-241) -----------------------------------
+ * W ranks (one process per GPU) each hold a full weight copy and 1/W of the txt rows and 1/W of the img rows of ONE
+ * sample.  Everything except attention is row-local.  For attention, rank s owns heads [s*heads/W, (s+1)*heads/W):
+ * the QKV GEMM epilogue scatters q/k/v by head into the owners' qkv buffers and the attention epilogue scatters its
+ * output rows back to the row owners' `cat` buffers, both as plain stores to cudaIpc-mapped peer memory; a flag
+ * barrier (system-scope release/acquire) separates the phases.  No NCCL call on the per-step path.
+ *
+ * vcb_peer_alloc / vcb_peer_open: zero-filled device memory that other processes on the node can map.  handle = 64 opaque bytes to
+ * pass to the peers (any host channel); vcb_peer_open maps a peer's allocation into this process (enables P2P). */
+int vcb_peer_alloc(int64_t bytes, void** ptr, void* handle64);
+int vcb_peer_open(const void* handle64, void** ptr);
+int vcb_peer_close(void* ptr);
+int vcb_peer_free(void* ptr);
+/* All-ranks barrier on `stream`: publishes epoch to every peer's flag word [rank] and waits until every peer has
+ * published >= epoch to ours.  flags[r] = rank r's int32[VCB_SP_MAX] flag array (peer-mapped for r != rank), zeroed
+ * before first use; epochs must increase by one per call, identically on all ranks.  err (device int32, local) is set
+ * to the epoch if a peer does not arrive within timeout_ms (the kernel then exits instead of hanging the GPU). */
+int vcb_sp_barrier(int32_t* const* flags, int32_t world, int32_t rank, int32_t epoch, int32_t* err, int32_t timeout_ms,
+                   void* stream);
+/* Shared buffers a rank must vcb_peer_alloc for Li_local + Lt_local rows: qkv [(W*L_local), 3*hidden/W] and
+ * cat [L_local, hidden + mlp_hidden], bf16. */
+int vcb_flux_sp_shared_bytes(const vcb_flux* f, int32_t Li_local, int32_t Lt_local, int64_t* qkv_bytes, int64_t* cat_bytes);
+/* Switch the engine to sequence-parallel mode (world == 1 switches back).  qkv/cat/flags: arrays [world] of the ranks'
+ * buffers as mapped in THIS process (entry [rank] is the local allocation).  vcb_flux_prepare / vcb_flux_forward then
+ * take LOCAL sizes: B == 1, Li = Li_local, Lt = Lt_local, ids / txt / img / out rows of this rank only, seqlens NULL. */
+int vcb_flux_sp_attach(vcb_flux* f, int32_t world, int32_t rank, void* const* qkv, void* const* cat, int32_t* const* flags,
+                       int32_t* err, int32_t timeout_ms);
 
 /* ---- VAE decoder (models/modules/autoencoder.py:183-259, 307-309; the pipeline's AutoencoderKL.decode, visualcloze.py:430)
  * NHWC bf16 activations; 3x3 convs as implicit tcgen05 GEMMs, GroupNorm(32)+swish, nearest-2x upsampling and the

@@ -138,6 +138,42 @@ def test_gather_tiles_world2_gloo(tmp_path):
     assert shard_samples(5, 1, 2) == [1, 3] and gather_tiles([torch.zeros(1, 2, 2)], 1)[0].shape == (1, 2, 2)
 
 
+_SP_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO"])
+from visualcloze_b200.parallel import sp_gather_rows, sp_row_slice, sp_shard_rows
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{os.environ['PORT']}", rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+g = torch.Generator().manual_seed(3)
+x = torch.randn(4, 1, 48, 8, generator=g)                 # [steps, B, Li, C] trajectory, identical on both ranks
+loc = sp_shard_rows(x, rank, 2, dim=2)
+assert loc.shape == (4, 1, 24, 8) and torch.equal(loc, x[:, :, 24 * rank: 24 * (rank + 1)])
+row_local = loc * 2 + 1                                    # any row-local computation (the Euler update is one)
+assert torch.equal(sp_gather_rows(row_local, dim=2), x * 2 + 1), "gathered rows differ from the unsharded computation"
+assert sp_row_slice(512, rank, 2) == slice(256 * rank, 256 * (rank + 1))
+try:
+    sp_row_slice(49, rank, 2); raise SystemExit("indivisible row count must be rejected")
+except ValueError:
+    pass
+dist.barrier(); dist.destroy_process_group(); print("ok", rank)
+"""
+
+
+def test_sequence_parallel_row_sharding_world2_gloo(tmp_path):
+    """host side of the single-image sequence-parallel mode: row shards of both streams, gather = inverse."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "w_sp.py"
+    script.write_text(_SP_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(os.environ, RANK=str(r), PORT=str(port), REPO=REPO),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    from visualcloze_b200 import parallel
+    with pytest.raises(RuntimeError, match="process group"):
+        parallel.SequenceParallel()
+
+
 def test_pipeline_host_helpers_match_einops_and_reference_rules():
     from einops import rearrange
     from PIL import Image

@@ -6,7 +6,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvcb200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
+SP_MAX = 8
 
 _lib = None
 
@@ -33,6 +34,7 @@ class GemmArgs(C.Structure):
         ("rope", C.c_void_p), ("rope_rows", C.c_int64),
         ("out2", C.c_void_p), ("ldo2", C.c_int64), ("out2_col_offset", C.c_int32),
         ("block_n", C.c_int32), ("cta_group", C.c_int32),
+        ("sp_world", C.c_int32), ("sp_row_offset", C.c_int32), ("sp_out", C.c_void_p * SP_MAX),
     ]
 
 
@@ -145,6 +147,17 @@ _OPTIONAL: dict = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
     "vcb_flux_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    # sequence-parallel single-image mode
+    "vcb_attention_fwd_sp": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    "vcb_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "vcb_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "vcb_peer_close": (C.c_int, [C.c_void_p]),
+    "vcb_peer_free": (C.c_int, [C.c_void_p]),
+    "vcb_sp_barrier": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vcb_flux_sp_shared_bytes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "vcb_flux_sp_attach": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), C.c_void_p, C.c_int32]),
 }
 
 

@@ -40,7 +40,7 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
             const int g = (int)(warp - 2) & 7;
             const int row = q0 + ((int)(warp - 2) >> 3) * kAttnTile + (int)(warp & 3) * 32 + (int)lane;
             if (row < p.L) {
-                uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)b * p.L + row) * p.ldo + p.out_col_offset + head * 128 + (g >> 2) * 64);
+                uint4* dst = reinterpret_cast<uint4*>(attn_out_row(p, b, row) + p.out_col_offset + head * 128 + (g >> 2) * 64);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
             }
@@ -180,7 +180,7 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         const uint32_t p_addr = tmem_base + lane_addr + t * 128 + half * 64;
         const uint32_t o_addr = tmem_base + lane_addr + 256 + t * 128 + half * 64;   // my 64 output columns
         const uint32_t bar_id = 1 + t * 4 + quarter;              // named barrier of this warp pair (64 threads)
-        __nv_bfloat16* dst = p.out + ((long long)b * p.L + row) * p.ldo + p.out_col_offset + head * 128 + half * 64;
+        __nv_bfloat16* dst = attn_out_row(p, b, row) + p.out_col_offset + head * 128 + half * 64;
         if (t == 1 && !tile1) {
             if (row < p.L) {
 #pragma unroll

@@ -25,7 +25,20 @@ struct AttnParams {
     int out_col_offset;
     int q_col, k_col, v_col;     // column of head 0 of q / k / v inside the qkv matrix
     float scale_log2;            // head_dim^-0.5 * log2(e)
+    // Sequence-parallel output routing (attn_fwd3 only, B == 1; sp_world <= 1 = off): query row r belongs to rank
+    // r / sp_rows and is stored over NVLink into that rank's peer-mapped buffer sp_out[rank] at row r % sp_rows.
+    int sp_world, sp_rows;
+    __nv_bfloat16* sp_out[8];
 };
+
+// first element of output row `row` of sample b (columns are added by the caller)
+VCB_DEVICE __nv_bfloat16* attn_out_row(const AttnParams& p, int b, int row) {
+    if (p.sp_world > 1) {
+        const int owner = min(row / p.sp_rows, p.sp_world - 1);
+        return p.sp_out[owner] + (long long)(row - owner * p.sp_rows) * p.ldo;
+    }
+    return p.out + ((long long)b * p.L + row) * p.ldo;
+}
 
 constexpr int kAttnThreads = 192;
 constexpr int kAttnTile = 128;           // query rows per CTA == kv rows per tile == head_dim

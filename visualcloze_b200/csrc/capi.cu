@@ -15,6 +15,7 @@
 #include "gemm_sm100.cuh"
 #include "host_util.cuh"
 #include "probe.cuh"
+#include "sp_sm100.cuh"
 
 using namespace vcb;
 
@@ -162,6 +163,13 @@ int check_gemm_args(const vcb_gemm_args* a) {
             return set_error("gemm: LINEAR1 epilogue needs out2");
         if (a->epilogue == VCB_EPI_QKV && a->N != 3 * a->hidden) return set_error("gemm: QKV epilogue needs N == 3*hidden");
     }
+    if (a->sp_world > 1) {
+        if (!head) return set_error("gemm: sp_world > 1 needs the QKV or LINEAR1 epilogue");
+        if (a->sp_world > VCB_SP_MAX || a->M != a->rows_per_batch || (a->hidden / 128) % a->sp_world || a->sp_row_offset < 0)
+            return set_error("gemm: sequence-parallel routing needs one sample, world <= %d and heads %% world == 0", VCB_SP_MAX);
+        for (int r = 0; r < a->sp_world; ++r)
+            if (!a->sp_out[r]) return set_error("gemm: sp_out[%d] is null", r);
+    }
     if (a->epilogue == VCB_EPI_GATE_RES && (!a->res || a->ld_res % 8 || a->gate_stride % 8))
         return set_error("gemm: GATE_RES epilogue needs res (gate may be NULL = ungated residual)");
     if (a->epilogue < 0 || a->epilogue > VCB_EPI_BIAS_F32) return set_error("gemm: unknown epilogue %d", a->epilogue);
@@ -186,6 +194,8 @@ int build_problem(const vcb_gemm_args* a, int bn, int cg, Problem* out) {
     p.hidden = a->hidden; p.q_scale = (const __nv_bfloat16*)a->q_scale; p.k_scale = (const __nv_bfloat16*)a->k_scale;
     p.rope = (const float2*)a->rope; p.rope_rows = a->rope_rows;
     p.out2 = (__nv_bfloat16*)a->out2; p.ldo2 = a->ldo2; p.out2_col_offset = a->out2_col_offset;
+    p.sp_world = a->sp_world > 1 ? a->sp_world : 0; p.sp_row_offset = a->sp_row_offset;
+    for (int r = 0; r < kSpMaxRanks; ++r) p.sp_out[r] = r < p.sp_world ? (__nv_bfloat16*)a->sp_out[r] : nullptr;
     if (int rc = make_tmap_3d(&out->ta, a->A, (uint64_t)a->K, (uint64_t)a->rows_per_batch, (uint64_t)batch, (uint64_t)a->lda,
                               (uint64_t)a_bstride, 64, 128)) return rc;
     if (int rc = make_tmap_2d(&out->tb, a->W, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldw, 64, (uint32_t)(bn / cg))) return rc;
@@ -297,10 +307,11 @@ extern "C" int vcb_conv3x3_nhwc(const void* x, const void* w, const float* bias,
 // ------------------------------------------------------------------------------------------------
 // attention
 // ------------------------------------------------------------------------------------------------
-extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_col, int32_t v_col,
-                                 const int32_t* seqlens, int32_t B, int32_t L, int32_t heads, void* out, int64_t ldo,
-                                 int32_t out_col_offset, void* stream) {
-    if (!qkv || !out || B <= 0 || L <= 0 || heads <= 0) return set_error("attention: bad arguments");
+namespace {
+int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_col, int32_t v_col,
+                     const int32_t* seqlens, int32_t B, int32_t L, int32_t heads, void* out, int64_t ldo,
+                     int32_t out_col_offset, void* const* out_peers, int32_t world, int32_t rows_per_rank, void* stream) {
+    if (!qkv || (!out && !out_peers) || B <= 0 || L <= 0 || heads <= 0) return set_error("attention: bad arguments");
     if (ld_qkv % 8 || ldo % 8 || q_col % 8 || k_col % 8 || v_col % 8 || out_col_offset % 8)
         return set_error("attention: leading dims / column offsets must be multiples of 8");
     if (int rc = ensure_device()) return rc;
@@ -326,6 +337,16 @@ extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col,
     p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.out_col_offset = out_col_offset;
     p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
     p.scale_log2 = 0.08838834764831845f * 1.4426950408889634f;     // 128^-0.5 * log2(e)
+    if (out_peers) {
+        if (world < 2 || world > VCB_SP_MAX || B != 1 || seqlens || rows_per_rank <= 0 || (int64_t)rows_per_rank * world != L)
+            return set_error("attention (sp): needs one unpadded sample with L == world * rows_per_rank, 2 <= world <= %d", VCB_SP_MAX);
+        if (use_v1 || use_v2) return set_error("attention (sp): only the default kernel (attn_fwd3) routes to peers");
+        p.sp_world = world; p.sp_rows = rows_per_rank;
+        for (int r = 0; r < world; ++r) {
+            if (!out_peers[r]) return set_error("attention (sp): out_peers[%d] is null", r);
+            p.sp_out[r] = (__nv_bfloat16*)out_peers[r];
+        }
+    }
     ProfScope prof(PROF_ATTN, stream);
     if (use_v1) {
         dim3 grid((L + kAttnTile - 1) / kAttnTile, heads, B);
@@ -339,6 +360,89 @@ extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col,
         return 0;
     }
     return check_launch("attention");
+}
+}  // namespace
+
+extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_col, int32_t v_col,
+                                 const int32_t* seqlens, int32_t B, int32_t L, int32_t heads, void* out, int64_t ldo,
+                                 int32_t out_col_offset, void* stream) {
+    if (!out) return set_error("attention: bad arguments");
+    return attention_launch(qkv, ld_qkv, q_col, k_col, v_col, seqlens, B, L, heads, out, ldo, out_col_offset, nullptr, 0, 0, stream);
+}
+
+extern "C" int vcb_attention_fwd_sp(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_col, int32_t v_col, int32_t L,
+                                    int32_t heads, void* const* out_peers, int32_t world, int32_t rows_per_rank, int64_t ldo,
+                                    int32_t out_col_offset, void* stream) {
+    if (!out_peers) return set_error("attention (sp): out_peers is null");
+    return attention_launch(qkv, ld_qkv, q_col, k_col, v_col, nullptr, 1, L, heads, nullptr, ldo, out_col_offset, out_peers, world,
+                            rows_per_rank, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sequence-parallel plumbing: peer-mappable allocations (CUDA IPC) and the cross-GPU phase barrier
+// ------------------------------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "vcb_peer_alloc hands out 64-byte handles");
+
+extern "C" int vcb_peer_alloc(int64_t bytes, void** ptr, void* handle64) {
+    if (bytes <= 0 || !ptr || !handle64) return set_error("peer_alloc: bad arguments");
+    if (int rc = ensure_device()) return rc;
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, (size_t)bytes);
+    if (e != cudaSuccess) return set_error("peer_alloc: cudaMalloc(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+    e = cudaMemset(d, 0, (size_t)bytes);                  // flag arrays must start at zero; synchronous on return
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return set_error("peer_alloc: cudaMemset: %s", cudaGetErrorString(e));
+    }
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, d);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return set_error("peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, 64);
+    *ptr = d;
+    return 0;
+}
+
+extern "C" int vcb_peer_open(const void* handle64, void** ptr) {
+    if (!handle64 || !ptr) return set_error("peer_open: bad arguments");
+    if (int rc = ensure_device()) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* d = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return set_error("peer_open: cudaIpcOpenMemHandle: %s (peer access between the two GPUs is required)", cudaGetErrorString(e));
+    *ptr = d;
+    return 0;
+}
+
+extern "C" int vcb_peer_close(void* ptr) {
+    if (!ptr) return 0;
+    cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    return e == cudaSuccess ? 0 : set_error("peer_close: %s", cudaGetErrorString(e));
+}
+
+extern "C" int vcb_peer_free(void* ptr) {
+    if (!ptr) return 0;
+    cudaError_t e = cudaFree(ptr);
+    return e == cudaSuccess ? 0 : set_error("peer_free: %s", cudaGetErrorString(e));
+}
+
+extern "C" int vcb_sp_barrier(int32_t* const* flags, int32_t world, int32_t rank, int32_t epoch, int32_t* err, int32_t timeout_ms,
+                              void* stream) {
+    if (!flags || !err || world < 1 || world > VCB_SP_MAX || rank < 0 || rank >= world) return set_error("sp_barrier: bad arguments");
+    if (int rc = ensure_device()) return rc;
+    SpFlags f{};
+    for (int r = 0; r < world; ++r) {
+        if (!flags[r]) return set_error("sp_barrier: flags[%d] is null", r);
+        f.f[r] = flags[r];
+    }
+    ProfScope prof(PROF_OTHER, stream);
+    // plain (fully serialised) launch: every earlier kernel of the stream has completed, so its peer stores are performed
+    sp_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, world, rank, epoch, err, (unsigned long long)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull);
+    return check_launch("sp_barrier");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -30,6 +30,12 @@ struct vcb_flux {
              *qkv = nullptr, *cat = nullptr;
     std::vector<uint16_t*> mod_dbl;   // [depth * 2] (img, txt), each [E*B, 6H]
     std::vector<uint16_t*> mod_sgl;   // [depth_single], each [E*B, 3H]
+    // sequence-parallel mode (vcb_flux_sp_attach): W ranks share one sample; qkv / cat live in peer-mapped buffers
+    int sp_world = 1, sp_rank = 0, sp_epoch = 0, sp_timeout_ms = 2000;
+    void* sp_qkv[VCB_SP_MAX] = {};
+    void* sp_cat[VCB_SP_MAX] = {};
+    int32_t* sp_flags[VCB_SP_MAX] = {};
+    int32_t* sp_err = nullptr;
 };
 
 namespace {
@@ -66,8 +72,10 @@ int64_t carve(vcb_flux* f, uint8_t* base, int B, int Li, int Lt, int E) {
     uint16_t* mod_final = cv.take<uint16_t>(EB * 2 * H);
     uint16_t* x = cv.take<uint16_t>((int64_t)B * L * H);
     uint16_t* xm = cv.take<uint16_t>((int64_t)B * L * H);
-    uint16_t* qkv = cv.take<uint16_t>((int64_t)B * L * 3 * H);
-    uint16_t* cat = cv.take<uint16_t>((int64_t)B * L * (H + c.mlp_hidden));
+    // sequence-parallel: qkv [W*L, 3H/W] and cat [L, H+mlp] are the caller's peer-mapped allocations (same sizes)
+    const bool sp = f->sp_world > 1;
+    uint16_t* qkv = sp ? static_cast<uint16_t*>(f->sp_qkv[f->sp_rank]) : cv.take<uint16_t>((int64_t)B * L * 3 * H);
+    uint16_t* cat = sp ? static_cast<uint16_t*>(f->sp_cat[f->sp_rank]) : cv.take<uint16_t>((int64_t)B * L * (H + c.mlp_hidden));
     if (base) {
         f->rope = rope; f->txt0 = txt0; f->temb_t = temb_t; f->temb_g = temb_g; f->h1 = h1; f->e_time = e_time;
         f->e_guid = e_guid; f->e_vec = e_vec; f->vec = vec; f->svec = svec; f->mod_dbl = md; f->mod_sgl = ms;
@@ -118,6 +126,34 @@ extern "C" int64_t vcb_flux_workspace_bytes(const vcb_flux* f, int32_t B, int32_
     return carve(const_cast<vcb_flux*>(f), nullptr, B, Li, Lt, n_evals);
 }
 
+extern "C" int vcb_flux_sp_shared_bytes(const vcb_flux* f, int32_t Li_local, int32_t Lt_local, int64_t* qkv_bytes, int64_t* cat_bytes) {
+    if (!f || Li_local <= 0 || Lt_local < 0 || !qkv_bytes || !cat_bytes) return set_error("flux_sp_shared_bytes: bad arguments");
+    const int64_t L = (int64_t)Li_local + Lt_local, H = f->cfg.hidden;
+    *qkv_bytes = L * 3 * H * 2;                       // [W * L, 3H / W] bf16
+    *cat_bytes = L * (H + f->cfg.mlp_hidden) * 2;
+    return 0;
+}
+
+extern "C" int vcb_flux_sp_attach(vcb_flux* f, int32_t world, int32_t rank, void* const* qkv, void* const* cat,
+                                  int32_t* const* flags, int32_t* err, int32_t timeout_ms) {
+    if (!f) return set_error("flux_sp_attach: null engine");
+    f->prepared = false;
+    if (world <= 1) {
+        f->sp_world = 1; f->sp_rank = 0;
+        return 0;
+    }
+    if (world > VCB_SP_MAX || rank < 0 || rank >= world || !qkv || !cat || !flags || !err)
+        return set_error("flux_sp_attach: bad arguments (world <= %d)", VCB_SP_MAX);
+    if (f->cfg.heads % world) return set_error("flux_sp_attach: heads (%d) must be a multiple of world (%d)", f->cfg.heads, world);
+    for (int r = 0; r < world; ++r) {
+        if (!qkv[r] || !cat[r] || !flags[r]) return set_error("flux_sp_attach: null buffer for rank %d", r);
+        f->sp_qkv[r] = qkv[r]; f->sp_cat[r] = cat[r]; f->sp_flags[r] = flags[r];
+    }
+    f->sp_world = world; f->sp_rank = rank; f->sp_err = err; f->sp_epoch = 0;
+    f->sp_timeout_ms = timeout_ms > 0 ? timeout_ms : 2000;
+    return 0;
+}
+
 extern "C" int vcb_flux_prepare(vcb_flux* f, void* workspace, int64_t workspace_bytes, int32_t B, int32_t Li, int32_t Lt,
                                 int32_t n_evals, const void* txt, const void* y, const float* ids, const float* t_scaled,
                                 const float* g_scaled, const float* freqs, const int32_t* seqlens, void* stream) {
@@ -125,6 +161,7 @@ extern "C" int vcb_flux_prepare(vcb_flux* f, void* workspace, int64_t workspace_
     if (B <= 0 || Li <= 0 || Lt <= 0 || n_evals <= 0) return set_error("flux_prepare: bad sizes");
     const vcb_flux_config& c = f->cfg;
     if (c.guidance_embed && !g_scaled) return set_error("Didn't get guidance strength for guidance distilled model.");
+    if (f->sp_world > 1 && (B != 1 || seqlens)) return set_error("flux_prepare: sequence-parallel mode takes one unpadded sample (B == 1, seqlens NULL)");
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return set_error("flux_prepare: workspace must be 256-byte aligned");
     const int64_t need = carve(f, nullptr, B, Li, Lt, n_evals);
     if (workspace_bytes < need) return set_error("flux_prepare: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
@@ -188,7 +225,25 @@ vcb_gemm_args stream_args(const vcb_flux* f, const StreamView& sv, const uint16_
     g.gate = gate; g.gate_stride = gate_stride; g.res = out; g.ld_res = ldo;
     g.hidden = f->cfg.hidden; g.q_scale = q_scale; g.k_scale = k_scale; g.rope = f->rope; g.rope_rows = (int64_t)f->B * f->L;
     g.out2 = out2; g.ldo2 = ldo2; g.out2_col_offset = out2_col;
+    if (f->sp_world > 1 && (epi == VCB_EPI_QKV || epi == VCB_EPI_LINEAR1)) {
+        g.sp_world = f->sp_world; g.sp_row_offset = f->sp_rank * f->L;
+        for (int r = 0; r < f->sp_world; ++r) g.sp_out[r] = f->sp_qkv[r];
+    }
     return g;
+}
+
+// attention over the joint sequence; sequence-parallel: barrier, attention of this rank's heads over all ranks' rows with
+// the output rows scattered back to their owners, barrier
+int joint_attention(vcb_flux* f, int64_t ldc, void* stream) {
+    const vcb_flux_config& c = f->cfg;
+    const int H = c.hidden;
+    if (f->sp_world <= 1) return vcb_attention_fwd(f->qkv, 3 * H, 0, H, 2 * H, f->seqlens, f->B, f->L, c.heads, f->cat, ldc, 0, stream);
+    const int W = f->sp_world, hw = H / W;
+    int rc;
+    if ((rc = vcb_sp_barrier(f->sp_flags, W, f->sp_rank, ++f->sp_epoch, f->sp_err, f->sp_timeout_ms, stream))) return rc;
+    if ((rc = vcb_attention_fwd_sp(f->qkv, 3 * hw, 0, hw, 2 * hw, W * f->L, c.heads / W, f->sp_cat, W, f->L, ldc, f->sp_rank * hw, stream)))
+        return rc;
+    return vcb_sp_barrier(f->sp_flags, W, f->sp_rank, ++f->sp_epoch, f->sp_err, f->sp_timeout_ms, stream);
 }
 
 int stream_gemm(const vcb_flux* f, const StreamView& sv, const uint16_t* a_buf, int64_t lda, int a_col, int K,
@@ -254,7 +309,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
                                    sw[s]->q_scale, sw[s]->k_scale, nullptr, 0, 0);
             if ((rc = vcb_gemm_bf16_grouped(&g[0], &g[1], stream))) return rc;
         }
-        if ((rc = vcb_attention_fwd(f->qkv, 3 * H, 0, H, 2 * H, f->seqlens, B, L, c.heads, f->cat, ldc, 0, stream))) return rc;
+        if ((rc = joint_attention(f, ldc, stream))) return rc;
         {
             vcb_gemm_args g[2];
             for (int s = 0; s < 2; ++s)
@@ -286,7 +341,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
         if ((rc = stream_ln(f, s_all, mod + 0, mod + H, 3 * H, stream))) return rc;
         if ((rc = stream_gemm(f, s_all, f->xm, H, 0, H, w.linear1, 3 * H + mlp, VCB_EPI_LINEAR1, f->qkv, 3 * H, 0, nullptr, 0,
                               nullptr, w.q_scale, w.k_scale, f->cat, ldc, H, stream))) return rc;
-        if ((rc = vcb_attention_fwd(f->qkv, 3 * H, 0, H, 2 * H, f->seqlens, B, L, c.heads, f->cat, ldc, 0, stream))) return rc;
+        if ((rc = joint_attention(f, ldc, stream))) return rc;
         if ((rc = stream_gemm(f, s_all, f->cat, ldc, 0, H + mlp, w.linear2, H, VCB_EPI_GATE_RES, f->x, H, 0, mod + 2 * H, 3 * H,
                               nullptr, nullptr, nullptr, nullptr, 0, 0, stream))) return rc;
     }

@@ -31,6 +31,7 @@ enum GemmEpilogue : int {
 // patch loaded by ONE 4-D TMA box at the tap's (dx, dy) shift -- out-of-image pixels are zero-filled by the TMA unit,
 // which is exactly the conv's zero padding.
 enum GemmAMode : int { A_MATRIX = 0, A_CONV3X3 = 1 };
+constexpr int kSpMaxRanks = 8;
 constexpr int kConvTileW = 16, kConvTileH = 8;
 
 struct GemmParams {
@@ -64,6 +65,11 @@ struct GemmParams {
     // conv_stride 1 (pad 1 all round) or 2 (pad right/bottom only, autoencoder.py:91-95): for stride 2 the tensor map carries
     // elementStrides = 2, so one box still lands as a dense 16 x 8 pixel patch; coordinates are in input pixels.
     int conv_H, conv_W, conv_C, conv_stride;
+    // Sequence-parallel head routing (EPI_QKV / EPI_LINEAR1, batch == 1; sp_world <= 1 = off).  Token rows are sharded over
+    // sp_world ranks, heads over the same ranks for attention: the q/k/v columns of head h are stored straight into rank
+    // h / (heads/W)'s peer-mapped qkv buffer [W * rows, 3 * hidden / W] over NVLink, at row sp_row_offset + output row.
+    int sp_world, sp_row_offset;
+    __nv_bfloat16* sp_out[kSpMaxRanks];
 };
 
 // Stream-K tail (optional): the tiles of the partial last wave are cut along K into one equal contiguous range per CTA
@@ -495,6 +501,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     if (ng >= P.N) break;
                     const uint32_t tg = taddr + hg * 128;
                     const int region = ng / P.hidden;            // 0 q, 1 k, 2 v, >= 3 mlp (LINEAR1)
+                    // destination of this head's 128 q / k / v columns: the local qkv buffer, or (sequence-parallel) the
+                    // qkv buffer of the rank that owns the head -- plain stores to a peer-mapped address travel over NVLink
+                    __nv_bfloat16* qkv_dst;
+                    if (P.sp_world > 1 && region < 3) {
+                        const int hw = P.hidden / P.sp_world;    // q (or k, v) columns per rank
+                        const int cin = ng - region * P.hidden;
+                        const int owner = cin / hw;
+                        qkv_dst = P.sp_out[owner] + (orow + P.sp_row_offset) * (3LL * hw) + region * hw + (cin - owner * hw);
+                    } else {
+                        qkv_dst = P.out + orow * P.ldo + P.out_col_offset + ng;
+                    }
                     if (region >= 2) {
 #pragma unroll 1
                         for (int c = 0; c < 4; ++c) {
@@ -507,7 +524,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                 for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
                                 store_bf16x32(P.out2 + orow * P.ldo2 + P.out2_col_offset + (n0 - 3 * P.hidden), v, n0, P.N);
                             } else {
-                                store_bf16x32(P.out + orow * P.ldo + P.out_col_offset + n0, v, n0, P.N);
+                                store_bf16x32(qkv_dst + c * 32, v, n0, P.N);
                             }
                         }
                     } else {
@@ -548,7 +565,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                     v[j] = __fadd_rn(__fmul_rn(cs.x, x0), __fmul_rn(-cs.y, x1));
                                     v[j + 1] = __fadd_rn(__fmul_rn(cs.y, x0), __fmul_rn(cs.x, x1));
                                 }
-                                store_bf16x32(P.out + orow * P.ldo + P.out_col_offset + n0, v, n0, P.N);
+                                store_bf16x32(qkv_dst + c * 32, v, n0, P.N);
                             }
                         }
                     }

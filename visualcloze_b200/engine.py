@@ -41,7 +41,20 @@ class FluxEngine:
             self._build()
         self._ws = None
         self._shape = None
+        self._sp = None
         self._freqs = _freqs().to(self.device)
+
+    # ---- single-image sequence parallelism -------------------------------------------
+    def enable_sequence_parallel(self, sp) -> None:
+        """``sp``: a ``parallel.SequenceParallel`` (or None to switch back).  Every rank then passes the FULL txt / ids to
+        ``prepare`` (identical on all ranks) and its LOCAL img rows (``sp.shard``) to ``forward``."""
+        if sp is not None and self.params.num_heads % sp.world:
+            raise ValueError(f"num_heads ({self.params.num_heads}) must be a multiple of the sequence-parallel world size ({sp.world})")
+        if sp is None and self._sp is not None:
+            check(self.lib.vcb_flux_sp_attach(self._h, 1, 0, None, None, None, None, 0), "vcb_flux_sp_attach")
+            self._sp.release()
+        self._sp = sp if (sp is not None and sp.world > 1) else None
+        self._shape = None
 
     # ---- weight packing -----------------------------------------------------------------------
     def _linear(self, name: str) -> LinearW:
@@ -121,6 +134,18 @@ class FluxEngine:
         E = int(timesteps.shape[0])
         dev = self.device
         st = torch.cuda.current_stream().cuda_stream
+        sp = self._sp
+        if sp is not None:
+            # one unpadded sample, rows of both streams split evenly over the ranks; ``n_img_tokens`` is the FULL count
+            if B != 1:
+                raise ValueError("sequence-parallel mode shares ONE sample across the ranks (batch must be 1)")
+            for m in (txt_mask, img_mask):
+                if m is not None and not bool(m.to(torch.bool).all()):
+                    raise ValueError("sequence-parallel mode does not take padded samples")
+            txt_mask = img_mask = None
+            txt, txt_ids, img_ids = sp.shard(txt), sp.shard(txt_ids), sp.shard(img_ids)
+            Lt, Li = txt.shape[1], sp.row_slice(Li).stop - sp.row_slice(Li).start
+            sp.attach(self, Li, Lt)
         need = self.lib.vcb_flux_workspace_bytes(self._h, B, Li, Lt, E)
         if need < 0:
             raise _lib.VcbError("vcb_flux_workspace_bytes: bad shape")

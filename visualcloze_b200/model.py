@@ -155,7 +155,17 @@ class Flux(nn.Module):
         if self._engine is None or key != self._packed_key:
             self._engine = FluxEngine(self.params, dict(self.named_parameters()), self.lora_scale)
             self._packed_key = key
+            if getattr(self, "_sp", None) is not None:
+                self._engine.enable_sequence_parallel(self._sp)
         return self._engine
+
+    def enable_sequence_parallel(self, sp) -> None:
+        """Single-image latency mode over several GPUs (``parallel.SequenceParallel``; None switches it off).  No counterpart
+        in the reference (single-GPU inference); the call signature and the results' contract are unchanged: every rank
+        passes the same full inputs and receives the same full output."""
+        self._sp = sp
+        if self._engine is not None:
+            self._engine.enable_sequence_parallel(sp)
 
     # ------------------------------------------------------------------------------------------
     def forward(self, img: Tensor, img_ids: Tensor, txt: Tensor, txt_ids: Tensor, timesteps: Tensor, y: Tensor,
@@ -167,6 +177,10 @@ class Flux(nn.Module):
         eng = self.engine()
         eng.prepare(txt=txt, y=y, img_ids=img_ids, txt_ids=txt_ids, timesteps=timesteps[None], guidance=guidance,
                     txt_mask=txt_mask, img_mask=img_mask, n_img_tokens=img.shape[1])
+        if eng._sp is not None:        # sequence-parallel: every rank passes the full inputs and gets the full output
+            out = eng._sp.gather(eng.forward(0, eng._sp.shard(img)), dim=1)
+            eng._sp.check()
+            return out
         return eng.forward(0, img)
 
     def get_fsdp_wrap_module_list(self):      # training-side helpers of the reference; inference-only here

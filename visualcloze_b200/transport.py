@@ -132,6 +132,14 @@ def _euler_sample(x, model, model_kwargs, t0, t1, num_steps, do_shift, time_shif
     # dt is a 0-dim fp32 tensor multiplied into a bf16 tensor: it acts as a bf16 scalar
     dts = [float((t[k + 1] - t[k]).to(th.bfloat16)) for k in range(n_eval)]
 
+    native = _is_native_forward(model)
+    sp = model.__self__.engine()._sp if native else None
+    if sp is not None:
+        # single-image sequence parallelism: this rank integrates its own token rows (the ODE is row-local apart from the
+        # attention inside the model); the trajectory is gathered once at the end.  The time grid above used the FULL Li.
+        x = sp.shard(x).contiguous()
+        cond = None if cond is None else sp.shard(cond)
+    Li_full, Li = Li, x.shape[1]
     traj = th.empty(int(num_steps), B, Li, C, dtype=x.dtype, device=x.device)
     traj[0].copy_(x)
     Cc = 0 if cond is None else cond.shape[-1]
@@ -140,14 +148,13 @@ def _euler_sample(x, model, model_kwargs, t0, t1, num_steps, do_shift, time_shif
     if cond is not None:
         ops.copy_cols(cond.to(x.dtype).reshape(B * Li, Cc).contiguous(), inp.reshape(B * Li, C + Cc), C)
 
-    native = _is_native_forward(model)
     if native:
         flux = model.__self__
         eng = flux.engine()
         if flux.params.guidance_embed and kw.get("guidance") is None:
             raise ValueError("Didn't get guidance strength for guidance distilled model.")
         eng.prepare(txt=kw["txt"], y=kw["y"], img_ids=kw["img_ids"], txt_ids=kw["txt_ids"], timesteps=flux_t,
-                    guidance=kw.get("guidance"), txt_mask=kw.get("txt_mask"), img_mask=kw.get("img_mask"), n_img_tokens=Li)
+                    guidance=kw.get("guidance"), txt_mask=kw.get("txt_mask"), img_mask=kw.get("img_mask"), n_img_tokens=Li_full)
         v = th.empty(B, Li, flux.params.out_channels, dtype=x.dtype, device=x.device)
     for k in range(n_eval):
         if native:
@@ -158,4 +165,7 @@ def _euler_sample(x, model, model_kwargs, t0, t1, num_steps, do_shift, time_shif
         assert out.shape == x.shape, "Output shape from ODE solver must match input shape"
         ops.euler_update(traj[k].reshape(B * Li, C), out.reshape(B * Li, C), dts[k], traj[k + 1].reshape(B * Li, C),
                          inp.reshape(B * Li, C + Cc))
+    if sp is not None:
+        traj = sp.gather(traj, dim=2)
+        sp.check()
     return traj
