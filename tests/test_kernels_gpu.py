@@ -252,6 +252,62 @@ def test_gemm_linear1_epilogue(ops, cta_group):
     assert float(cat[:, :H].abs().max()) == 0
 
 
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("epi", ["qkv", "linear1"])
+def test_gemm_sequence_parallel_head_routing(ops, epi, cta_group):
+    """Sequence-parallel epilogue (SURVEY.md 8f-2): the q/k/v columns of head h land in rank h // (heads/W)'s buffer
+    [W * rows, 3H/W] at row sp_row_offset + output row, through staged TMA tile stores (here both "ranks" are local buffers).
+    L = 300 leaves a partial second M tile: the TMA unit must clip the rows past the problem's extent."""
+    W, rank, L, H, heads, K, row_off, Ltot, mlp = 2, 1, 300, 512, 4, 256, 24, 340, 384
+    hw = H // W
+    N = 3 * H + (mlp if epi == "linear1" else 0)
+    a, w = _randn(L, K, seed=1), _randn(N, K, seed=2, scale=1 / math.sqrt(K))
+    bias = _randn(N, seed=3, dtype=torch.float32, scale=0.1)
+    qs, ks = (1 + 0.1 * _randn(128, seed=4, dtype=torch.float32)).to(BF16), (1 + 0.1 * _randn(128, seed=5, dtype=torch.float32)).to(BF16)
+    ang = _randn(Ltot, 64, seed=6, dtype=torch.float32) * 3
+    cos, sin = torch.cos(ang), torch.sin(ang)
+    rope = torch.stack([cos, sin], -1).permute(1, 0, 2).contiguous()
+    bufs = [torch.zeros(W * Ltot, 3 * hw, dtype=BF16, device="cuda") for _ in range(W)]
+    local = torch.zeros(Ltot, 3 * H, dtype=BF16, device="cuda")          # `out` is not written for q/k/v columns in this mode
+    cat = torch.zeros(Ltot, H + mlp, dtype=BF16, device="cuda")
+    kw = dict(out2=cat, out2_col_offset=H) if epi == "linear1" else {}
+    ops.gemm(a.cuda(), w.cuda(), bias.cuda(), local, epilogue=ops.EPI_LINEAR1 if epi == "linear1" else ops.EPI_QKV, hidden=H,
+             q_scale=qs.cuda(), k_scale=ks.cuda(), rope=rope.cuda(), rows_per_batch=L, out_batch_rows=Ltot, out_row_offset=row_off,
+             cta_group=cta_group, sp_out=bufs, sp_row_offset=rank * Ltot, **kw)
+    torch.cuda.synchronize()
+    ref = _qkv_reference(a, w[:3 * H], bias[:3 * H], qs, ks, cos[row_off:row_off + L], sin[row_off:row_off + L], heads)   # [L, 3H]
+    r0 = rank * Ltot + row_off
+    for owner in range(W):
+        want = torch.cat([ref[:, reg * H + owner * hw: reg * H + (owner + 1) * hw] for reg in range(3)], dim=1)
+        got = bufs[owner][r0:r0 + L].cpu()
+        assert rel_l2(got, want) < 6e-3, (owner, _stats(got, want))
+        assert float(bufs[owner][:r0].abs().max()) == 0 and float(bufs[owner][r0 + L:].abs().max()) == 0, "rows outside the problem were written"
+    assert float(local.abs().max()) == 0
+    if epi == "linear1":
+        lin = (a.float() @ w[3 * H:].float().T + bias[3 * H:]).to(BF16)
+        assert rel_l2(cat[row_off:row_off + L, H:].cpu(), torch.nn.functional.gelu(lin, approximate="tanh")) < 4e-3
+
+
+def test_attention_sequence_parallel_row_routing(ops):
+    """vcb_attention_fwd_sp: this rank's heads over all L rows; query row r goes to out_peers[r // rows] at row r % rows
+    (rows = 200: the 128-row tiles straddle the owners' boundary)."""
+    from oracle import flux_oracle as fo
+    W, rows, heads, rank = 2, 200, 2, 1
+    L, hw = W * rows, heads * 128
+    qkv = _randn(L, 3 * hw, seed=17)
+    ldo = W * hw + 64
+    peers = [torch.zeros(rows, ldo, dtype=BF16, device="cuda") for _ in range(W)]
+    ops.attention_sp(qkv.cuda(), L, heads, peers, rows, ldo, q_col=0, k_col=hw, v_col=2 * hw, out_col_offset=rank * hw)
+    torch.cuda.synchronize()
+    q, k, v = fo._split_heads(qkv.reshape(1, L, 3 * hw), heads)
+    ref = fo.joint_attention(q, k, v, torch.ones(1, L, 64), torch.zeros(1, L, 64), torch.ones(1, L, dtype=torch.int32),
+                             fo.Numerics("cuda_bf16")).reshape(L, hw)
+    for owner in range(W):
+        got = peers[owner].cpu()
+        assert rel_l2(got[:, rank * hw:(rank + 1) * hw], ref[owner * rows:(owner + 1) * rows]) < 8e-3
+        assert float(got[:, :rank * hw].abs().max()) == 0 and float(got[:, (rank + 1) * hw:].abs().max()) == 0
+
+
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------

@@ -23,8 +23,17 @@ constexpr int kAttn3Threads = 576;          // TMA warp + MMA warp + 2 tiles x 8
 constexpr int kAttn3Slots = 4;              // K/V ring (one slot less than attn2: room for the exchange buffer)
 constexpr int kAttn3SmemBytes = (2 + kAttn3Slots) * kSlotBytes + 1024 + 256 + 4096;
 
+// Sequence-parallel output maps (kSp): m[r] = rank r's [rows_per_rank, ldo] output buffer (all columns), box 64 columns x
+// 32 rows, 128-byte swizzle.  Each softmax warp stages its 32 x 64 piece of O in the (by then idle) Q tile and ships it with
+// one TMA tile store per owner; rows outside an owner's extent are clipped by the TMA unit.
+template <bool kSp>
+struct AttnSpMapsT { CUtensorMap m[8]; };
+template <>
+struct AttnSpMapsT<false> { int unused; };
+
+template <bool kSp>
 __global__ void __launch_bounds__(kAttn3Threads, 1)
-attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p) {
+attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p, const __grid_constant__ AttnSpMapsT<kSp> spm) {
     const int q_pair = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
     const int seqlen = p.seqlens ? min(p.seqlens[b], p.L) : p.L;
     const int q0 = q_pair * 2 * kAttnTile;
@@ -276,6 +285,10 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
             mbar_wait(&o_done[t], (uint32_t)(n_kv - 1) & 1u);
             tc_fence_after();
             const bool valid = row < seqlen;
+            // kSp: a 32-row piece that straddles two owners' row ranges (rows_per_rank % 32 != 0) keeps the per-thread
+            // stores through the peer-mapped pointers -- TMA tile stores take no negative start coordinate
+            [[maybe_unused]] const int piece_r0 = q0 + t * kAttnTile + (int)quarter * 32;
+            [[maybe_unused]] const bool staged = kSp && (piece_r0 / p.sp_rows == min(piece_r0 + 31, p.L - 1) / p.sp_rows);
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 uint32_t o[32];
@@ -286,7 +299,9 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
 #pragma unroll
                     for (int i = 0; i < 32; ++i) o[i] = 0u;
                 }
-                if (row < p.L) {
+                if (staged || row < p.L) {
+                    // kSp: my row of the warp's staging piece inside the idle Q tile (o_done => every QK of this tile has run)
+                    [[maybe_unused]] uint8_t* stg_row = smem_q + t * kSlotBytes + half * (kSlotBytes / 2) + rit * 128;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         uint4 u;
@@ -294,8 +309,21 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                         u.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
                         u.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
                         u.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
-                        *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = u;
+                        if (staged) *reinterpret_cast<uint4*>(stg_row + (((c * 4 + g) ^ (rit & 7)) << 4)) = u;
+                        else *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = u;
                     }
+                }
+            }
+            if constexpr (kSp) {
+                // the warp's 32 rows x 64 columns leave as one TMA tile store into the owner's buffer
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && staged && piece_r0 < p.L) {
+                    const uint8_t* piece = smem_q + t * kSlotBytes + half * (kSlotBytes / 2) + (int)quarter * 32 * 128;
+                    const int owner = piece_r0 / p.sp_rows;
+                    tma_store_2d(&spm.m[owner], piece, p.out_col_offset + head * 128 + half * 64, piece_r0 - owner * p.sp_rows);
+                    tma_store_commit();
+                    tma_store_wait_all();
                 }
             }
         }

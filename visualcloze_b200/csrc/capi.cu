@@ -24,7 +24,7 @@ using namespace vcb;
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-struct Problem { CUtensorMap ta, tb; GemmParams p; };
+struct Problem { CUtensorMap ta, tb; GemmParams p; CUtensorMap sp[kSpMaxRanks]; };
 
 // stream-K scratch: one slot of 128 x 256 fp32 per CTA and one flag per CTA, per stream (launches on one stream are
 // ordered, so a single scratch per stream is enough); allocated on first use (call once before CUDA-graph capture)
@@ -42,24 +42,42 @@ inline SkScratch* sk_scratch(cudaStream_t st) {
     }
     return &s;
 }
-// Off by default: measured on B200 (cfg B, power-capped at ~985 W) the tail-only stream-K is 1 % SLOWER end to end even
-// when restricted to the GEMMs with the emptiest last wave -- idle SMs in a partial wave give their power budget to the
-// busy ones (higher clocks), so the "lost" time is largely recovered, while the partial exchange costs real work.
-// VCB_STREAMK=1 enables it (tests/test_kernels_gpu.py::test_gemm_streamk_multiwave exercises it either way).
-inline bool streamk_allowed() {
-    static const bool on = [] { const char* e = getenv("VCB_STREAMK"); return e && atoi(e); }();
-    return on;
+// Stream-K policy.  VCB_STREAMK unset = auto, 0 = never, 1 = whenever feasible and the estimated saving exceeds 20 us.
+// Auto enables the tail split only when the idle part of the last wave is a large share of the WHOLE launch (>= 20 %) --
+// the few-wave GEMMs of the sequence-parallel mode (M ~ 2000: 96 pair tiles on 74 pairs).  Measured on B200 (cfg B,
+// power-capped at ~985 W): for the 3-wave GEMMs of the single-GPU path (idle share 13 %) the tail split is 1 % SLOWER end
+// to end -- idle SMs in a partial wave give their power budget to the busy ones (higher clocks), so most of the "lost"
+// time is recovered anyway, while the partial exchange costs real work.
+inline int streamk_mode() {
+    static const int m = [] { const char* e = getenv("VCB_STREAMK"); return e ? (atoi(e) ? 1 : 0) : -1; }();
+    return m;
+}
+constexpr float kSkOverheadUs = 15.f;      // partial dump + fold of a split tile
+// time of one output tile (us) for a configuration with the measured full-wave rate `rate` (TFLOP/s over all SMs)
+inline float tile_time_us(int bn, int K, float rate) { return 2.f * 128.f * bn * (float)K * (float)num_sms() / (rate * 1e6f); }
+inline bool streamk_feasible(long tiles, int slots) {
+    const long rem = tiles % slots;
+    return tiles > slots && rem != 0 && rem * (kSkMaxParts - 1) >= slots && num_sms() <= 160;
+}
+inline bool streamk_wanted(long tiles, int slots, float tile_us) {
+    const int mode = streamk_mode();
+    if (mode == 0 || !streamk_feasible(tiles, slots)) return false;
+    const long waves = (tiles + slots - 1) / slots;
+    const float idle = 1.0f - (float)(tiles % slots) / slots;
+    if (idle * tile_us <= 20.f + (mode < 0 ? kSkOverheadUs : 0.f)) return false;
+    return mode == 1 || idle / waves >= 0.2f;
 }
 
-template <int BN, int CG, int EPI>
-int launch_gemm_inst(const Problem& g0, const Problem& g1, cudaStream_t st) {
+template <int BN, int CG, int EPI, bool SP = false>
+int launch_gemm_inst(const Problem& g0, const Problem& g1, float rate, cudaStream_t st) {
     const CUtensorMap& ta = g0.ta; const CUtensorMap& tb = g0.tb; const GemmParams& p = g0.p;
     using Cfg = GemmCfg<BN, CG>;
-    auto kern = gemm_bf16_tcgen05_kernel<BN, CG, EPI>;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, CG, EPI, A_MATRIX, SP>;
+    constexpr int kSmem = Cfg::kSmemBytes + (SP ? kSpStageBytes : 0);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] {
-        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     });
     if (attr_err != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(attr_err));
     const int tile_m = kBlockM * CG;
@@ -67,39 +85,36 @@ int launch_gemm_inst(const Problem& g0, const Problem& g1, cudaStream_t st) {
     if (g1.p.batch > 0) tiles += g1.p.batch * ((g1.p.rows_per_batch + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
     int clusters = num_sms() / CG;
     if (tiles < clusters) clusters = tiles;
-    // stream-K when there is more than one wave and it is not (nearly) integral: every CTA pair gets an equal share of
-    // the (tile, k-block) space; needs >= one tile's worth of k-blocks per pair so a tile is split at most in two
+    // stream-K tail: the tiles of the partial last wave are cut along K into one equal range per CTA (pair)
     StreamKParams skp{nullptr, nullptr, 0, 0};
-    const int rem = tiles % clusters;
-    // tail tiles are split at most kSkMaxParts ways: needs rem * (kSkMaxParts - 1) >= clusters (else keep the plain tail)
-    // worth it only when the idle part of the last wave outweighs the partial dump / fold (~15 us): estimated saving =
-    // (1 - rem/pairs) x tile time, tile time ~ 0.31 us per 256-wide k-block at power-capped clocks
-    const int num_kb_h = (p.K + kBlockK - 1) / kBlockK;
-    const float saving_us = rem ? (1.0f - (float)rem / clusters) * num_kb_h * 0.31f * (BN / 256.0f) : 0.f;
-    if (streamk_allowed() && tiles > clusters && rem != 0 && rem * (kSkMaxParts - 1) >= clusters && saving_us > 20.f &&
-        num_sms() <= 160) {
+    if (streamk_wanted(tiles, clusters, tile_time_us(BN, p.K, rate))) {
         SkScratch* sc = sk_scratch(st);
         if (!sc) return set_error("gemm: stream-K scratch allocation failed");
         skp.ws = sc->ws; skp.flags = sc->flags; skp.epoch = ++sc->epoch; skp.enabled = 1;
     }
-    cudaError_t e = launch_pdl(kern, dim3(clusters * CG), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, st, CG, ta, tb, p, g1.ta, g1.tb, g1.p, skp);
+    SpMapsT<SP> spm{};
+    if constexpr (SP) {
+        for (int r = 0; r < kSpMaxRanks; ++r) { spm.m[0][r] = g0.sp[r]; spm.m[1][r] = g1.sp[r]; }
+    }
+    cudaError_t e = launch_pdl(kern, dim3(clusters * CG), dim3(kGemmThreads), (size_t)kSmem, st, CG, ta, tb, p, g1.ta, g1.tb, g1.p, skp, spm);
     if (e != cudaSuccess) return set_error("gemm launch (BN=%d CG=%d EPI=%d): %s", BN, CG, EPI, cudaGetErrorString(e));
     count_launch();
     return 0;
 }
 
 template <int BN, int CG>
-int launch_gemm_epi(int epi, const Problem& g0, const Problem& g1, cudaStream_t st) {
+int launch_gemm_epi(int epi, const Problem& g0, const Problem& g1, float rate, cudaStream_t st) {
     switch (epi) {
-        case EPI_BIAS: return launch_gemm_inst<BN, CG, EPI_BIAS>(g0, g1, st);
-        case EPI_BIAS_GELU: return launch_gemm_inst<BN, CG, EPI_BIAS_GELU>(g0, g1, st);
-        case EPI_GATE_RES: return launch_gemm_inst<BN, CG, EPI_GATE_RES>(g0, g1, st);
-        case EPI_BIAS_F32: return launch_gemm_inst<BN, CG, EPI_BIAS_F32>(g0, g1, st);
+        case EPI_BIAS: return launch_gemm_inst<BN, CG, EPI_BIAS>(g0, g1, rate, st);
+        case EPI_BIAS_GELU: return launch_gemm_inst<BN, CG, EPI_BIAS_GELU>(g0, g1, rate, st);
+        case EPI_GATE_RES: return launch_gemm_inst<BN, CG, EPI_GATE_RES>(g0, g1, rate, st);
+        case EPI_BIAS_F32: return launch_gemm_inst<BN, CG, EPI_BIAS_F32>(g0, g1, rate, st);
         default: break;
     }
     if constexpr (BN % 128 == 0) {
-        if (epi == EPI_QKV) return launch_gemm_inst<BN, CG, EPI_QKV>(g0, g1, st);
-        if (epi == EPI_LINEAR1) return launch_gemm_inst<BN, CG, EPI_LINEAR1>(g0, g1, st);
+        const bool sp = g0.p.sp_world > 1;        // sequence-parallel: staged TMA tile stores into the owners' buffers
+        if (epi == EPI_QKV) return sp ? launch_gemm_inst<BN, CG, EPI_QKV, true>(g0, g1, rate, st) : launch_gemm_inst<BN, CG, EPI_QKV>(g0, g1, rate, st);
+        if (epi == EPI_LINEAR1) return sp ? launch_gemm_inst<BN, CG, EPI_LINEAR1, true>(g0, g1, rate, st) : launch_gemm_inst<BN, CG, EPI_LINEAR1>(g0, g1, rate, st);
     }
     return set_error("gemm: epilogue %d not available for block_n %d", epi, BN);
 }
@@ -119,8 +134,9 @@ struct TileCfg { int cg, bn; float rate; };
 constexpr TileCfg kTileCfgs[] = {{2, 256, 1630.f}, {1, 256, 1445.f}, {1, 192, 1355.f}, {2, 192, 1250.f},
                                  {1, 128, 970.f},  {2, 128, 950.f}};
 
-void pick_tile(int batch, int rows, int N, bool head_structured, int want_cg, int want_bn, int* cg_out, int* bn_out) {
-    float best_cost = -1.f;
+void pick_tile(int batch, int rows, int N, int K, bool head_structured, int want_cg, int want_bn, int* cg_out, int* bn_out,
+               float* rate_out) {
+    float best_cost = -1.f, best_rate = 1630.f;
     int best_cg = 1, best_bn = 256;
     for (const TileCfg& c : kTileCfgs) {
         if (want_cg && c.cg != want_cg) continue;
@@ -130,12 +146,15 @@ void pick_tile(int batch, int rows, int N, bool head_structured, int want_cg, in
         const long mt = (long)batch * ((rows + kBlockM * c.cg - 1) / (kBlockM * c.cg));
         const long tiles = mt * ((N + c.bn - 1) / c.bn);
         const long waves = (tiles + slots - 1) / slots;
-        const float cost = (float)waves * (float)c.bn / c.rate;
-        if (best_cost < 0.f || cost < best_cost) { best_cost = cost; best_cg = c.cg; best_bn = c.bn; }
+        const float tile_us = tile_time_us(c.bn, K, c.rate);
+        // with the stream-K tail the last wave costs its filled fraction (+ the partial exchange) instead of a whole wave
+        const float cost = streamk_wanted(tiles, slots, tile_us) ? (float)tiles / slots * tile_us + kSkOverheadUs : (float)waves * tile_us;
+        if (best_cost < 0.f || cost < best_cost) { best_cost = cost; best_cg = c.cg; best_bn = c.bn; best_rate = c.rate; }
     }
     if (best_cost < 0.f) { best_cg = want_cg ? want_cg : 1; best_bn = want_bn ? want_bn : 256; }   // e.g. block_n 64
     *cg_out = best_cg;
     *bn_out = best_bn;
+    *rate_out = best_rate;
 }
 
 }  // namespace
@@ -199,6 +218,12 @@ int build_problem(const vcb_gemm_args* a, int bn, int cg, Problem* out) {
     if (int rc = make_tmap_3d(&out->ta, a->A, (uint64_t)a->K, (uint64_t)a->rows_per_batch, (uint64_t)batch, (uint64_t)a->lda,
                               (uint64_t)a_bstride, 64, 128)) return rc;
     if (int rc = make_tmap_2d(&out->tb, a->W, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldw, 64, (uint32_t)(bn / cg))) return rc;
+    // sequence-parallel destinations: this problem's rows of every rank's [W * rows, 3 * hidden / W] qkv buffer
+    for (int r = 0; r < p.sp_world; ++r) {
+        const int64_t ld = 3LL * (a->hidden / a->sp_world);
+        const __nv_bfloat16* base = p.sp_out[r] + ((int64_t)a->sp_row_offset + a->out_row_offset) * ld;
+        if (int rc = make_tmap_2d(&out->sp[r], base, (uint64_t)ld, (uint64_t)a->rows_per_batch, (uint64_t)ld, 64, 32)) return rc;
+    }
     return 0;
 }
 
@@ -206,16 +231,17 @@ int gemm_dispatch(const vcb_gemm_args* a, const vcb_gemm_args* a1, void* stream)
     if (int rc = check_gemm_args(a)) return rc;
     if (a1) {
         if (int rc = check_gemm_args(a1)) return rc;
-        if (a1->N != a->N || a1->K != a->K || a1->epilogue != a->epilogue)
-            return set_error("gemm (grouped): both problems need the same N, K and epilogue");
+        if (a1->N != a->N || a1->K != a->K || a1->epilogue != a->epilogue || (a1->sp_world > 1) != (a->sp_world > 1))
+            return set_error("gemm (grouped): both problems need the same N, K, epilogue and sequence-parallel mode");
     }
     if (int rc = ensure_device()) return rc;
     const bool head = a->epilogue == VCB_EPI_QKV || a->epilogue == VCB_EPI_LINEAR1;
     int cg, bn;
     // tile choice for the combined tile count (the second problem only adds tiles of the same shape)
     const int batch = a->M / a->rows_per_batch;
-    pick_tile(batch, a->rows_per_batch + (a1 ? a1->M / batch : 0), a->N, head, a->cta_group ? a->cta_group : forced_cta_group(),
-              a->block_n, &cg, &bn);
+    float rate;
+    pick_tile(batch, a->rows_per_batch + (a1 ? a1->M / batch : 0), a->N, a->K, head, a->cta_group ? a->cta_group : forced_cta_group(),
+              a->block_n, &cg, &bn, &rate);
     ProfScope prof(PROF_GEMM, stream);
     Problem g0, g1;
     if (int rc = build_problem(a, bn, cg, &g0)) return rc;
@@ -227,7 +253,7 @@ int gemm_dispatch(const vcb_gemm_args* a, const vcb_gemm_args* a1, void* stream)
     }
     cudaStream_t st = (cudaStream_t)stream;
 #define VCB_GEMM_CASE(BN, CG) \
-    if (bn == BN && cg == CG) return launch_gemm_epi<BN, CG>(a->epilogue, g0, g1, st);
+    if (bn == BN && cg == CG) return launch_gemm_epi<BN, CG>(a->epilogue, g0, g1, rate, st);
     VCB_GEMM_CASE(64, 1)
     VCB_GEMM_CASE(128, 1)
     VCB_GEMM_CASE(192, 1)
@@ -267,7 +293,7 @@ int launch_conv_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     int grid = num_sms();
     if (tiles < grid) grid = tiles;
     GemmParams none{};
-    cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, st, 1, ta, tb, p, ta, tb, none, StreamKParams{nullptr, nullptr, 0, 0});
+    cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, st, 1, ta, tb, p, ta, tb, none, StreamKParams{nullptr, nullptr, 0, 0}, SpMapsT<false>{});
     if (e != cudaSuccess) return set_error("conv3x3 launch: %s", cudaGetErrorString(e));
     count_launch();
     return 0;
@@ -323,7 +349,9 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(attn_fwd2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes);
         if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
+            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
         const char* e = getenv("VCB_ATTN_V1");
         use_v1 = e ? atoi(e) : 0;
         e = getenv("VCB_ATTN_V2");
@@ -348,13 +376,25 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         }
     }
     ProfScope prof(PROF_ATTN, stream);
+    static const bool sp_direct = [] { const char* e = getenv("VCB_SP_ATTN_DIRECT"); return e && atoi(e); }();
+    if (out_peers && !sp_direct) {
+        // staged TMA tile stores into the row owners' buffers (NVLink for remote owners)
+        AttnSpMapsT<true> spm{};
+        for (int r = 0; r < world; ++r)
+            if (int rc = make_tmap_2d(&spm.m[r], out_peers[r], (uint64_t)ldo, (uint64_t)rows_per_rank, (uint64_t)ldo, 64, 32)) return rc;
+        dim3 grid((L + 2 * kAttnTile - 1) / (2 * kAttnTile), heads, B);
+        cudaError_t e = launch_pdl(attn_fwd3_tcgen05_kernel<true>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, spm);
+        if (e != cudaSuccess) return set_error("attention (sp) launch: %s", cudaGetErrorString(e));
+        count_launch();
+        return 0;
+    }
     if (use_v1) {
         dim3 grid((L + kAttnTile - 1) / kAttnTile, heads, B);
         attn_fwd_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmemBytes, (cudaStream_t)stream>>>(tm, p);
     } else {
         dim3 grid((L + 2 * kAttnTile - 1) / (2 * kAttnTile), heads, B);
         cudaError_t e = use_v2 ? launch_pdl(attn_fwd2_tcgen05_kernel, grid, dim3(kAttn2Threads), (size_t)kAttn2SmemBytes, (cudaStream_t)stream, 1, tm, p)
-                               : launch_pdl(attn_fwd3_tcgen05_kernel, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p);
+                               : launch_pdl(attn_fwd3_tcgen05_kernel<false>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{});
         if (e != cudaSuccess) return set_error("attention launch: %s", cudaGetErrorString(e));
         count_launch();
         return 0;

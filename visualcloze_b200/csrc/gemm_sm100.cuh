@@ -68,9 +68,20 @@ struct GemmParams {
     // Sequence-parallel head routing (EPI_QKV / EPI_LINEAR1, batch == 1; sp_world <= 1 = off).  Token rows are sharded over
     // sp_world ranks, heads over the same ranks for attention: the q/k/v columns of head h are stored straight into rank
     // h / (heads/W)'s peer-mapped qkv buffer [W * rows, 3 * hidden / W] over NVLink, at row sp_row_offset + output row.
+    // The kernel's kSp instantiation stages each 32-row x 64-column piece in shared memory and ships it with one TMA tile
+    // store through SpMaps (one map per destination rank, covering exactly this problem's rows of that rank's buffer).
     int sp_world, sp_row_offset;
     __nv_bfloat16* sp_out[kSpMaxRanks];
 };
+
+// Tensor maps of the sequence-parallel destinations: m[g][r] = rows [sp_row_offset + out_row_offset, + rows_per_batch) of rank
+// r's qkv buffer for problem g of the launch; box 64 columns x 32 rows, 128-byte swizzle.  Rows past the problem's extent
+// are clipped by the TMA unit, which is what masks the partial last M tile.
+template <bool kSp>
+struct SpMapsT { CUtensorMap m[2][kSpMaxRanks]; };
+template <>
+struct SpMapsT<false> { int unused; };
+constexpr int kSpStageBytes = 8 * 32 * 128;    // one 32-row x 128-byte staging tile per epilogue warp
 
 // Stream-K tail (optional): the tiles of the partial last wave are cut along K into one equal contiguous range per CTA
 // (pair), so no SM idles while a few CTAs finish whole tiles.  A split tile is produced by up to kSkMaxParts CTAs: the one
@@ -78,7 +89,7 @@ struct GemmParams {
 // A waiter only waits on CTAs with a larger index, whose contributing item is their FIRST item of the phase and waits on
 // nothing: deadlock-free.  (A fully contiguous stream-K over ALL tiles was measured 30 % slower: CTAs of one wave no
 // longer share B tiles, and the 100-200 MB operands stop fitting in L2.)
-constexpr int kSkMaxParts = 4;
+constexpr int kSkMaxParts = 8;
 struct StreamKParams {
     float* ws;              // [gridDim.x][128][BLOCK_N] fp32 partial accumulators (one slot per CTA)
     int* flags;             // [gridDim.x]
@@ -186,11 +197,13 @@ VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, in
 // ----------------------------------------------------------------------------------------------
 // the kernel
 // ----------------------------------------------------------------------------------------------
-template <int BLOCK_N, int kCtaGroup, int kEpi, int kAMode = A_MATRIX>
+template <int BLOCK_N, int kCtaGroup, int kEpi, int kAMode = A_MATRIX, bool kSp = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p, const __grid_constant__ CUtensorMap tmap_a1,
-                         const __grid_constant__ CUtensorMap tmap_b1, const GemmParams p1, const StreamKParams skp) {
+                         const __grid_constant__ CUtensorMap tmap_b1, const GemmParams p1, const StreamKParams skp,
+                         const __grid_constant__ SpMapsT<kSp> spm) {
+    static_assert(!kSp || kEpi == EPI_QKV || kEpi == EPI_LINEAR1, "sequence-parallel routing lives in the head-structured epilogues");
     // Grouped launch: an optional second problem (p1.batch > 0) with the same N, K and epilogue but its own operands --
     // the txt stream of a DoubleStreamBlock rides in the img stream's launch and fills its partial last wave.
     using Cfg = GemmCfg<BLOCK_N, kCtaGroup>;
@@ -199,7 +212,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint8_t* smem_stage = smem + kStages * Cfg::kStageBytes;                 // kSp: 8 x 4 KB epilogue staging (1 KB aligned)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + (kSp ? kSpStageBytes : 0));
     uint64_t* full_bar = bars;                    // [kStages]
     uint64_t* empty_bar = bars + kStages;         // [kStages]
     uint64_t* tmem_full = bars + 2 * kStages;     // [2]
@@ -502,29 +516,63 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const uint32_t tg = taddr + hg * 128;
                     const int region = ng / P.hidden;            // 0 q, 1 k, 2 v, >= 3 mlp (LINEAR1)
                     // destination of this head's 128 q / k / v columns: the local qkv buffer, or (sequence-parallel) the
-                    // qkv buffer of the rank that owns the head -- plain stores to a peer-mapped address travel over NVLink
-                    __nv_bfloat16* qkv_dst;
-                    if (P.sp_world > 1 && region < 3) {
-                        const int hw = P.hidden / P.sp_world;    // q (or k, v) columns per rank
-                        const int cin = ng - region * P.hidden;
-                        const int owner = cin / hw;
-                        qkv_dst = P.sp_out[owner] + (orow + P.sp_row_offset) * (3LL * hw) + region * hw + (cin - owner * hw);
-                    } else {
-                        qkv_dst = P.out + orow * P.ldo + P.out_col_offset + ng;
+                    // qkv buffer of the rank that owns the head
+                    __nv_bfloat16* qkv_dst = P.out + orow * P.ldo + P.out_col_offset + ng;
+                    [[maybe_unused]] const CUtensorMap* sp_map = nullptr;
+                    [[maybe_unused]] int sp_col = 0;
+                    [[maybe_unused]] uint8_t* stg = smem_stage + (warp - 2) * 4096;
+                    [[maybe_unused]] const int sp_row0 = (mt % mps) * tile_m + (int)cta_rank * kBlockM + (int)quarter * 32;
+                    if constexpr (kSp) {
+                        if (region < 3) {
+                            const int hw = P.hidden / P.sp_world;    // q (or k, v) columns per rank
+                            const int cin = ng - region * P.hidden;
+                            const int owner = cin / hw;
+                            sp_map = &spm.m[g1 ? 1 : 0][owner];
+                            sp_col = region * hw + (cin - owner * hw);
+                        }
                     }
+                    // kSp: 32 columns of this thread's row -> staging tile (128-byte swizzle); every second chunk the warp's
+                    // 32 x 64 piece leaves as ONE asynchronous TMA tile store (NVLink for a remote owner)
+                    auto sp_emit = [&](int c, const float (&v)[32]) {
+                        if ((c & 1) == 0) {
+                            if (lane == 0) tma_store_wait_read();           // previous piece has left the staging tile
+                            __syncwarp();
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 u;
+                            u.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+                            u.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                            u.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+                            u.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                            const int chunk = (c & 1) * 4 + g;
+                            *reinterpret_cast<uint4*>(stg + lane * 128 + ((chunk ^ ((int)lane & 7)) << 4)) = u;
+                        }
+                        if (c & 1) {
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0 && sp_row0 < P.rows_per_batch) {
+                                tma_store_2d(sp_map, stg, sp_col + (c >> 1) * 64, sp_row0);
+                                tma_store_commit();
+                            }
+                        }
+                    };
                     if (region >= 2) {
 #pragma unroll 1
                         for (int c = 0; c < 4; ++c) {
                             const int n0 = ng + c * 32;
                             float v[32];
                             load_acc_bias(tg + c * 32, P.bias, n0, P.N, v);
-                            if (!row_ok) {
-                            } else if (kEpi == EPI_LINEAR1 && region >= 3) {
+                            if (kEpi == EPI_LINEAR1 && region >= 3) {
+                                if (row_ok) {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-                                store_bf16x32(P.out2 + orow * P.ldo2 + P.out2_col_offset + (n0 - 3 * P.hidden), v, n0, P.N);
+                                    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+                                    store_bf16x32(P.out2 + orow * P.ldo2 + P.out2_col_offset + (n0 - 3 * P.hidden), v, n0, P.N);
+                                }
+                            } else if constexpr (kSp) {
+                                sp_emit(c, v);          // whole warp; rows past the problem's extent are clipped by the TMA unit
                             } else {
-                                store_bf16x32(qkv_dst + c * 32, v, n0, P.N);
+                                if (row_ok) store_bf16x32(qkv_dst + c * 32, v, n0, P.N);
                             }
                         }
                     } else {
@@ -565,8 +613,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                     v[j] = __fadd_rn(__fmul_rn(cs.x, x0), __fmul_rn(-cs.y, x1));
                                     v[j + 1] = __fadd_rn(__fmul_rn(cs.y, x0), __fmul_rn(cs.x, x1));
                                 }
-                                store_bf16x32(qkv_dst + c * 32, v, n0, P.N);
+                                if constexpr (!kSp) store_bf16x32(qkv_dst + c * 32, v, n0, P.N);
                             }
+                            if constexpr (kSp) sp_emit(c, v);
                         }
                     }
                 }
@@ -583,6 +632,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
 
     // ===================== teardown =====================
+    if constexpr (kSp) {
+        if (warp >= 2 && lane == 0) tma_store_wait_all();       // this warp's tile stores have landed (staging smem is released)
+    }
     tc_fence_before();
     if constexpr (kCtaGroup == 2) cluster_sync(); else __syncthreads();
     if (warp == 1) {

@@ -96,6 +96,16 @@ VCB_DEVICE void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
 
+// smem -> global tile store (bulk async-group completion); the destination may be peer memory mapped over NVLink
+VCB_DEVICE void tma_store_2d(const CUtensorMap* m, const void* src_smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src_smem)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+VCB_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+VCB_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // smem reusable
+VCB_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // writes done
+
 // kPeer: 2-CTA mode -- the transaction bytes are credited to the leader CTA's barrier.
 template <bool kPeer>
 VCB_DEVICE void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, uint64_t hint) {

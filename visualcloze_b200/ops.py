@@ -49,7 +49,8 @@ def gemm_args(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: 
          out_col_offset: int = 0, rows_per_batch: int | None = None, out_batch_rows: int | None = None,
          out_row_offset: int = 0, gate: torch.Tensor | None = None, res: torch.Tensor | None = None,
          hidden: int = 0, q_scale=None, k_scale=None, rope=None, out2=None, out2_col_offset: int = 0,
-         block_n: int = 0, cta_group: int = 0, a_batch_stride: int = 0, m: int | None = None):
+         block_n: int = 0, cta_group: int = 0, a_batch_stride: int = 0, m: int | None = None,
+         sp_out: list | None = None, sp_row_offset: int = 0):
     """out[...] = epilogue(a @ w.T).  a [M,K], w [N,K], out 2-D (rows, ld); see include/vcb200.h.
     With batching (rows_per_batch < M) sample b's rows start at a + b * a_batch_stride (elements)."""
     _req(a, BF16, "a"); _req(w, BF16, "w"); _req(out, BF16, "out")
@@ -80,7 +81,12 @@ def gemm_args(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: 
         _req(out2, BF16, "out2")
         g.out2, g.ldo2, g.out2_col_offset = out2.data_ptr(), out2.stride(0), out2_col_offset
     g.block_n, g.cta_group = block_n, cta_group
-    g._keepalive = (a, w, bias, out, gate, res, q_scale, k_scale, rope, out2)
+    if sp_out is not None:
+        # sequence-parallel head routing: tensors (local stand-ins in tests) or raw peer-mapped addresses, one per rank
+        g.sp_world, g.sp_row_offset = len(sp_out), sp_row_offset
+        for r, t in enumerate(sp_out):
+            g.sp_out[r] = t.data_ptr() if torch.is_tensor(t) else int(t)
+    g._keepalive = (a, w, bias, out, gate, res, q_scale, k_scale, rope, out2, sp_out)
     return g, out
 
 
@@ -93,6 +99,16 @@ def attention(qkv: torch.Tensor, B: int, L: int, heads: int, out: torch.Tensor, 
     check(_lib.lib().vcb_attention_fwd(qkv.data_ptr(), qkv.stride(0), q_col, k_col, v_col, _p(seqlens), B, L, heads,
                                        out.data_ptr(), out.stride(0), out_col_offset, _stream()), "vcb_attention_fwd")
     return out
+
+
+def attention_sp(qkv: torch.Tensor, L: int, heads: int, out_peers: list, rows_per_rank: int, ldo: int, *, q_col: int, k_col: int,
+                 v_col: int, out_col_offset: int = 0) -> None:
+    """Sequence-parallel attention of this rank's ``heads`` heads over all L rows; query row r is stored into
+    ``out_peers[r // rows_per_rank]`` (tensors or raw peer-mapped addresses, leading dimension ``ldo``) at row r % rows_per_rank."""
+    _req(qkv, BF16, "qkv")
+    arr = (C.c_void_p * len(out_peers))(*[(t.data_ptr() if torch.is_tensor(t) else int(t)) for t in out_peers])
+    check(_lib.lib().vcb_attention_fwd_sp(qkv.data_ptr(), qkv.stride(0), q_col, k_col, v_col, L, heads, arr, len(out_peers),
+                                          rows_per_rank, ldo, out_col_offset, _stream()), "vcb_attention_fwd_sp")
 
 
 def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: torch.Tensor, rows_per_batch: int,
