@@ -68,7 +68,11 @@ def main():
     # ---- 2. small model: Flux.forward, SP vs single GPU vs oracle vs reference golden ---------------------
     from test_flux_gpu import _build, _cuda, _load
     g = _load("flux_small_b1.pt")
-    cfg, params, model = _build(m, g["cfg"], g["param_seed"])
+    cfg_dict = dict(g["cfg"])
+    pinned = cfg_dict["num_heads"] % world == 0        # the reference-generated golden is for the 2-head geometry
+    if not pinned:                                     # more ranks than heads: widen to one head per rank (oracle-checked only)
+        cfg_dict.update(num_heads=world, hidden_size=128 * world)
+    cfg, params, model = _build(m, cfg_dict, g["param_seed"])
     inp = g["inputs"]
     single = model(**_cuda(inp)).cpu()
     sp = parallel.SequenceParallel()
@@ -77,7 +81,7 @@ def main():
     ref = fo.flux_forward(params, cfg, **inp, mode="cuda_bf16")
     rep["small_sp_vs_single"] = rel_l2(spo, single)
     rep["small_sp_vs_oracle"] = rel_l2(spo, ref)
-    rep["small_sp_vs_golden"] = rel_l2(spo, g["out_cpu_bf16"])
+    rep["small_sp_vs_golden"] = rel_l2(spo, g["out_cpu_bf16"]) if pinned else None
     allo = [torch.empty_like(spo).cuda() for _ in range(world)]
     dist.all_gather(allo, spo.cuda())
     rep["small_ranks_identical"] = all(torch.equal(a, allo[0]) for a in allo)
@@ -93,7 +97,7 @@ def main():
     traj_1 = fn(gs["x"].cuda(), model.forward, mk).cpu()
     rep["traj_shape_ok"] = tuple(traj_sp.shape) == tuple(gs["traj"].shape)
     rep["traj_sp_vs_single"] = rel_l2(traj_sp[-1], traj_1[-1])
-    rep["traj_sp_vs_golden"] = rel_l2(traj_sp[-1], gs["traj"][-1])
+    rep["traj_sp_vs_golden"] = rel_l2(traj_sp[-1], gs["traj"][-1]) if pinned else None
     rep["traj_x0_exact"] = bool(torch.equal(traj_sp[0], gs["x"]))
 
     # ---- 4. FLUX width (hidden 3072, 24 heads) at depth 1+1 on the cfg-B token count: parity + per-eval timing ------

@@ -30,15 +30,18 @@ def _run(world, tmp_path, mode):
     return json.loads(out.read_text())
 
 
-def test_sequence_parallel_two_gpus(tmp_path):
-    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs on one node")
-    rep = _run(2, tmp_path, os.environ.get("VCB_SP_TEST_MODE", "quick"))
+@pytest.mark.parametrize("world", [2, 4])
+def test_sequence_parallel(tmp_path, world):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs on one node")
+    rep = _run(world, tmp_path, os.environ.get("VCB_SP_TEST_MODE", "quick"))
     assert rep["peer_store_ok"] and rep["barrier2_ok"] and rep["timeout_reported"]
     assert rep["small_ranks_identical"]
     assert rep["small_sp_vs_single"] < 1e-2, rep
-    assert rep["small_sp_vs_oracle"] < 2e-2 and rep["small_sp_vs_golden"] < 2.5e-2, rep
+    assert rep["small_sp_vs_oracle"] < 2e-2, rep
     assert rep["traj_shape_ok"] and rep["traj_x0_exact"]
-    assert rep["traj_sp_vs_single"] < 3e-2 and rep["traj_sp_vs_golden"] < 5e-2, rep
+    assert rep["traj_sp_vs_single"] < 3e-2, rep
+    if rep["small_sp_vs_golden"] is not None:          # 2 ranks: the reference-generated 2-head fixtures apply
+        assert rep["small_sp_vs_golden"] < 2.5e-2 and rep["traj_sp_vs_golden"] < 5e-2, rep
     if "big_sp_vs_single" in rep:
         assert rep["big_sp_vs_single"] < 1e-2, rep

@@ -480,9 +480,11 @@ extern "C" int vcb_sp_barrier(int32_t* const* flags, int32_t world, int32_t rank
         f.f[r] = flags[r];
     }
     ProfScope prof(PROF_OTHER, stream);
-    // plain (fully serialised) launch: every earlier kernel of the stream has completed, so its peer stores are performed
-    sp_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, world, rank, epoch, err, (unsigned long long)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull);
-    return check_launch("sp_barrier");
+    cudaError_t e = launch_pdl(sp_barrier_kernel, dim3(1), dim3(32), (size_t)0, (cudaStream_t)stream, 1, f, (int)world, (int)rank, (int)epoch,
+                               (int*)err, (unsigned long long)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull);
+    if (e != cudaSuccess) return set_error("sp_barrier launch: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -24,6 +24,12 @@ VCB_DEVICE unsigned long long global_timer_ns() {
 }
 
 __global__ void sp_barrier_kernel(SpFlags flags, int world, int rank, int epoch, int* err, unsigned long long timeout_ns) {
+    // Launched with programmatic stream serialization: this CTA is resident while the producer kernel still runs and lets the
+    // consumer kernel launch right away (it parks in its own griddepcontrol.wait until this grid has completed), so neither
+    // launch latency sits on the critical path.  griddepcontrol.wait returns once the producer grid has completed and its
+    // memory operations -- including the stores to peer memory -- have been performed.
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = (int)threadIdx.x;
     if (t >= world || t == rank) return;
     __threadfence_system();
