@@ -78,6 +78,20 @@ if os.path.exists(f"{G}/bench_kernels.jsonl"):
         val = r.get("tflops", r.get("gbs", 0))
         out.append(f"| {r['kernel']} | {case} | {cfg} | {r['ms']:.4f} | {val:.1f} |\n")
 
+sp = [(w, f"profiles/{tag}_bench_sp{w}.json") for w in (2, 4, 8) if os.path.exists(f"profiles/{tag}_bench_sp{w}.json")]
+if sp:
+    section("one image over W GPUs: `bench.py --gpus W --mode sp` (sequence-parallel, strong scaling; rank 0's kernel times)")
+    out.append("| W | images/s | ms per image | e2e images/s | gemm ms | attention ms | LayerNorm ms | barriers+other ms | SM MHz |\n|---|---|---|---|---|---|---|---|---|\n")
+    for w, path in sp:
+        b = json.load(open(path))
+        k = b["kernel_time_share"]
+        out.append(f"| {w} | {b['value']:.3f} | {b['ms_per_step']:.0f} | {b['e2e']['value']:.3f} | {k['gemm_ms']:.0f} | {k['attention_ms']:.0f} | "
+                   f"{k['ln_modulate_ms']:.0f} | {k['other_ms']:.0f} | {b['clocks']['sm_mhz']:.0f} |\n")
+    for w in (2, 4, 8):
+        rp = f"profiles/{tag}_sp{w}_report.json"
+        if os.path.exists(rp):
+            out.append(f"\nparity report W={w} (`tests/sp_worker.py`): `{json.dumps(json.load(open(rp)))}`\n")
+
 os.makedirs("profiles", exist_ok=True)
 open(f"profiles/{tag}_summary.md", "w").write("".join(out))
 print(f"wrote profiles/{tag}_summary.md ({sum(len(s) for s in out)} bytes)")
