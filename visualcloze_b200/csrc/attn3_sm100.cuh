@@ -31,7 +31,8 @@ struct AttnSpMapsT { CUtensorMap m[8]; };
 template <>
 struct AttnSpMapsT<false> { int unused; };
 
-template <bool kSp>
+// kPC: number of instalments (2 or 4) in which a softmax thread publishes the P of its 64 key columns per K/V tile
+template <bool kSp, int kPC = 2>
 __global__ void __launch_bounds__(kAttn3Threads, 1)
 attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p, const __grid_constant__ AttnSpMapsT<kSp> spm) {
     const int q_pair = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -66,8 +67,10 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     uint64_t* kv_full = bars + 1;                  // [slots]
     uint64_t* kv_empty = kv_full + kAttn3Slots;    // [slots]
     uint64_t* s_full = kv_empty + kAttn3Slots;     // [2] per tile
-    uint64_t* p_full = s_full + 2;                 // [2]
-    uint64_t* o_done = p_full + 2;                 // [2]
+    uint64_t* p_full = s_full + 2;                 // [2 tiles][kPC column chunks]
+    uint64_t* o_done = p_full + 2 * kPC;           // [2]
+    static_assert(kPC == 2 || kPC == 4, "P instalments");
+    constexpr int kCW = 64 / kPC;                  // key columns per instalment and thread
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
     // [parity][tile][column half][row]: row-max / row-sum exchange between the two threads of a row
     float (*xch)[2][2][128] = reinterpret_cast<float (*)[2][2][128]>(smem + (2 + kAttn3Slots) * kSlotBytes + 256);
@@ -76,7 +79,11 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < kAttn3Slots; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 8 /* one arrive per softmax warp */); mbar_init(&o_done[t], 1); }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&s_full[t], 1);
+            for (int c = 0; c < kPC; ++c) mbar_init(&p_full[kPC * t + c], 8 /* one arrive per softmax warp */);
+            mbar_init(&o_done[t], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
@@ -135,17 +142,28 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 }
                 __syncwarp();
             };
-            auto issue_pv = [&](int t, int j) {                  // O_t += P_t V_j
+            // O_t += P_t V_j in kPC instalments: every softmax thread publishes its P in kPC chunks of 64/kPC keys, so the k steps
+            // of chunk 0 (kPC = 2: keys [0,32) and [64,96)) run on the tensor pipe while the later chunks' exponentials are
+            // still being computed
+            auto issue_pv = [&](int t, int j) {
                 const uint32_t va = smem_u32(smem_kv + slot_of(2 * j + 1) * kSlotBytes);
                 const uint64_t vd = make_smem_desc(va, kSlotBytes / 2, 1024, kSwizzle128B);
-                if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + (ks >> 2) * 64 + (ks & 3) * 8,   // split P layout
-                                vd + (uint64_t)(ks * (2048 >> 4)), idesc_pv, (j | ks) != 0);
-                    umma_commit<1>(&o_done[t]);
+                for (int c = 0; c < kPC; ++c) {
+                    mbar_wait(&p_full[kPC * t + c], (uint32_t)j & 1u);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        constexpr int kPer = kCW / 16;           // 16-key k steps per chunk and column half
+#pragma unroll
+                        for (int i = 0; i < 2 * kPer; ++i) {
+                            const int ks = (i / kPer) * 4 + c * kPer + (i % kPer);
+                            umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + (ks >> 2) * 64 + (ks & 3) * 8,   // split P layout
+                                    vd + (uint64_t)(ks * (2048 >> 4)), idesc_pv, (j | c | i) != 0);
+                        }
+                        if (c == kPC - 1) umma_commit<1>(&o_done[t]);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             };
             mbar_wait(q_full, 0);
             wait_kv(0);
@@ -156,15 +174,9 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
             for (int j = 0; j < n_kv; ++j) {
                 const bool more = (j + 1) < n_kv;
                 wait_kv(2 * j + 1);                               // V_j
-                mbar_wait(&p_full[0], (uint32_t)j & 1u);
-                tc_fence_after();
                 issue_pv(0, j);
                 if (more) { wait_kv(2 * j + 2); issue_qk(0, j + 1); }
-                if (tile1) {
-                    mbar_wait(&p_full[1], (uint32_t)j & 1u);
-                    tc_fence_after();
-                    issue_pv(1, j);
-                }
+                if (tile1) issue_pv(1, j);
                 if (elect_one()) umma_commit<1>(&kv_empty[slot_of(2 * j + 1)]);    // V_j free once both PVs have run
                 __syncwarp();
                 if (more) {
@@ -244,18 +256,19 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                     const uint64_t sc2 = pack_f32x2(sc, sc), nm2 = pack_f32x2(-m_new, -m_new);
                     uint64_t acc_a = pack_f32x2(0.f, 0.f), acc_b = acc_a;
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t sr[32];
-                        tmem_ld_x32(s_addr + c * 32, sr);
+                    for (int c = 0; c < kPC; ++c) {
+                        uint32_t sr[kCW];
+                        if constexpr (kCW == 32) tmem_ld_x32(s_addr + c * kCW, sr);
+                        else tmem_ld_x16(s_addr + c * kCW, sr);
                         tmem_wait_ld();
                         if (kv_left < 64) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (c * 32 + i >= kv_left) sr[i] = 0xff800000u;     // -inf -> p = 0
+                            for (int i = 0; i < kCW; ++i)
+                                if (c * kCW + i >= kv_left) sr[i] = 0xff800000u;     // -inf -> p = 0
                         }
-                        uint32_t pk[16];
+                        uint32_t pk[kCW / 2];
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
+                        for (int i = 0; i < kCW; i += 2) {
                             const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])), sc2, nm2);
                             float p0, p1;
                             unpack_f32x2(x2, p0, p1);
@@ -265,18 +278,19 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                             else acc_a = add_f32x2(acc_a, pack_f32x2(p0, p1));
                             pk[i >> 1] = pack_bf16x2(p0, p1);
                         }
-                        // P chunk c overwrites columns [c*16, +16) of my own score region: already consumed (c' <= c)
-                        tmem_st_x16(p_addr + c * 16, pk);
+                        // P chunk c overwrites columns [c*kCW/2, +kCW/2) of my own score region: already consumed (c' <= c)
+                        if constexpr (kCW == 32) tmem_st_x16(p_addr + c * (kCW / 2), pk);
+                        else tmem_st_x8(p_addr + c * (kCW / 2), pk);
+                        tmem_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&p_full[kPC * t + c]);   // one mbarrier arrive per warp and chunk
                     }
                     float a0, a1, b0, b1;
                     unpack_f32x2(acc_a, a0, a1);
                     unpack_f32x2(acc_b, b0, b1);
                     l_run += (a0 + b0) + (a1 + b1);
                 }
-                tmem_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[t]);       // one mbarrier arrive per warp (not per thread)
             }
             // ---- epilogue: total row sum = my half + partner's half ----
             xch[n_kv & 1][t][half][rit] = l_run;

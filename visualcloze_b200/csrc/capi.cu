@@ -349,9 +349,11 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(attn_fwd2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes);
         if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
+            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
         if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
+            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
         const char* e = getenv("VCB_ATTN_V1");
         use_v1 = e ? atoi(e) : 0;
         e = getenv("VCB_ATTN_V2");
@@ -376,6 +378,7 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         }
     }
     ProfScope prof(PROF_ATTN, stream);
+    static const bool pchunks4 = [] { const char* e = getenv("VCB_ATTN_PCHUNKS"); return e && atoi(e) == 4; }();
     static const bool sp_direct = [] { const char* e = getenv("VCB_SP_ATTN_DIRECT"); return e && atoi(e); }();
     if (out_peers && !sp_direct) {
         // staged TMA tile stores into the row owners' buffers (NVLink for remote owners)
@@ -383,7 +386,7 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         for (int r = 0; r < world; ++r)
             if (int rc = make_tmap_2d(&spm.m[r], out_peers[r], (uint64_t)ldo, (uint64_t)rows_per_rank, (uint64_t)ldo, 64, 32)) return rc;
         dim3 grid((L + 2 * kAttnTile - 1) / (2 * kAttnTile), heads, B);
-        cudaError_t e = launch_pdl(attn_fwd3_tcgen05_kernel<true>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, spm);
+        cudaError_t e = launch_pdl(attn_fwd3_tcgen05_kernel<true, 2>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, spm);
         if (e != cudaSuccess) return set_error("attention (sp) launch: %s", cudaGetErrorString(e));
         count_launch();
         return 0;
@@ -394,7 +397,8 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
     } else {
         dim3 grid((L + 2 * kAttnTile - 1) / (2 * kAttnTile), heads, B);
         cudaError_t e = use_v2 ? launch_pdl(attn_fwd2_tcgen05_kernel, grid, dim3(kAttn2Threads), (size_t)kAttn2SmemBytes, (cudaStream_t)stream, 1, tm, p)
-                               : launch_pdl(attn_fwd3_tcgen05_kernel<false>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{});
+                               : (pchunks4 ? launch_pdl(attn_fwd3_tcgen05_kernel<false, 4>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{})
+                                           : launch_pdl(attn_fwd3_tcgen05_kernel<false, 2>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{}));
         if (e != cudaSuccess) return set_error("attention launch: %s", cudaGetErrorString(e));
         count_launch();
         return 0;

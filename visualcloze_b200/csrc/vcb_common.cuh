@@ -298,6 +298,11 @@ VCB_DEVICE void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+VCB_DEVICE void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 
 // fast math used by the softmax inner loop: single-instruction ex2, packed fp32x2 FMA / ADD (FFMA2 / FADD2 on sm_100)
 VCB_DEVICE float ex2_approx(float x) {
