@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define VCB_ABI_VERSION 2
+#define VCB_ABI_VERSION 3
 #define VCB_SP_MAX 8          /* ranks of one sequence-parallel group (one NVSwitch domain) */
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -113,6 +113,19 @@ int vcb_attention_fwd_sp(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t
                          int32_t heads, void* const* out_peers, int32_t world, int32_t rows_per_rank, int64_t ldo,
                          int32_t out_col_offset, void* stream);
 
+/* General form.  score_bound_log2 > 0 promises |q.k| * 128^-0.5 * log2(e) <= score_bound_log2 for every query/key pair (true
+ * after QK-RMSNorm: |q| <= max|q_scale| * sqrt(128), layers.py:63-84): softmax is shift invariant, so the kernel then uses
+ * exp2(s - bound) with no running row max -- same result up to rounding, shorter dependency chain.  Must be <= 64 (fp32 /
+ * bf16 exponent range); 0 = exact online softmax.  out_peers != NULL selects the sequence-parallel output routing. */
+typedef struct vcb_attn_args {
+    const void* qkv; int64_t ld_qkv; int32_t q_col, k_col, v_col;
+    const int32_t* seqlens; int32_t B, L, heads;
+    void* out; int64_t ldo; int32_t out_col_offset;
+    void* const* out_peers; int32_t world, rows_per_rank;
+    float score_bound_log2;
+} vcb_attn_args;
+int vcb_attention_fwd_ex(const vcb_attn_args* args, void* stream);
+
 /* ---- AdaLN modulated LayerNorm (layers.py:163-164,191,195,234,257):
  *      y = bf16( bf16(1 + scale[b]) * LayerNorm(x) + shift[b] ), eps 1e-6, no affine; hidden % 256 == 0.
  *      Logical row r = (b, i) with b = r / rows_per_batch lives at physical row b * batch_rows + i of x and y
@@ -148,10 +161,13 @@ typedef struct vcb_stream_w {           /* one stream of a DoubleStreamBlock (la
     vcb_linear_w mod, qkv, proj, mlp0, mlp2;
     const void* q_scale; const void* k_scale;      /* [128] bf16 */
 } vcb_stream_w;
-typedef struct vcb_double_w { vcb_stream_w img, txt; } vcb_double_w;
+/* attn_score_bound: 0, or an upper bound (log2 units) of the block's scaled attention scores derived from its QK-norm scales
+ * = max|q_scale| * max|k_scale| * sqrt(128) * log2(e) * (1 + margin); see vcb_attn_args.score_bound_log2 */
+typedef struct vcb_double_w { vcb_stream_w img, txt; float attn_score_bound; } vcb_double_w;
 typedef struct vcb_single_w {           /* SingleStreamBlock (layers.py:199-230) */
     vcb_linear_w mod, linear1, linear2;
     const void* q_scale; const void* k_scale;
+    float attn_score_bound;
 } vcb_single_w;
 
 typedef struct vcb_flux_config {        /* FluxParams (models/model.py:18-32) */

@@ -350,6 +350,41 @@ def test_attention_ragged_batch(ops):
     assert float(got.reshape(B, L, -1)[1, 301:].abs().max()) == 0
 
 
+@pytest.mark.parametrize("case", ["full", "ragged"])
+def test_attention_score_bound_equals_online_softmax(ops, case):
+    """vcb_attn_args.score_bound_log2: with q, k bounded like QK-RMSNorm leaves them (|q| = a*sqrt(128), |k| = b*sqrt(128))
+    the fixed-reference softmax exp2(s - bound) must equal the exact online-max kernel and the oracle (shift invariance)."""
+    from oracle import flux_oracle as fo
+    B, L, heads = (1, 648, 2) if case == "full" else (2, 520, 2)
+    seqlens = None if case == "full" else [520, 301]
+    H = heads * 128
+    qkv = _randn(B * L, 3 * H, seed=41).float().reshape(B * L, 3, heads, 128)
+    qa, ka = 1.3, 0.9
+    for i, a in ((0, qa), (1, ka)):       # unit-RMS rows times a scale, as after RMSNorm * scale (layers.py:63-84)
+        qkv[:, i] = a * qkv[:, i] / qkv[:, i].pow(2).mean(-1, keepdim=True).sqrt()
+    qkv = qkv.reshape(B * L, 3 * H).to(BF16)
+    bound = qa * ka * math.sqrt(128.0) * math.log2(math.e) * 1.03
+    sl = None if seqlens is None else torch.tensor(seqlens, dtype=torch.int32, device="cuda")
+    outs = []
+    for sb in (0.0, bound):
+        out = torch.full((B * L, H), 5.0, dtype=BF16, device="cuda")
+        ops.attention(qkv.cuda(), B, L, heads, out, q_col=0, k_col=H, v_col=2 * H, seqlens=sl, score_bound_log2=sb)
+        torch.cuda.synchronize()
+        outs.append(out.cpu())
+    q, k, v = fo._split_heads(qkv.reshape(B, L, 3 * H), heads)
+    mask = torch.ones(B, L, dtype=torch.int32)
+    if seqlens is not None:
+        for b, n in enumerate(seqlens):
+            mask[b, n:] = 0
+    ref = fo.joint_attention(q, k, v, torch.ones(B, L, 64), torch.zeros(B, L, 64), mask, fo.Numerics("cuda_bf16")).reshape(B * L, H)
+    assert rel_l2(outs[1], ref) < 8e-3, _stats(outs[1], ref)
+    assert rel_l2(outs[1], outs[0]) < 5e-3, _stats(outs[1], outs[0])
+    if seqlens is not None:
+        assert float(outs[1].reshape(B, L, H)[1, 301:].abs().max()) == 0, "padded query rows must be zero"
+    with pytest.raises(Exception, match="score_bound_log2"):
+        ops.attention(qkv.cuda(), B, L, heads, torch.empty_like(outs[0]).cuda(), q_col=0, k_col=H, v_col=2 * H, score_bound_log2=80.0)
+
+
 def test_attention_strided_output_columns(ops):
     """writes into columns [0, H) of the [L, H + mlp] linear2 input of a single block."""
     from oracle import flux_oracle as fo

@@ -74,6 +74,8 @@ def bench_attn():
         fl = 4.0 * L * L * H
         med, best = timeit(lambda: ops.attention(qkv, 1, L, heads, out, q_col=0, k_col=H, v_col=2 * H))
         emit(kernel="vcb_attention", L=L, ms=med, tflops=fl / med / 1e9, best_tflops=fl / best / 1e9)
+        med, best = timeit(lambda: ops.attention(qkv, 1, L, heads, out, q_col=0, k_col=H, v_col=2 * H, score_bound_log2=30.0))
+        emit(kernel="vcb_attention_bounded", L=L, ms=med, tflops=fl / med / 1e9, best_tflops=fl / best / 1e9)
         q, k, v = (qkv[:, i * H:(i + 1) * H].reshape(1, L, heads, 128) for i in range(3))
         try:
             from flash_attn import flash_attn_func

@@ -6,7 +6,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvcb200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 SP_MAX = 8
 
 _lib = None
@@ -77,12 +77,21 @@ class StreamW(C.Structure):
 
 
 class DoubleW(C.Structure):
-    _fields_ = [("img", StreamW), ("txt", StreamW)]
+    _fields_ = [("img", StreamW), ("txt", StreamW), ("attn_score_bound", C.c_float)]
 
 
 class SingleW(C.Structure):
     _fields_ = [("mod", LinearW), ("linear1", LinearW), ("linear2", LinearW), ("q_scale", C.c_void_p),
-                ("k_scale", C.c_void_p)]
+                ("k_scale", C.c_void_p), ("attn_score_bound", C.c_float)]
+
+
+class AttnArgs(C.Structure):
+    """struct vcb_attn_args (include/vcb200.h)."""
+    _fields_ = [("qkv", C.c_void_p), ("ld_qkv", C.c_int64), ("q_col", C.c_int32), ("k_col", C.c_int32), ("v_col", C.c_int32),
+                ("seqlens", C.c_void_p), ("B", C.c_int32), ("L", C.c_int32), ("heads", C.c_int32),
+                ("out", C.c_void_p), ("ldo", C.c_int64), ("out_col_offset", C.c_int32),
+                ("out_peers", C.POINTER(C.c_void_p)), ("world", C.c_int32), ("rows_per_rank", C.c_int32),
+                ("score_bound_log2", C.c_float)]
 
 
 class FluxConfigC(C.Structure):
@@ -150,6 +159,7 @@ _OPTIONAL: dict = {
     # sequence-parallel single-image mode
     "vcb_attention_fwd_sp": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    "vcb_attention_fwd_ex": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
     "vcb_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "vcb_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "vcb_peer_close": (C.c_int, [C.c_void_p]),

@@ -32,7 +32,10 @@ template <>
 struct AttnSpMapsT<false> { int unused; };
 
 // kPC: number of instalments (2 or 4) in which a softmax thread publishes the P of its 64 key columns per K/V tile
-template <bool kSp, int kPC = 2>
+// kFixed: the caller guarantees |scaled score| <= p.fixed_max (log2 units) -- true after QK-RMSNorm, where |q| and |k| are
+// bounded by the norm scales (layers.py:63-84).  softmax is shift invariant, so exp2(s - fixed_max) needs no running row
+// max: the max pass over S, the per-tile exchange between the two threads of a row and the O rescaling all disappear.
+template <bool kSp, int kPC = 2, bool kFixed = false>
 __global__ void __launch_bounds__(kAttn3Threads, 1)
 attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p, const __grid_constant__ AttnSpMapsT<kSp> spm) {
     const int q_pair = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -208,13 +211,16 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(dst)[i] = make_uint4(0, 0, 0, 0);
             }
         } else {
-            float m_run = -INFINITY, l_run = 0.f;
+            [[maybe_unused]] float m_run = -INFINITY;
+            float l_run = 0.f;
             const float sc = p.scale_log2;
             for (int j = 0; j < n_kv; ++j) {
                 mbar_wait(&s_full[t], (uint32_t)j & 1u);
                 tc_fence_after();
-                // pass 1: row max of my 64 columns (scores are re-read from TMEM in pass 2: keeps the live set at one chunk)
                 const int kv_left = seqlen - j * kAttnTile - half * 64;     // my columns >= kv_left are padding
+                float m_new = p.fixed_max;
+                if constexpr (!kFixed) {
+                // pass 1: row max of my 64 columns (scores are re-read from TMEM in pass 2: keeps the live set at one chunk)
                 float m_tile = -INFINITY;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
@@ -235,7 +241,7 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 named_bar_sync(bar_id, 64);
                 m_tile = fmaxf(m_tile, xch[j & 1][t][half ^ 1][rit]) * sc;   // scaled log2 units
                 const bool grow = (m_tile - m_run) > kRescaleThreshold;
-                const float m_new = grow ? m_tile : m_run;
+                m_new = grow ? m_tile : m_run;
                 const float alpha = grow ? ex2_approx(m_run - m_new) : 1.0f;
                 if (j > 0 && __any_sync(0xffffffffu, grow)) {
                     mbar_wait(&o_done[t], (uint32_t)(j - 1) & 1u);
@@ -252,6 +258,7 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 }
                 l_run *= alpha;
                 m_run = m_new;
+                }
                 {
                     const uint64_t sc2 = pack_f32x2(sc, sc), nm2 = pack_f32x2(-m_new, -m_new);
                     uint64_t acc_a = pack_f32x2(0.f, 0.f), acc_b = acc_a;

@@ -25,6 +25,7 @@ struct AttnParams {
     int out_col_offset;
     int q_col, k_col, v_col;     // column of head 0 of q / k / v inside the qkv matrix
     float scale_log2;            // head_dim^-0.5 * log2(e)
+    float fixed_max;             // > 0: upper bound of |score * scale_log2| guaranteed by the caller (attn_fwd3 kFixed)
     // Sequence-parallel output routing (attn_fwd3 only, B == 1; sp_world <= 1 = off): query row r belongs to rank
     // r / sp_rows and is stored over NVLink into that rank's peer-mapped buffer sp_out[rank] at row r % sp_rows.
     int sp_world, sp_rows;

@@ -336,7 +336,8 @@ extern "C" int vcb_conv3x3_nhwc(const void* x, const void* w, const float* bias,
 namespace {
 int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_col, int32_t v_col,
                      const int32_t* seqlens, int32_t B, int32_t L, int32_t heads, void* out, int64_t ldo,
-                     int32_t out_col_offset, void* const* out_peers, int32_t world, int32_t rows_per_rank, void* stream) {
+                     int32_t out_col_offset, void* const* out_peers, int32_t world, int32_t rows_per_rank, float bound, void* stream) {
+    if (bound < 0.f || bound > 64.f) return set_error("attention: score_bound_log2 must be in [0, 64] (0 = exact online softmax)");
     if (!qkv || (!out && !out_peers) || B <= 0 || L <= 0 || heads <= 0) return set_error("attention: bad arguments");
     if (ld_qkv % 8 || ldo % 8 || q_col % 8 || k_col % 8 || v_col % 8 || out_col_offset % 8)
         return set_error("attention: leading dims / column offsets must be multiples of 8");
@@ -354,6 +355,12 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
             attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
         const char* e = getenv("VCB_ATTN_V1");
         use_v1 = e ? atoi(e) : 0;
         e = getenv("VCB_ATTN_V2");
@@ -367,6 +374,10 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
     p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.out_col_offset = out_col_offset;
     p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
     p.scale_log2 = 0.08838834764831845f * 1.4426950408889634f;     // 128^-0.5 * log2(e)
+    static const bool no_bound = [] { const char* e = getenv("VCB_ATTN_EXACT_MAX"); return e && atoi(e); }();
+    const bool fixed = bound > 0.f && !no_bound;
+    p.fixed_max = fixed ? bound : 0.f;
+    if (fixed && (use_v1 || use_v2)) return set_error("attention: score_bound_log2 needs the default kernel (attn_fwd3)");
     if (out_peers) {
         if (world < 2 || world > VCB_SP_MAX || B != 1 || seqlens || rows_per_rank <= 0 || (int64_t)rows_per_rank * world != L)
             return set_error("attention (sp): needs one unpadded sample with L == world * rows_per_rank, 2 <= world <= %d", VCB_SP_MAX);
@@ -386,7 +397,8 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         for (int r = 0; r < world; ++r)
             if (int rc = make_tmap_2d(&spm.m[r], out_peers[r], (uint64_t)ldo, (uint64_t)rows_per_rank, (uint64_t)ldo, 64, 32)) return rc;
         dim3 grid((L + 2 * kAttnTile - 1) / (2 * kAttnTile), heads, B);
-        cudaError_t e = launch_pdl(attn_fwd3_tcgen05_kernel<true, 2>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, spm);
+        cudaError_t e = fixed ? launch_pdl(attn_fwd3_tcgen05_kernel<true, 2, true>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, spm)
+                              : launch_pdl(attn_fwd3_tcgen05_kernel<true, 2>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, spm);
         if (e != cudaSuccess) return set_error("attention (sp) launch: %s", cudaGetErrorString(e));
         count_launch();
         return 0;
@@ -397,6 +409,8 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
     } else {
         dim3 grid((L + 2 * kAttnTile - 1) / (2 * kAttnTile), heads, B);
         cudaError_t e = use_v2 ? launch_pdl(attn_fwd2_tcgen05_kernel, grid, dim3(kAttn2Threads), (size_t)kAttn2SmemBytes, (cudaStream_t)stream, 1, tm, p)
+                               : (fixed && pchunks4) ? launch_pdl(attn_fwd3_tcgen05_kernel<false, 4, true>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{})
+                               : fixed ? launch_pdl(attn_fwd3_tcgen05_kernel<false, 2, true>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{})
                                : (pchunks4 ? launch_pdl(attn_fwd3_tcgen05_kernel<false, 4>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{})
                                            : launch_pdl(attn_fwd3_tcgen05_kernel<false, 2>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{}));
         if (e != cudaSuccess) return set_error("attention launch: %s", cudaGetErrorString(e));
@@ -411,7 +425,14 @@ extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col,
                                  const int32_t* seqlens, int32_t B, int32_t L, int32_t heads, void* out, int64_t ldo,
                                  int32_t out_col_offset, void* stream) {
     if (!out) return set_error("attention: bad arguments");
-    return attention_launch(qkv, ld_qkv, q_col, k_col, v_col, seqlens, B, L, heads, out, ldo, out_col_offset, nullptr, 0, 0, stream);
+    return attention_launch(qkv, ld_qkv, q_col, k_col, v_col, seqlens, B, L, heads, out, ldo, out_col_offset, nullptr, 0, 0, 0.f, stream);
+}
+
+extern "C" int vcb_attention_fwd_ex(const vcb_attn_args* a, void* stream) {
+    if (!a) return set_error("attention: null args");
+    if (!a->out_peers && !a->out) return set_error("attention: bad arguments");
+    return attention_launch(a->qkv, a->ld_qkv, a->q_col, a->k_col, a->v_col, a->seqlens, a->out_peers ? 1 : a->B, a->L, a->heads, a->out,
+                            a->ldo, a->out_col_offset, a->out_peers, a->world, a->rows_per_rank, a->score_bound_log2, stream);
 }
 
 extern "C" int vcb_attention_fwd_sp(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_col, int32_t v_col, int32_t L,
@@ -419,7 +440,7 @@ extern "C" int vcb_attention_fwd_sp(const void* qkv, int64_t ld_qkv, int32_t q_c
                                     int32_t out_col_offset, void* stream) {
     if (!out_peers) return set_error("attention (sp): out_peers is null");
     return attention_launch(qkv, ld_qkv, q_col, k_col, v_col, nullptr, 1, L, heads, nullptr, ldo, out_col_offset, out_peers, world,
-                            rows_per_rank, stream);
+                            rows_per_rank, 0.f, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -234,15 +234,25 @@ vcb_gemm_args stream_args(const vcb_flux* f, const StreamView& sv, const uint16_
 
 // attention over the joint sequence; sequence-parallel: barrier, attention of this rank's heads over all ranks' rows with
 // the output rows scattered back to their owners, barrier
-int joint_attention(vcb_flux* f, int64_t ldc, void* stream) {
+int joint_attention(vcb_flux* f, int64_t ldc, float score_bound, void* stream) {
     const vcb_flux_config& c = f->cfg;
     const int H = c.hidden;
-    if (f->sp_world <= 1) return vcb_attention_fwd(f->qkv, 3 * H, 0, H, 2 * H, f->seqlens, f->B, f->L, c.heads, f->cat, ldc, 0, stream);
+    vcb_attn_args a{};
+    a.score_bound_log2 = score_bound;
+    a.ldo = ldc;
+    if (f->sp_world <= 1) {
+        a.qkv = f->qkv; a.ld_qkv = 3 * H; a.q_col = 0; a.k_col = H; a.v_col = 2 * H;
+        a.seqlens = f->seqlens; a.B = f->B; a.L = f->L; a.heads = c.heads;
+        a.out = f->cat; a.out_col_offset = 0;
+        return vcb_attention_fwd_ex(&a, stream);
+    }
     const int W = f->sp_world, hw = H / W;
     int rc;
     if ((rc = vcb_sp_barrier(f->sp_flags, W, f->sp_rank, ++f->sp_epoch, f->sp_err, f->sp_timeout_ms, stream))) return rc;
-    if ((rc = vcb_attention_fwd_sp(f->qkv, 3 * hw, 0, hw, 2 * hw, W * f->L, c.heads / W, f->sp_cat, W, f->L, ldc, f->sp_rank * hw, stream)))
-        return rc;
+    a.qkv = f->qkv; a.ld_qkv = 3 * hw; a.q_col = 0; a.k_col = hw; a.v_col = 2 * hw;
+    a.B = 1; a.L = W * f->L; a.heads = c.heads / W;
+    a.out_peers = f->sp_cat; a.world = W; a.rows_per_rank = f->L; a.out_col_offset = f->sp_rank * hw;
+    if ((rc = vcb_attention_fwd_ex(&a, stream))) return rc;
     return vcb_sp_barrier(f->sp_flags, W, f->sp_rank, ++f->sp_epoch, f->sp_err, f->sp_timeout_ms, stream);
 }
 
@@ -309,7 +319,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
                                    sw[s]->q_scale, sw[s]->k_scale, nullptr, 0, 0);
             if ((rc = vcb_gemm_bf16_grouped(&g[0], &g[1], stream))) return rc;
         }
-        if ((rc = joint_attention(f, ldc, stream))) return rc;
+        if ((rc = joint_attention(f, ldc, w.attn_score_bound, stream))) return rc;
         {
             vcb_gemm_args g[2];
             for (int s = 0; s < 2; ++s)
@@ -341,7 +351,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
         if ((rc = stream_ln(f, s_all, mod + 0, mod + H, 3 * H, stream))) return rc;
         if ((rc = stream_gemm(f, s_all, f->xm, H, 0, H, w.linear1, 3 * H + mlp, VCB_EPI_LINEAR1, f->qkv, 3 * H, 0, nullptr, 0,
                               nullptr, w.q_scale, w.k_scale, f->cat, ldc, H, stream))) return rc;
-        if ((rc = joint_attention(f, ldc, stream))) return rc;
+        if ((rc = joint_attention(f, ldc, w.attn_score_bound, stream))) return rc;
         if ((rc = stream_gemm(f, s_all, f->cat, ldc, 0, H + mlp, w.linear2, H, VCB_EPI_GATE_RES, f->x, H, 0, mod + 2 * H, 3 * H,
                               nullptr, nullptr, nullptr, nullptr, 0, 0, stream))) return rc;
     }

@@ -81,6 +81,16 @@ class FluxEngine:
         self._keep.append(t)
         return t.data_ptr()
 
+    def _score_bound(self, q_names: list[str], k_names: list[str]) -> float:
+        """Upper bound (log2 units) of the scaled attention scores of a block, from its QK-norm scales: after RMSNorm
+        ``|q| <= max|q_scale| * sqrt(128)`` (RoPE is a rotation), so ``|q.k| * 128^-0.5 <= max|qs| * max|ks| * sqrt(128)``;
+        3 % margin for the bf16 roundings.  0 (= exact online softmax in the kernel) when the bound leaves the safe
+        exponent range.  One-off host arithmetic on 128-element vectors at weight-packing time."""
+        qs = max(float(self._p[n].float().abs().max()) for n in q_names)
+        ks = max(float(self._p[n].float().abs().max()) for n in k_names)
+        b = qs * ks * math.sqrt(128.0) * math.log2(math.e) * 1.03
+        return b if 0.0 < b <= 64.0 else 0.0
+
     def _build(self):
         P = self.params
         cfg = FluxConfigC()
@@ -105,12 +115,16 @@ class FluxEngine:
                 dst.mlp0, dst.mlp2 = self._linear(b + "_mlp.0"), self._linear(b + "_mlp.2")
                 dst.q_scale = self._scale_vec(b + "_attn.norm.query_norm.scale")
                 dst.k_scale = self._scale_vec(b + "_attn.norm.key_norm.scale")
+            dbl[i].attn_score_bound = self._score_bound(
+                [f"double_blocks.{i}.{s}_attn.norm.query_norm.scale" for s in ("img", "txt")],
+                [f"double_blocks.{i}.{s}_attn.norm.key_norm.scale" for s in ("img", "txt")])
         sgl = (SingleW * max(1, P.depth_single_blocks))()
         for i in range(P.depth_single_blocks):
             b = f"single_blocks.{i}"
             sgl[i].mod, sgl[i].linear1, sgl[i].linear2 = self._linear(b + ".modulation.lin"), self._linear(b + ".linear1"), self._linear(b + ".linear2")
             sgl[i].q_scale = self._scale_vec(b + ".norm.query_norm.scale")
             sgl[i].k_scale = self._scale_vec(b + ".norm.key_norm.scale")
+            sgl[i].attn_score_bound = self._score_bound([b + ".norm.query_norm.scale"], [b + ".norm.key_norm.scale"])
         w.dbl, w.sgl = C.cast(dbl, C.POINTER(DoubleW)), C.cast(sgl, C.POINTER(SingleW))
         self._cfg, self._w, self._dbl, self._sgl = cfg, w, dbl, sgl
         h = C.c_void_p()
