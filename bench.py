@@ -326,7 +326,7 @@ def main():
                      "frac": gemm_fl / (pms[0] / 1000.0) / 1e12 / pk["tf"],
                      "traffic": traffic.get("gemm", {}).get("avg_dram_bytes_per_launch"), "peak_source": pk["src"] + " sustained",
                      "launches": int(pl[0]), "avg_launch_ms": pms[0] / max(1, pl[0]), "flops_per_image": gemm_fl},
-        "roofline_attention": {"kernel": "attn_fwd_tcgen05_kernel", "bound": "tensor", "achieved": attn_fl / (pms[1] / 1000.0) / 1e12,
+        "roofline_attention": {"kernel": "attn_fwd3_tcgen05_kernel (fixed-reference softmax variant when the QK-norm bound applies)", "bound": "tensor", "achieved": attn_fl / (pms[1] / 1000.0) / 1e12,
                                "peak": pk["tf"], "unit": "TFLOP/s", "frac": attn_fl / (pms[1] / 1000.0) / 1e12 / pk["tf"],
                                "launches": int(pl[1]), "avg_launch_ms": pms[1] / max(1, pl[1]),
                                "traffic": traffic.get("attention", {}).get("avg_dram_bytes_per_launch")},
