@@ -78,6 +78,30 @@ if os.path.exists(f"{G}/bench_kernels.jsonl"):
         val = r.get("tflops", r.get("gbs", 0))
         out.append(f"| {r['kernel']} | {case} | {cfg} | {r['ms']:.4f} | {val:.1f} |\n")
 
+# per-launch DRAM bytes of the captured launches -> profiles/<tag>_ncu_traffic.json (bench.py's roofline.traffic)
+traffic = {}
+for name, key in (("prof_gemm", "gemm"), ("prof_attn", "attention")):
+    p = f"{G}/{name}.ncu-rep"
+    if not os.path.exists(p):
+        continue
+    rows = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)))
+    if len(rows) < 3:
+        continue
+    hdr, units = rows[0], rows[1]
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def val(r, n):
+        i = hdr.index(n)
+        return float(r[i].replace(",", "")) * mult.get(units[i], 1)
+    L = [{"kernel": r[hdr.index("Kernel Name")][:70], "grid": r[hdr.index("Grid Size")],
+          "dram_bytes": val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"), "time_us": val(r, "gpu__time_duration.sum"),
+          "tensor_pipe_active_pct": val(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")} for r in rows[2:]]
+    traffic[key] = {"launches": L, "avg_dram_bytes_per_launch": sum(x["dram_bytes"] for x in L) / len(L)}
+if traffic:
+    traffic["note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full --clock-control none` "
+                       f"(profiles/{tag}_summary.md); cold caches")
+    json.dump(traffic, open(f"profiles/{tag}_ncu_traffic.json", "w"), indent=1)
+
 sp = [(w, f"profiles/{tag}_bench_sp{w}.json") for w in (2, 4, 8) if os.path.exists(f"profiles/{tag}_bench_sp{w}.json")]
 if sp:
     section("one image over W GPUs: `bench.py --gpus W --mode sp` (sequence-parallel, strong scaling; rank 0's kernel times)")
