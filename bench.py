@@ -310,9 +310,11 @@ def main():
     if sp_mode:                       # rank 0's kernels did 1/W of the image's GEMM rows and attention heads
         gemm_fl, attn_fl = gemm_fl / world, attn_fl / world
     traffic = {}
-    tp = os.path.join(REPO, "profiles", "r01_ncu_traffic.json")       # committed ncu --set full capture (per-launch DRAM bytes)
-    if os.path.exists(tp):
-        traffic = json.load(open(tp))
+    import glob
+    tps = sorted(glob.glob(os.path.join(REPO, "profiles", "r*_ncu_traffic.json")))   # committed ncu --set full captures, latest round
+    if tps:
+        traffic = json.load(open(tps[-1]))
+        traffic["source"] = os.path.relpath(tps[-1], REPO)
     jobs = 1 if sp_mode else world    # images per step over the whole job
     value = jobs * args.steps / (ms / 1000.0)
     out = {
@@ -324,7 +326,7 @@ def main():
         "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all fused-epilogue GEMMs of one image)", "bound": "tensor",
                      "achieved": gemm_fl / (pms[0] / 1000.0) / 1e12, "peak": pk["tf"], "unit": "TFLOP/s",
                      "frac": gemm_fl / (pms[0] / 1000.0) / 1e12 / pk["tf"],
-                     "traffic": traffic.get("gemm", {}).get("avg_dram_bytes_per_launch"), "peak_source": pk["src"] + " sustained",
+                     "traffic": traffic.get("gemm", {}).get("avg_dram_bytes_per_launch"), "traffic_source": traffic.get("source"), "peak_source": pk["src"] + " sustained",
                      "launches": int(pl[0]), "avg_launch_ms": pms[0] / max(1, pl[0]), "flops_per_image": gemm_fl},
         "roofline_attention": {"kernel": "attn_fwd3_tcgen05_kernel (fixed-reference softmax variant when the QK-norm bound applies)", "bound": "tensor", "achieved": attn_fl / (pms[1] / 1000.0) / 1e12,
                                "peak": pk["tf"], "unit": "TFLOP/s", "frac": attn_fl / (pms[1] / 1000.0) / 1e12 / pk["tf"],

@@ -159,8 +159,8 @@ class SequenceParallel:
     def attach(self, engine, li_local: int, lt_local: int) -> None:
         """collective; (re)allocates the shared qkv / cat / flag buffers when the local shape changes"""
         from . import _lib
-        key = (id(engine), li_local, lt_local)
-        if self._shape == key:
+        key = (engine, li_local, lt_local)            # the engine object itself (not id()): a recycled id must not alias
+        if self._shape is not None and self._shape[0] is engine and self._shape[1:] == key[1:]:
             return
         self.release()
         qb, cb = C.c_int64(), C.c_int64()
