@@ -134,6 +134,12 @@ int vcb_ln_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, const void
                     int64_t mod_stride, int32_t rows, int32_t hidden, int32_t rows_per_batch, int32_t batch_rows,
                     void* stream);
 
+/* Two row ranges of the same [*, hidden] buffers with their own modulation vectors in ONE launch (the img and txt streams of
+ * a DoubleStreamBlock): ldx / ldy / mod_stride / hidden / batch_rows are shared. */
+typedef struct vcb_ln_args { const void* x; void* y; const void* shift; const void* scale; int32_t rows, rows_per_batch; } vcb_ln_args;
+int vcb_ln_modulate_grouped(const vcb_ln_args* a0, const vcb_ln_args* a1, int64_t ldx, int64_t ldy, int64_t mod_stride,
+                            int32_t hidden, int32_t batch_rows, void* stream);
+
 /* ---- small helpers --------------------------------------------------------------------------------------- */
 /* layers.py:28-49; t_scaled = time_factor * t already in the reference's dtype; freqs[128] fp32; out [n,256] bf16 */
 int vcb_timestep_embedding(const float* t_scaled, const float* freqs, void* out, int32_t n, void* stream);

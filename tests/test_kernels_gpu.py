@@ -416,6 +416,25 @@ def test_ln_modulate(ops, H):
     assert rel_l2(out.cpu(), ref.reshape(B * Lb, H)) < 2e-3, _stats(out, ref.reshape(B * Lb, H))
 
 
+def test_ln_modulate_grouped_two_streams_one_launch(ops):
+    """img and txt streams of a double block (their own shift / scale, rows interleaved per sample in the joint buffer) in ONE
+    launch must equal two separate launches bit for bit."""
+    B, Lt, Li, H = 2, 24, 83, 512
+    L = Lt + Li
+    x = _randn(B * L, H, seed=61, scale=2.0).cuda()
+    mods = [_randn(B, 6 * H, seed=62 + s, scale=0.5).cuda() for s in range(2)]       # [B, 6H] rows: shift at col 0, scale at col H
+    ref = torch.zeros_like(x)
+    for s, (rows, off) in enumerate(((Li, Lt), (Lt, 0))):
+        ops.ln_modulate(x[off:], mods[s][:, 0:H], mods[s][:, H:2 * H], ref[off:], rows_per_batch=rows, mod_stride=6 * H,
+                        rows=B * rows, batch_rows=L)
+    got = torch.zeros_like(x)
+    ops.ln_modulate_grouped(x, got, [(Lt, B * Li, Li, mods[0][:, 0:H], mods[0][:, H:2 * H]),
+                                     (0, B * Lt, Lt, mods[1][:, 0:H], mods[1][:, H:2 * H])], H, L, 6 * H)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)
+    assert float(ref.abs().max()) > 0
+
+
 def test_timestep_embedding_silu_add3(ops):
     from oracle import flux_oracle as fo
     t = torch.tensor([1.0, 0.76096, 0.25, 0.0])

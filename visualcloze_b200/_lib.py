@@ -85,6 +85,12 @@ class SingleW(C.Structure):
                 ("k_scale", C.c_void_p), ("attn_score_bound", C.c_float)]
 
 
+class LnArgs(C.Structure):
+    """struct vcb_ln_args (include/vcb200.h)."""
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("shift", C.c_void_p), ("scale", C.c_void_p), ("rows", C.c_int32),
+                ("rows_per_batch", C.c_int32)]
+
+
 class AttnArgs(C.Structure):
     """struct vcb_attn_args (include/vcb200.h)."""
     _fields_ = [("qkv", C.c_void_p), ("ld_qkv", C.c_int64), ("q_col", C.c_int32), ("k_col", C.c_int32), ("v_col", C.c_int32),
@@ -160,6 +166,8 @@ _OPTIONAL: dict = {
     "vcb_attention_fwd_sp": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
     "vcb_attention_fwd_ex": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
+    "vcb_ln_modulate_grouped": (C.c_int, [C.POINTER(LnArgs), C.POINTER(LnArgs), C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                          C.c_int32, C.c_void_p]),
     "vcb_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "vcb_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "vcb_peer_close": (C.c_int, [C.c_void_p]),

@@ -515,21 +515,43 @@ extern "C" int vcb_sp_barrier(int32_t* const* flags, int32_t world, int32_t rank
 // ------------------------------------------------------------------------------------------------
 // elementwise
 // ------------------------------------------------------------------------------------------------
-extern "C" int vcb_ln_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, const void* shift, const void* scale,
-                               int64_t mod_stride, int32_t rows, int32_t hidden, int32_t rows_per_batch, int32_t batch_rows,
-                               void* stream) {
-    if (!x || !y || !shift || !scale || rows <= 0) return set_error("ln_modulate: bad arguments");
+namespace {
+int ln_launch(const vcb_ln_args* a0, const vcb_ln_args* a1, int64_t ldx, int64_t ldy, int64_t mod_stride, int32_t hidden,
+              int32_t batch_rows, void* stream) {
     if (hidden % 256 || hidden > 256 * kLnMaxChunks) return set_error("ln_modulate: hidden must be a multiple of 256, <= %d", 256 * kLnMaxChunks);
-    if (ldx % 8 || ldy % 8 || mod_stride % 8 || rows_per_batch <= 0) return set_error("ln_modulate: strides must be multiples of 8");
+    if (ldx % 8 || ldy % 8 || mod_stride % 8) return set_error("ln_modulate: strides must be multiples of 8");
+    LnProblem p[2] = {};
+    const vcb_ln_args* a[2] = {a0, a1};
+    for (int i = 0; i < 2; ++i) {
+        if (!a[i]) continue;
+        if (!a[i]->x || !a[i]->y || !a[i]->shift || !a[i]->scale || a[i]->rows <= 0 || a[i]->rows_per_batch <= 0)
+            return set_error("ln_modulate: bad arguments");
+        p[i] = LnProblem{(const __nv_bfloat16*)a[i]->x, (__nv_bfloat16*)a[i]->y, (const __nv_bfloat16*)a[i]->shift,
+                         (const __nv_bfloat16*)a[i]->scale, a[i]->rows, a[i]->rows_per_batch, (a[i]->rows + kLnWarps - 1) / kLnWarps};
+    }
     if (int rc = ensure_device()) return rc;
     ProfScope prof(PROF_LN, stream);
-    cudaError_t e = launch_pdl(ln_modulate_kernel, dim3((rows + kLnWarps - 1) / kLnWarps), dim3(kLnWarps * 32), (size_t)hidden * 4,
-                               (cudaStream_t)stream, 1, (const __nv_bfloat16*)x, (long long)ldx, (__nv_bfloat16*)y, (long long)ldy,
-                               (const __nv_bfloat16*)shift, (const __nv_bfloat16*)scale, (long long)mod_stride, (int)rows, (int)hidden,
-                               (int)rows_per_batch, (int)(batch_rows > 0 ? batch_rows : rows_per_batch));
+    const int br = batch_rows > 0 ? batch_rows : p[0].rows_per_batch;
+    cudaError_t e = launch_pdl(ln_modulate_kernel, dim3(p[0].blocks + p[1].blocks), dim3(kLnWarps * 32), (size_t)hidden * 4,
+                               (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx, (long long)ldy, (long long)mod_stride, (int)hidden, br);
     if (e != cudaSuccess) return set_error("ln_modulate launch: %s", cudaGetErrorString(e));
     count_launch();
     return 0;
+}
+}  // namespace
+
+extern "C" int vcb_ln_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, const void* shift, const void* scale,
+                               int64_t mod_stride, int32_t rows, int32_t hidden, int32_t rows_per_batch, int32_t batch_rows,
+                               void* stream) {
+    const vcb_ln_args a{x, y, shift, scale, rows, rows_per_batch};
+    return ln_launch(&a, nullptr, ldx, ldy, mod_stride, hidden, batch_rows, stream);
+}
+
+extern "C" int vcb_ln_modulate_grouped(const vcb_ln_args* a0, const vcb_ln_args* a1, int64_t ldx, int64_t ldy, int64_t mod_stride,
+                                       int32_t hidden, int32_t batch_rows, void* stream) {
+    if (!a0 || !a1) return set_error("ln_modulate (grouped): null problem");
+    if (batch_rows <= 0) return set_error("ln_modulate (grouped): batch_rows (rows of one sample in the joint buffer) is required");
+    return ln_launch(a0, a1, ldx, ldy, mod_stride, hidden, batch_rows, stream);
 }
 
 extern "C" int vcb_timestep_embedding(const float* t_scaled, const float* freqs, void* out, int32_t n, void* stream) {

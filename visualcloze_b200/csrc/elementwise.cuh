@@ -16,14 +16,26 @@ constexpr int kLnWarps = 8;           // rows per block iteration
 // One warp per row, 8 rows per block.  The block's modulation vectors (shift, 1 + scale) are staged once in shared
 // memory as bf16 pairs; a row is read once (16-byte loads, kept packed in registers), statistics are taken in one pass
 // (sum and sum of squares in fp32), and the modulated row is written once.
+// One launch may carry two problems (the img and txt streams of a DoubleStreamBlock, layers.py:163 / 170): blocks
+// [0, p0.blocks) work on p0, the rest on p1.
+struct LnProblem {
+    const __nv_bfloat16* x; __nv_bfloat16* y;
+    const __nv_bfloat16* shift; const __nv_bfloat16* scale;
+    int rows, rows_per_batch, blocks;
+};
 __global__ void __launch_bounds__(kLnWarps * 32)
-ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
-                   const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
-                   long long mod_stride, int rows, int H, int rows_per_batch, int batch_rows) {
+ln_modulate_kernel(const LnProblem p0, const LnProblem p1, long long ldx, long long ldy, long long mod_stride, int H, int batch_rows) {
     extern __shared__ uint4 ln_smem[];                 // [2][H / 8] : shift, scale of sample b0
     pdl_launch_dependents();
     pdl_wait();
-    const int row0 = blockIdx.x * kLnWarps;
+    const bool second = (int)blockIdx.x >= p0.blocks;
+    const LnProblem& P = second ? p1 : p0;
+    const __nv_bfloat16* __restrict__ x = P.x;
+    __nv_bfloat16* __restrict__ y = P.y;
+    const __nv_bfloat16* __restrict__ shift = P.shift;
+    const __nv_bfloat16* __restrict__ scale = P.scale;
+    const int rows = P.rows, rows_per_batch = P.rows_per_batch;
+    const int row0 = ((int)blockIdx.x - (second ? p0.blocks : 0)) * kLnWarps;
     const int b0 = row0 / rows_per_batch;
     const int nvec = H >> 3;
     for (int i = threadIdx.x; i < 2 * nvec; i += blockDim.x) {

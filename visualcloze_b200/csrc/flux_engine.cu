@@ -273,6 +273,16 @@ int stream_ln(const vcb_flux* f, const StreamView& sv, const uint16_t* shift, co
                            f->B * sv.rows, H, sv.rows, f->L, stream);
 }
 
+// both streams of a DoubleStreamBlock in one LayerNorm launch; mod_col = column of `shift` in the 6H modulation row
+int double_ln(const vcb_flux* f, const StreamView* const sv[2], const uint16_t* const mod[2], int mod_col, void* stream) {
+    const int H = f->cfg.hidden;
+    vcb_ln_args a[2];
+    for (int s = 0; s < 2; ++s)
+        a[s] = vcb_ln_args{f->x + (int64_t)sv[s]->off * H, f->xm + (int64_t)sv[s]->off * H, mod[s] + mod_col, mod[s] + mod_col + H,
+                           f->B * sv[s]->rows, sv[s]->rows};
+    return vcb_ln_modulate_grouped(&a[0], &a[1], H, H, 6 * H, H, f->L, stream);
+}
+
 }  // namespace
 
 extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t ld_img, void* out, int64_t ld_out,
@@ -310,8 +320,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
         const StreamView* sv[2] = {&s_img, &s_txt};
         const uint16_t* mod[2] = {f->mod_dbl[2 * i] + erow * 6 * H, f->mod_dbl[2 * i + 1] + erow * 6 * H};
         // both streams of a block share each launch (img first, txt fills the img problem's partial last wave)
-        for (int s = 0; s < 2; ++s)
-            if ((rc = stream_ln(f, *sv[s], mod[s] + 0, mod[s] + H, 6 * H, stream))) return rc;
+        if ((rc = double_ln(f, sv, mod, 0, stream))) return rc;
         {
             vcb_gemm_args g[2];
             for (int s = 0; s < 2; ++s)
@@ -327,8 +336,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
                                    nullptr, nullptr, nullptr, 0, 0);
             if ((rc = vcb_gemm_bf16_grouped(&g[0], &g[1], stream))) return rc;
         }
-        for (int s = 0; s < 2; ++s)
-            if ((rc = stream_ln(f, *sv[s], mod[s] + 3 * H, mod[s] + 4 * H, 6 * H, stream))) return rc;
+        if ((rc = double_ln(f, sv, mod, 3 * H, stream))) return rc;
         {
             vcb_gemm_args g[2];
             for (int s = 0; s < 2; ++s)

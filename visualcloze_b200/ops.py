@@ -131,6 +131,21 @@ def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: 
     return out
 
 
+def ln_modulate_grouped(x: torch.Tensor, out: torch.Tensor, problems: list, hidden: int, batch_rows: int, mod_stride: int) -> None:
+    """Two row ranges of the joint buffers in one launch.  ``problems``: two tuples (row_offset, rows, rows_per_batch, shift, scale);
+    x / out are the [*, hidden] joint buffers (vcb_ln_modulate_grouped)."""
+    _req(x, BF16, "x"); _req(out, BF16, "out")
+    args = []
+    for off, rows, rpb, shift, scale in problems:
+        _req(shift, BF16, "shift"); _req(scale, BF16, "scale")
+        a = _lib.LnArgs()
+        a.x, a.y = x.data_ptr() + off * x.stride(0) * 2, out.data_ptr() + off * out.stride(0) * 2
+        a.shift, a.scale, a.rows, a.rows_per_batch = shift.data_ptr(), scale.data_ptr(), rows, rpb
+        args.append(a)
+    check(_lib.lib().vcb_ln_modulate_grouped(C.byref(args[0]), C.byref(args[1]), x.stride(0), out.stride(0), mod_stride, hidden,
+                                             batch_rows, _stream()), "vcb_ln_modulate_grouped")
+
+
 def timestep_embedding(t_scaled: torch.Tensor, freqs: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     _req(t_scaled, torch.float32, "t_scaled"); _req(freqs, torch.float32, "freqs"); _req(out, BF16, "out")
     check(_lib.lib().vcb_timestep_embedding(t_scaled.data_ptr(), freqs.data_ptr(), out.data_ptr(), t_scaled.numel(),
