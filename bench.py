@@ -307,8 +307,10 @@ def main():
         return
     pk = peaks()
     gemm_fl, attn_fl = flops_per_image(Li, Lt, nfe)
+    # AdaLN LayerNorm passes per evaluation: 2 per double block and 1 per single block over all L rows, 1 over the img rows
+    ln_bytes = nfe * 4.0 * 3072 * ((2 * 19 + 38) * (Li + Lt) + Li)
     if sp_mode:                       # rank 0's kernels did 1/W of the image's GEMM rows and attention heads
-        gemm_fl, attn_fl = gemm_fl / world, attn_fl / world
+        gemm_fl, attn_fl, ln_bytes = gemm_fl / world, attn_fl / world, ln_bytes / world
     traffic = {}
     import glob
     tps = sorted(glob.glob(os.path.join(REPO, "profiles", "r*_ncu_traffic.json")))   # committed ncu --set full captures, latest round
@@ -333,7 +335,9 @@ def main():
                                "launches": int(pl[1]), "avg_launch_ms": pms[1] / max(1, pl[1]),
                                "traffic": traffic.get("attention", {}).get("avg_dram_bytes_per_launch")},
         "roofline_ln_modulate": {"kernel": "ln_modulate_kernel", "bound": "hbm", "unit": "GB/s", "peak": pk["hbm"],
-                                 "launches": int(pl[2]), "avg_launch_ms": pms[2] / max(1, pl[2])},
+                                 "achieved": ln_bytes / (pms[2] / 1000.0) / 1e9, "frac": ln_bytes / (pms[2] / 1000.0) / 1e9 / pk["hbm"],
+                                 "launches": int(pl[2]), "avg_launch_ms": pms[2] / max(1, pl[2]),
+                                 "note": "algorithmic bytes = read + write of the normalised rows; ~10 us of every launch is fixed cost"},
         "kernel_time_share": {"gemm_ms": pms[0], "attention_ms": pms[1], "ln_modulate_ms": pms[2], "other_ms": pms[3]},
     }
     if world == 1 and not args.no_cpu_baseline:
