@@ -30,6 +30,30 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().vcb_abi_version() == _lib.ABI_VERSION
 
 
+def test_header_is_plain_c_and_struct_layouts_match_the_binding(tmp_path):
+    """include/vcb200.h must be consumable from C (the drop-in boundary is a C ABI) and the ctypes mirrors must have the sizes
+    the C compiler gives the structs."""
+    import shutil
+    from visualcloze_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(REPO, "include", "vcb200.h")
+    assert subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr]).returncode == 0
+    names = {"vcb_gemm_args": _lib.GemmArgs, "vcb_attn_args": _lib.AttnArgs, "vcb_ln_args": _lib.LnArgs, "vcb_flux_config": _lib.FluxConfigC,
+             "vcb_flux_weights": _lib.FluxWeightsC, "vcb_double_w": _lib.DoubleW, "vcb_single_w": _lib.SingleW,
+             "vcb_vae_config": _lib.VaeConfigC, "vcb_vae_weights": _lib.VaeWeightsC, "vcb_vae_enc_weights": _lib.VaeEncWeightsC}
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "vcb200.h"\nint main(void) {\n' +
+                   "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    assert subprocess.run([gcc, "-std=c99", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)]).returncode == 0
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout
+    for line in out.splitlines():
+        n, size = line.split()
+        assert ctypes.sizeof(names[n]) == int(size), f"{n}: C says {size}, ctypes says {ctypes.sizeof(names[n])}"
+
+
 def test_no_cpu_fallback():
     from visualcloze_b200 import _lib, model as M, ops
     x = torch.zeros(4, 256, dtype=torch.bfloat16)

@@ -85,11 +85,12 @@ class FluxEngine:
         """Upper bound (log2 units) of the scaled attention scores of a block, from its QK-norm scales: after RMSNorm
         ``|q| <= max|q_scale| * sqrt(128)`` (RoPE is a rotation), so ``|q.k| * 128^-0.5 <= max|qs| * max|ks| * sqrt(128)``;
         3 % margin for the bf16 roundings.  0 (= exact online softmax in the kernel) when the bound leaves the safe
-        exponent range.  One-off host arithmetic on 128-element vectors at weight-packing time."""
+        exponent range (b > 48).  One-off host arithmetic on 128-element vectors at weight-packing time."""
         qs = max(float(self._p[n].float().abs().max()) for n in q_names)
         ks = max(float(self._p[n].float().abs().max()) for n in k_names)
         b = qs * ks * math.sqrt(128.0) * math.log2(math.e) * 1.03
-        return b if 0.0 < b <= 64.0 else 0.0
+        # exp2(s - b) >= 2^-(2b / 1.03): b <= 48 keeps even an all-anti-aligned row ~2^30 above the fp32 / bf16 underflow threshold
+        return b if 0.0 < b <= 48.0 else 0.0
 
     def _build(self):
         P = self.params
