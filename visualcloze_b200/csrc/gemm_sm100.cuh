@@ -383,7 +383,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
             if (sk_contrib) {
                 // dump this CTA's raw fp32 accumulator rows into its workspace slot, then publish
-                float* slot = skp.ws + ((long long)my_cta * kBlockM + row_in_tile) * BLOCK_N;
+                // slot layout [BLOCK_N / 4 float4 columns][128 rows]: the lanes of a warp (consecutive rows) write consecutive
+                // 16-byte words -- fully coalesced 512-byte stores (a row-major slot costs one sector per lane and store)
+                uint4* slot = reinterpret_cast<uint4*>(skp.ws + (long long)my_cta * kBlockM * BLOCK_N) + row_in_tile;
 #pragma unroll 1
                 for (int c = 0; c < kHalfN / 32; ++c) {
                     const int cc = half * (kHalfN / 32) + c;
@@ -393,7 +395,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     tmem_wait_ld();
 #pragma unroll
                     for (int q4 = 0; q4 < 8; ++q4)
-                        *reinterpret_cast<uint4*>(slot + cc * 32 + q4 * 4) = make_uint4(r[q4 * 4], r[q4 * 4 + 1], r[q4 * 4 + 2], r[q4 * 4 + 3]);
+                        slot[(cc * 8 + q4) * kBlockM] = make_uint4(r[q4 * 4], r[q4 * 4 + 1], r[q4 * 4 + 2], r[q4 * 4 + 3]);
                 }
                 __threadfence();
                 named_bar_sync(1, 256);                             // all 8 epilogue warps have written and fenced
@@ -420,7 +422,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         }
                     }
                     __syncwarp();
-                    const float* part = skp.ws + ((long long)partner * kBlockM + row_in_tile) * BLOCK_N;
+                    const float4* part = reinterpret_cast<const float4*>(skp.ws + (long long)partner * kBlockM * BLOCK_N) + row_in_tile;
 #pragma unroll 1
                     for (int c = 0; c < kHalfN / 32; ++c) {
                         const int cc = half * (kHalfN / 32) + c;
@@ -430,7 +432,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         tmem_wait_ld();
 #pragma unroll
                         for (int q4 = 0; q4 < 8; ++q4) {
-                            const float4 f = __ldcg(reinterpret_cast<const float4*>(part + cc * 32 + q4 * 4));
+                            const float4 f = __ldcg(part + (cc * 8 + q4) * kBlockM);
                             r[q4 * 4 + 0] = __float_as_uint(__uint_as_float(r[q4 * 4 + 0]) + f.x);
                             r[q4 * 4 + 1] = __float_as_uint(__uint_as_float(r[q4 * 4 + 1]) + f.y);
                             r[q4 * 4 + 2] = __float_as_uint(__uint_as_float(r[q4 * 4 + 2]) + f.z);
