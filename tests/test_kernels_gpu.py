@@ -193,6 +193,21 @@ def test_gemm_qkv_epilogue(ops, block_n, cta_group):
 
 
 @pytest.mark.parametrize("cta_group", [1, 2])
+def test_gemm_streamk_fewer_tiles_than_ctas(ops, cta_group):
+    """One partial wave (M = 600, N = 3072: 36 pair tiles / 60 single tiles on 74 / 148 slots) with a long K: with stream-K
+    (VCB_STREAMK=1, or the auto policy) every CTA gets an equal K range of the few tiles; results must match either way."""
+    M, N, K = 600, 3072, 8192
+    a, w = _randn(M, K, seed=1), _randn(N, K, seed=2, scale=1 / math.sqrt(K))
+    bias = _randn(N, seed=3, dtype=torch.float32, scale=0.1)
+    gate, x = _randn(1, N, seed=4), _randn(M, N, seed=5)
+    out = x.cuda().clone()
+    ops.gemm(a.cuda(), w.cuda(), bias.cuda(), out, epilogue=ops.EPI_GATE_RES, gate=gate.cuda(), res=out, cta_group=cta_group, block_n=256)
+    torch.cuda.synchronize()
+    ref = x + gate * (a.float() @ w.float().T + bias).to(BF16)
+    assert rel_l2(out.cpu(), ref) < 4e-3, _stats(out, ref)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
 @pytest.mark.parametrize("epi", ["qkv", "gelu", "gate"])
 def test_gemm_streamk_multiwave(ops, epi, cta_group):
     """More tiles than CTA pairs and a non-integral wave count.  With VCB_STREAMK=1 in the environment the partial last wave
@@ -495,6 +510,16 @@ torch.cuda.synchronize()
 ref = (a.float() @ w.float().T + bias).bfloat16().float()
 err = float((out.float().cpu() - ref).norm() / ref.norm())
 assert err < 3e-3, err
+# fewer tiles than CTA pairs (36 on 74): every pair gets an equal K range of the few tiles
+M = 600
+a = torch.randn(M, 8192, generator=g).bfloat16(); w = (torch.randn(N, 8192, generator=g) / math.sqrt(8192)).bfloat16()
+out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+for cg in (1, 2):
+    ops.gemm(a.cuda(), w.cuda(), bias.cuda(), out, cta_group=cg, block_n=256)
+    torch.cuda.synchronize()
+    ref = (a.float() @ w.float().T + bias).bfloat16().float()
+    err2 = float((out.float().cpu() - ref).norm() / ref.norm())
+    assert err2 < 3e-3, (cg, err2)
 print("streamk ok", err)
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, VCB_STREAMK="1"), capture_output=True, text=True, timeout=300)

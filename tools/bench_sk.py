@@ -11,7 +11,7 @@ from visualcloze_b200 import ops  # noqa: E402
 
 BF16 = torch.bfloat16
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-for M, N, K in ((1984, 3072, 12288), (1984, 3072, 15360), (1984, 3072, 3072), (992, 3072, 15360), (1984, 12288, 3072), (3968, 3072, 15360),
+for M, N, K in ((1984, 3072, 12288), (1984, 3072, 15360), (1984, 3072, 3072), (992, 3072, 15360), (1984, 12288, 3072), (992, 3072, 12288), (496, 3072, 15360), (496, 3072, 12288), (992, 12288, 3072), (3968, 3072, 15360),
                 (3968, 3072, 12288), (3968, 12288, 3072), (3968, 3072, 3072)):
     a = torch.randn(M, K, device="cuda").to(BF16)
     w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(BF16)

@@ -52,19 +52,20 @@ inline int streamk_mode() {
     static const int m = [] { const char* e = getenv("VCB_STREAMK"); return e ? (atoi(e) ? 1 : 0) : -1; }();
     return m;
 }
-constexpr float kSkOverheadUs = 15.f;      // partial dump + fold of a split tile
+constexpr float kSkOverheadUs = 30.f;      // partial dump + fold of a split tile, waiting for the partners (measured, tools/bench_sk.py)
 // time of one output tile (us) for a configuration with the measured full-wave rate `rate` (TFLOP/s over all SMs)
 inline float tile_time_us(int bn, int K, float rate) { return 2.f * 128.f * bn * (float)K * (float)num_sms() / (rate * 1e6f); }
 inline bool streamk_feasible(long tiles, int slots) {
+    // also with fewer tiles than CTA slots (one partial "wave"): every slot then gets an equal K range of the few tiles
     const long rem = tiles % slots;
-    return tiles > slots && rem != 0 && rem * (kSkMaxParts - 1) >= slots && num_sms() <= 160;
+    return rem != 0 && rem * (kSkMaxParts - 1) >= slots && num_sms() <= 160;
 }
 inline bool streamk_wanted(long tiles, int slots, float tile_us) {
     const int mode = streamk_mode();
     if (mode == 0 || !streamk_feasible(tiles, slots)) return false;
     const long waves = (tiles + slots - 1) / slots;
     const float idle = 1.0f - (float)(tiles % slots) / slots;
-    if (idle * tile_us <= 20.f + (mode < 0 ? kSkOverheadUs : 0.f)) return false;
+    if (idle * tile_us <= (mode < 0 ? kSkOverheadUs : 20.f)) return false;   // the split must save more than it costs
     return mode == 1 || idle / waves >= 0.2f;
 }
 
@@ -84,10 +85,11 @@ int launch_gemm_inst(const Problem& g0, const Problem& g1, float rate, cudaStrea
     int tiles = p.batch * ((p.rows_per_batch + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
     if (g1.p.batch > 0) tiles += g1.p.batch * ((g1.p.rows_per_batch + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
     int clusters = num_sms() / CG;
-    if (tiles < clusters) clusters = tiles;
     // stream-K tail: the tiles of the partial last wave are cut along K into one equal range per CTA (pair)
     StreamKParams skp{nullptr, nullptr, 0, 0};
-    if (streamk_wanted(tiles, clusters, tile_time_us(BN, p.K, rate))) {
+    const bool sk = streamk_wanted(tiles, clusters, tile_time_us(BN, p.K, rate));
+    if (tiles < clusters && !sk) clusters = tiles;
+    if (sk) {
         SkScratch* sc = sk_scratch(st);
         if (!sc) return set_error("gemm: stream-K scratch allocation failed");
         skp.ws = sc->ws; skp.flags = sc->flags; skp.epoch = ++sc->epoch; skp.enabled = 1;
