@@ -11,9 +11,15 @@
 //   warp 1       MMA issuer     S_t = Q_t K_j^T (SS) ; O_t += P_t V_j (TS, P from TMEM, V MN-major), issue order
 //                               QK0(0) QK1(0) | PV0(j) QK0(j+1) PV1(j) QK1(j+1) | ...  so while group t does its softmax the
 //                               pipe runs the other tile's PV and QK
-//   warps 2..5   softmax group 0 (thread == row of tile 0)      warps 6..9   softmax group 1 (tile 1)
+//   warps 2..9   softmax group 0 (tile 0; warp pair (w, w+4) = column halves of the same 32 rows)    warps 10..17  group 1
 // TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512), fp32; P_t overwrites the first 64 columns of S_t
 // as packed bf16 (here: per column half, at the start of that half's own score columns).  K and V are fetched once per 256 queries.
+//
+// Two refinements of the S -> P -> PV -> QK chain:
+//   * P leaves in kPC instalments with their own mbarriers, so the first k steps of P V overlap the remaining exponentials;
+//   * kFixed: a caller-promised bound of the scaled scores (QK-RMSNorm) replaces the running row max -- no max pass over S, no
+//     exchange between the two threads of a row, no O rescaling.
+// kSp (sequence parallelism): the epilogue ships O to the row owners' buffers with TMA tile stores (NVLink for peers).
 #pragma once
 #include "attn2_sm100.cuh"
 
