@@ -534,8 +534,12 @@ int ln_launch(const vcb_ln_args* a0, const vcb_ln_args* a1, int64_t ldx, int64_t
     if (int rc = ensure_device()) return rc;
     ProfScope prof(PROF_LN, stream);
     const int br = batch_rows > 0 ? batch_rows : p[0].rows_per_batch;
-    cudaError_t e = launch_pdl(ln_modulate_kernel, dim3(p[0].blocks + p[1].blocks), dim3(kLnWarps * 32), (size_t)hidden * 4,
-                               (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx, (long long)ldy, (long long)mod_stride, (int)hidden, br);
+    const dim3 grid(p[0].blocks + p[1].blocks), block(kLnWarps * 32);
+    cudaError_t e = hidden <= 12 * 256
+        ? launch_pdl(ln_modulate_kernel<12, 3>, grid, block, (size_t)hidden * 4, (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx,
+                     (long long)ldy, (long long)mod_stride, (int)hidden, br)
+        : launch_pdl(ln_modulate_kernel<kLnMaxChunks, 2>, grid, block, (size_t)hidden * 4, (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx,
+                     (long long)ldy, (long long)mod_stride, (int)hidden, br);
     if (e != cudaSuccess) return set_error("ln_modulate launch: %s", cudaGetErrorString(e));
     count_launch();
     return 0;

@@ -23,7 +23,10 @@ struct LnProblem {
     const __nv_bfloat16* shift; const __nv_bfloat16* scale;
     int rows, rows_per_batch, blocks;
 };
-__global__ void __launch_bounds__(kLnWarps * 32)
+// kChunks = H / 256 at compile time: the row lives in kChunks uint4 registers per lane (12 for H = 3072), which keeps the kernel
+// at 3 blocks per SM; the generic instantiation (kLnMaxChunks) serves every other hidden size.
+template <int kChunks, int kMinBlocks>
+__global__ void __launch_bounds__(kLnWarps * 32, kMinBlocks)
 ln_modulate_kernel(const LnProblem p0, const LnProblem p1, long long ldx, long long ldy, long long mod_stride, int H, int batch_rows) {
     extern __shared__ uint4 ln_smem[];                 // [2][H / 8] : shift, scale of sample b0
     pdl_launch_dependents();
@@ -49,15 +52,15 @@ ln_modulate_kernel(const LnProblem p0, const LnProblem p1, long long ldx, long l
     const int b = active ? row / rows_per_batch : b0;
     // logical row (b, i) lives at physical row b * batch_rows + i of x and y (a stream inside a joint [B, L, H] buffer)
     const long long prow = (long long)b * batch_rows + (row - b * rows_per_batch);
-    uint4 v[kLnMaxChunks];
+    uint4 v[kChunks];
     float sum = 0.f, sq = 0.f;
     if (active) {
         const __nv_bfloat16* xr = x + prow * ldx;
 #pragma unroll
-        for (int c = 0; c < kLnMaxChunks; ++c)
+        for (int c = 0; c < kChunks; ++c)
             if (c < nchunks) v[c] = *reinterpret_cast<const uint4*>(xr + c * 256 + lane * 8);
 #pragma unroll
-        for (int c = 0; c < kLnMaxChunks; ++c)
+        for (int c = 0; c < kChunks; ++c)
             if (c < nchunks) {
                 const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
 #pragma unroll
@@ -83,7 +86,7 @@ ln_modulate_kernel(const LnProblem p0, const LnProblem p1, long long ldx, long l
     const uint4* sc_g = reinterpret_cast<const uint4*>(scale + (long long)b * mod_stride);
     __nv_bfloat16* yr = y + prow * ldy;
 #pragma unroll
-    for (int c = 0; c < kLnMaxChunks; ++c)
+    for (int c = 0; c < kChunks; ++c)
         if (c < nchunks) {
             const int vi = c * 32 + lane;
             const uint4 hu = staged ? ln_smem[vi] : __ldg(sh_g + vi);
