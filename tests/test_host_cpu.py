@@ -54,6 +54,28 @@ def test_header_is_plain_c_and_struct_layouts_match_the_binding(tmp_path):
         assert ctypes.sizeof(names[n]) == int(size), f"{n}: C says {size}, ctypes says {ctypes.sizeof(names[n])}"
 
 
+def test_attention_score_bound_from_norm_scales():
+    """engine._score_bound: the promised bound must really dominate every scaled score q.k * 128^-0.5 * log2(e) of vectors that
+    went through RMSNorm * scale (+ a rotation), and must switch itself off (0 = exact online softmax) outside the safe range."""
+    import math
+    import types
+    from visualcloze_b200.engine import FluxEngine
+    g = torch.Generator().manual_seed(0)
+    qs, ks = (1 + 0.2 * torch.randn(128, generator=g)).bfloat16(), (1 + 0.2 * torch.randn(128, generator=g)).bfloat16()
+    fake = types.SimpleNamespace(_p={"q": qs, "k": ks, "big": 3.0 * torch.ones(128)})
+    b = FluxEngine._score_bound(fake, ["q"], ["k"])
+    assert 0 < b <= 48
+    x, y = torch.randn(4096, 128, generator=g) * 5, torch.randn(4096, 128, generator=g) * 0.01
+    rms = lambda t: t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6)
+    q = (rms(x).bfloat16() * qs).float()                      # layers.py:68-72 rounding points
+    k = (rms(y).bfloat16() * ks).float()
+    k[0] = q[0] * (k[0].norm() / q[0].norm())                 # one perfectly aligned pair
+    scores = (q @ k.T) * (128 ** -0.5) * math.log2(math.e)
+    assert float(scores.abs().max()) <= b
+    assert float(scores.abs().max()) > 0.25 * b               # and it is not vacuous
+    assert FluxEngine._score_bound(fake, ["big"], ["big"]) == 0.0      # 9 * 16.3 > 48: exact kernel
+
+
 def test_no_cpu_fallback():
     from visualcloze_b200 import _lib, model as M, ops
     x = torch.zeros(4, 256, dtype=torch.bfloat16)
