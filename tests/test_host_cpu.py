@@ -76,6 +76,40 @@ def test_attention_score_bound_from_norm_scales():
     assert FluxEngine._score_bound(fake, ["big"], ["big"]) == 0.0      # 9 * 16.3 > 48: exact kernel
 
 
+def test_bench_algorithmic_flops_match_the_survey_table():
+    """bench.py's roofline numerators (per evaluation at cfg B 51.23 TF of merged-LoRA GEMMs in the 57 blocks
+    + embed/final, 11.03 TF of attention)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(REPO, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    gemm1, attn1 = bench.flops_per_image(3456, 512, 1)
+    gemm2, attn2 = bench.flops_per_image(3456, 512, 2)
+    per_eval = gemm2 - gemm1                                   # the step-invariant part (txt_in, embedders) cancels
+    assert abs(attn1 - 11.03e12) / 11.03e12 < 2e-3
+    assert abs((attn2 - attn1) - attn1) < 1e-6 * attn1
+    blocks = 57 * 24 * 3968 * 3072 ** 2
+    assert blocks < per_eval < 1.01 * blocks and abs(blocks - 51.23e12) / 51.23e12 < 1e-3
+    x, kw, Li, Lt = bench.make_inputs("B", 1234)
+    assert (Li, Lt) == (3456, 512) and x.shape == (1, 3456, 64) and kw["cond"].shape == (1, 3456, 320)
+    assert kw["img_ids"][0, :, 0].unique().tolist() == [1.0, 2.0]            # one RoPE row id per grid row (sampling.py:56-61)
+
+
+def test_fixed_reference_softmax_is_the_same_function():
+    """The identity the bounded attention kernel relies on: softmax(s) == 2^(s' - B) / sum 2^(s' - B) for ANY reference B
+    (s' = s * log2 e), evaluated the way the kernel does (P rounded to bf16, fp32 row sum of the unrounded p)."""
+    import math
+    g = torch.Generator().manual_seed(1)
+    s = torch.randn(64, 512, generator=g) * 3
+    v = torch.randn(512, 128, generator=g)
+    ref = torch.softmax(s, dim=-1) @ v
+    s2 = s * math.log2(math.e)
+    for B in (float(s2.max()), float(s2.max()) + 11.0, 40.0):
+        p = torch.exp2(s2 - B)
+        out = (p.bfloat16().float() @ v) / p.sum(-1, keepdim=True)
+        assert float((out - ref).norm() / ref.norm()) < 3e-3, B
+
+
 def test_no_cpu_fallback():
     from visualcloze_b200 import _lib, model as M, ops
     x = torch.zeros(4, 256, dtype=torch.bfloat16)
