@@ -1,4 +1,4 @@
-"""Bounded attention kernel at L = 3968 / 7424 (CUDA events, L2 flushed); run once per VCB_ATTN_POLY setting."""
+"""Bounded attention kernel at L = 3968 / 7424 (CUDA events, L2 flushed)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from visualcloze_b200 import ops
@@ -16,4 +16,4 @@ for L in (3968, 7424):
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     ts.sort()
-    print(f"VCB_ATTN_POLY={os.environ.get('VCB_ATTN_POLY', '0')} L={L}: {ts[7] * 1e3:.1f} us, {4.0 * L * L * H / ts[7] / 1e9:.0f} TFLOP/s", flush=True)
+    print(f"L={L}: {ts[7] * 1e3:.1f} us, {4.0 * L * L * H / ts[7] / 1e9:.0f} TFLOP/s", flush=True)

@@ -41,9 +41,7 @@ struct AttnSpMapsT<false> { int unused; };
 // kFixed: the caller guarantees |scaled score| <= p.fixed_max (log2 units) -- true after QK-RMSNorm, where |q| and |k| are
 // bounded by the norm scales (layers.py:63-84).  softmax is shift invariant, so exp2(s - fixed_max) needs no running row
 // max: the max pass over S, the per-tile exchange between the two threads of a row and the O rescaling all disappear.
-// kPoly (experimental, VCB_ATTN_POLY=1, kFixed only): every other column pair takes 2^x from a degree-3 polynomial on the
-// FMA pipe instead of MUFU.EX2 (ncu on the bounded kernel: tensor pipe 70 %, XU pipe 70 %, issue slots 33 %).
-template <bool kSp, int kPC = 2, bool kFixed = false, bool kPoly = false>
+template <bool kSp, int kPC = 2, bool kFixed = false>
 __global__ void __launch_bounds__(kAttn3Threads, 1)
 attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p, const __grid_constant__ AttnSpMapsT<kSp> spm) {
     const int q_pair = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -287,27 +285,8 @@ attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                             const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])), sc2, nm2);
                             float p0, p1;
                             unpack_f32x2(x2, p0, p1);
-                            if (kPoly && ((i >> 1) & 1)) {
-                                // x = n + f, n = round(x) through the 1.5 * 2^23 trick, |f| <= 0.5; 2^f ~ degree-3 minimax polynomial
-                                // (rel. err 8e-5, far below the bf16 rounding of P); 2^n goes into the exponent field.  With the fixed
-                                // reference x >= -2 * 48, so only masked (-inf) columns need the clamp.
-                                uint64_t xc = x2;
-                                if (kv_left < 64) xc = pack_f32x2(fmaxf(p0, -125.f), fmaxf(p1, -125.f));
-                                const uint64_t magic2 = pack_f32x2(12582912.f, 12582912.f);
-                                const uint64_t t2 = add_f32x2(xc, magic2);                                        // 1.5 * 2^23 + n
-                                const uint64_t f2 = add_f32x2(xc, add_f32x2(magic2, t2 ^ 0x8000000080000000ull));   // x - n
-                                uint64_t q2 = fma_f32x2(pack_f32x2(0.055088684f, 0.055088684f), f2, pack_f32x2(0.24260405f, 0.24260405f));
-                                q2 = fma_f32x2(q2, f2, pack_f32x2(0.6932762f, 0.6932762f));
-                                q2 = fma_f32x2(q2, f2, pack_f32x2(0.99992895f, 0.99992895f));
-                                float t0, t1, q0, q1;
-                                unpack_f32x2(t2, t0, t1);
-                                unpack_f32x2(q2, q0, q1);
-                                p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
-                                p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
-                            } else {
-                                p0 = ex2_approx(p0);
-                                p1 = ex2_approx(p1);
-                            }
+                            p0 = ex2_approx(p0);
+                            p1 = ex2_approx(p1);
                             if ((i >> 1) & 1) acc_b = add_f32x2(acc_b, pack_f32x2(p0, p1));
                             else acc_a = add_f32x2(acc_a, pack_f32x2(p0, p1));
                             pk[i >> 1] = pack_bf16x2(p0, p1);

@@ -363,8 +363,6 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
             attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
         const char* e = getenv("VCB_ATTN_V1");
         use_v1 = e ? atoi(e) : 0;
         e = getenv("VCB_ATTN_V2");
@@ -393,7 +391,6 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         }
     }
     ProfScope prof(PROF_ATTN, stream);
-    static const bool poly = [] { const char* e = getenv("VCB_ATTN_POLY"); return e && atoi(e); }();
     static const bool pchunks4 = [] { const char* e = getenv("VCB_ATTN_PCHUNKS"); return e && atoi(e) == 4; }();
     static const bool sp_direct = [] { const char* e = getenv("VCB_SP_ATTN_DIRECT"); return e && atoi(e); }();
     if (out_peers && !sp_direct) {
@@ -414,7 +411,6 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
     } else {
         dim3 grid((L + 2 * kAttnTile - 1) / (2 * kAttnTile), heads, B);
         cudaError_t e = use_v2 ? launch_pdl(attn_fwd2_tcgen05_kernel, grid, dim3(kAttn2Threads), (size_t)kAttn2SmemBytes, (cudaStream_t)stream, 1, tm, p)
-                               : (fixed && poly) ? launch_pdl(attn_fwd3_tcgen05_kernel<false, 2, true, true>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{})
                                : (fixed && pchunks4) ? launch_pdl(attn_fwd3_tcgen05_kernel<false, 4, true>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{})
                                : fixed ? launch_pdl(attn_fwd3_tcgen05_kernel<false, 2, true>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{})
                                : (pchunks4 ? launch_pdl(attn_fwd3_tcgen05_kernel<false, 4>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{})
