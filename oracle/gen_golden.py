@@ -41,7 +41,7 @@ def _odeint(func, y0, t, method="euler", atol=None, rtol=None):
     ys = [y0]
     y = y0
     for k in range(len(t) - 1):
-        y = y + (t[k + 1] - t[k]) * func(t[k], y)
+        y = y + (t[k + 1] - t[k]) * func(t[k].to(y.abs().dtype), y)      # _PerturbFunc casts t to the state dtype
         ys.append(y)
     return torch.stack(ys, 0)
 

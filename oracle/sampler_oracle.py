@@ -10,7 +10,9 @@ Restates:
   * ``torchdiffeq.odeint(method="euler")`` -- third-party, unpinned, absent from /root/reference:
     fixed-grid Euler, ``y[k+1] = y[k] + (t[k+1] - t[k]) * f(t[k], y[k])``, returns the stacked
     trajectory.  With a bf16 state and a 0-dim fp32 ``dt`` tensor, torch type promotion makes
-    the update ``bf16(y + bf16(bf16(dt) * f))`` (probed).
+    the update ``bf16(y + bf16(bf16(dt) * f))`` (probed).  ``odeint`` wraps ``f`` in
+    ``_PerturbFunc``, whose forward casts the evaluation time to the state dtype (``t.to(y.abs().dtype)``), so
+    a bf16 state makes the model see ``bf16(t[k])``; ``dt`` is taken from the un-rounded fp32 grid.
 
 Parity status: pinned against the reference ``transport`` package run in the build container
 with a 12-line Euler ``torchdiffeq`` shim (``oracle/gen_golden.py``).
@@ -49,7 +51,7 @@ def sample_ode(x: torch.Tensor, model_fn, model_kwargs: dict, num_steps: int, do
     ys = [x]
     y = x
     for k in range(num_steps - 1):
-        tau = t[k]
+        tau = t[k].to(y.dtype)                                     # torchdiffeq _PerturbFunc: t.to(y.abs().dtype)
         t_vec = torch.ones(y.shape[0]) * tau                       # integrators.py:109
         t_flux = torch.ones_like(t_vec) * (1 - t_vec)              # transport.py:384
         inp = y if cond is None else torch.cat((y, cond), dim=-1)  # transport.py:194-196

@@ -177,10 +177,23 @@ class FluxEngine:
         ids = torch.cat((txt_ids.to(dev), img_ids.to(dev)), dim=1).float().contiguous()
         if ids.shape != (B, Lt + Li, 3):
             raise ValueError(f"ids must be [B, Lt+Li, 3], got {tuple(ids.shape)}")
+        # Masks -> per-sample valid length of the joint [txt | img] sequence.  The kernels treat the FIRST seqlen rows as valid
+        # (the layout the pipeline produces: txt_mask all ones, sampling.py:98; img right-padded to the batch max, :82-88).
+        # The reference's _upad_input honours arbitrary masks (math.py:40-60); anything else is refused here rather than
+        # silently attending to padded txt rows (one host sync per image, where the reference has two per attention call).
         seqlens = None
-        if img_mask is not None:
-            tm = txt_mask if txt_mask is not None else torch.ones(B, Lt, dtype=torch.int32, device=dev)
-            seqlens = (tm.to(dev).sum(dim=-1, dtype=torch.int32) + img_mask.to(dev).sum(dim=-1, dtype=torch.int32)).contiguous()
+        if txt_mask is not None or img_mask is not None:
+            tm = (txt_mask.to(dev) != 0) if txt_mask is not None else torch.ones(B, Lt, dtype=torch.bool, device=dev)
+            im = (img_mask.to(dev) != 0) if img_mask is not None else torch.ones(B, Li, dtype=torch.bool, device=dev)
+            if tuple(tm.shape) != (B, Lt) or tuple(im.shape) != (B, Li):
+                raise ValueError(f"txt_mask / img_mask must be [B, Lt] / [B, Li] = {(B, Lt)} / {(B, Li)}")
+            n_img = im.sum(dim=-1, dtype=torch.int32)
+            prefix = torch.arange(Li, device=dev)[None, :] < n_img[:, None]
+            if not bool(tm.all() & (im == prefix).all()):
+                raise ValueError("unsupported attention mask: the sm_100a attention kernel takes a fully valid txt_mask and a "
+                                 "right-padded (prefix) img_mask -- the layout prepare_modified produces (models/sampling.py:82-98)")
+            if img_mask is not None:
+                seqlens = (n_img + Lt).contiguous()
         txt_c = txt.to(dev, BF16).contiguous()
         y_c = y.to(dev, BF16).contiguous()
         self._hold = (ts, gs, ids, seqlens, txt_c, y_c)      # keep alive until the next prepare

@@ -119,6 +119,9 @@ class Flux(nn.Module):
         self.lora_scale = 1.0
         self._engine: FluxEngine | None = None
         self._packed_key = None
+        # names of the parameters that have received values (load_state_dict / init_synthetic / mark_initialized): base weights
+        # are allocated with torch.empty, and packing an engine from never-loaded memory must fail loudly, not render garbage
+        self._initialized: set[str] = set()
         kw = dict(device=device, dtype=dtype)
         for name, fin, fout in linear_table(params):
             _attach(self, name + ".weight", nn.Parameter(torch.empty(fout, fin, **kw), requires_grad=False))
@@ -147,10 +150,33 @@ class Flux(nn.Module):
                         std /= math.sqrt(nblk)
                     p.copy_(std * torch.randn(p.shape, generator=g, device=dev))
         self._packed_key = None
+        self._initialized = {n for n, _ in self.named_parameters()}
         return self
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """``nn.Module.load_state_dict`` that also records which parameters received values (see ``uninitialized``)."""
+        res = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        own = {n for n, _ in self.named_parameters()}
+        self._initialized |= own & set(state_dict.keys())
+        return res
+
+    def mark_initialized(self, names=None) -> None:
+        """Declare parameters filled by other means (``p.copy_`` ...) as initialised; ``None`` = all of them."""
+        self._initialized |= {n for n, _ in self.named_parameters()} if names is None else set(names)
+
+    def uninitialized(self) -> list[str]:
+        """Base parameters still holding ``torch.empty`` memory.  QK-norm scales (ones) and the LoRA tensors (zero update)
+        have well-defined defaults, exactly like the reference modules (layers.py:66, lora.py:84-86)."""
+        return [n for n, _ in self.named_parameters()
+                if n not in self._initialized and not n.endswith(".scale") and ".lora_" not in n]
 
     def engine(self) -> FluxEngine:
         """Packed-weight engine, rebuilt when a parameter was replaced or modified in place or the LoRA scale changed."""
+        missing = self.uninitialized()
+        if missing:
+            from ._lib import VcbError
+            raise VcbError(f"{len(missing)} base parameters were never loaded (e.g. {missing[:3]}): load the FLUX.1-Fill checkpoint "
+                           "(VisualClozeModel(flux_ckpt=...) / load_state_dict) or call init_synthetic() before running the model")
         key = (self.lora_scale,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._engine is None or key != self._packed_key:
             self._engine = FluxEngine(self.params, dict(self.named_parameters()), self.lora_scale)
@@ -201,7 +227,9 @@ class FluxLoraWrapper(Flux):
         kw = dict(device=some.device, dtype=some.dtype)
         for name, fin, fout in linear_table(self.params):
             r = min(lora_rank, fin, fout)
-            _attach(self, name + ".lora_A.weight", nn.Parameter(torch.empty(r, fin, **kw), requires_grad=False))
+            # zero default (the reference draws lora_A at random, lora.py:84; with lora_B = 0 the update is zero either way, and
+            # zeros cannot inject NaNs from uninitialised memory into the merged weight)
+            _attach(self, name + ".lora_A.weight", nn.Parameter(torch.zeros(r, fin, **kw), requires_grad=False))
             # the reference zero-initialises lora_B (lora.py:84-86)
             _attach(self, name + ".lora_B.weight", nn.Parameter(torch.zeros(fout, r, **kw), requires_grad=False))
             _attach(self, name + ".lora_B.bias", nn.Parameter(torch.zeros(fout, **kw), requires_grad=False))

@@ -176,8 +176,14 @@ def rope_table(ids: torch.Tensor, axes_dim, theta: float, out: torch.Tensor) -> 
 
 
 def euler_update(x, v, dt_bf16: float, x_new, model_in=None) -> torch.Tensor:
+    """x_new = bf16(x + bf16(dt * (-v))) on dense [rows, C] matrices (the kernel indexes x, v and x_new flat)."""
     _req(x, BF16, "x"); _req(v, BF16, "v"); _req(x_new, BF16, "x_new")
     rows, Cc = x.shape
+    if not v.is_contiguous():
+        v = v.contiguous()                   # e.g. a foreign model returning a column slice y[..., :64]
+    for name, t in (("x", x), ("v", v), ("x_new", x_new)):
+        if tuple(t.shape) != (rows, Cc) or t.stride(0) != Cc:
+            raise ValueError(f"euler_update: {name} must be a dense [{rows}, {Cc}] matrix, got shape {tuple(t.shape)} strides {t.stride()}")
     check(_lib.lib().vcb_euler_update(x.data_ptr(), v.data_ptr(), dt_bf16, x_new.data_ptr(), _p(model_in),
                                       0 if model_in is None else model_in.stride(0), rows, Cc, _stream()),
           "vcb_euler_update")

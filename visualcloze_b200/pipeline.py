@@ -87,10 +87,38 @@ def _patchify(lat: torch.Tensor) -> torch.Tensor:
     return lat.reshape(b, c, H // 2, 2, W // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(b, (H // 2) * (W // 2), c * 4)
 
 
+def _load_file(path: str, device) -> dict:
+    """safetensors (BFL / diffusers releases) or a torch checkpoint (the LoRA files written by train.py:690-705)."""
+    if str(path).endswith(".safetensors"):
+        from safetensors.torch import load_file
+        return load_file(path, device=str(device))
+    return torch.load(path, map_location=device)
+
+
+def _expand_state_dict(model, sd: dict) -> dict:
+    """``optionally_expand_state_dict`` (models/util.py:456-472): zero-expand tensors smaller than the model's parameter
+    (FLUX.1-dev ``img_in`` 64 -> 384 input channels when a non-Fill base is given)."""
+    own = dict(model.named_parameters())
+    for name, t in list(sd.items()):
+        p = own.get(name)
+        if p is not None and tuple(t.shape) != tuple(p.shape):
+            big = torch.zeros_like(p, device=t.device)
+            big[tuple(slice(0, d) for d in t.shape)] = t
+            sd[name] = big
+    return sd
+
+
 class VisualClozeModel:
     def __init__(self, model_path=None, model_name="flux-dev-fill-lora", max_length=512, lora_rank=256, atol=1e-6, rtol=1e-3,
                  solver="euler", time_shifting_factor=1, resolution=384, precision="bf16", *, model=None, ae_decoder=None,
-                 ae_encoder=None, t5=None, clip=None, encode=None, device=None):
+                 ae_encoder=None, t5=None, clip=None, encode=None, device=None, flux_ckpt=None, ae_ckpt=None):
+        """Positional arguments as the reference (visualcloze.py:79-82).  The reference constructor also pulls the base
+        FLUX.1-Fill-dev weights (``load_flow_model``: ``$FLUX_DEV_FILL`` or a hub download) and the FLUX VAE
+        (``AutoencoderKL.from_pretrained``); there is no network on the inference box, so here they come from files:
+        ``flux_ckpt`` (default ``$FLUX_DEV_FILL``, BFL safetensors or a torch file) and ``ae_ckpt`` (default ``$AE``; BFL
+        ``ae.safetensors`` or diffusers ``vae/diffusion_pytorch_model.safetensors`` -- keys are converted).  Pre-built
+        ``model`` / ``ae_decoder`` / ``ae_encoder`` objects are used as they are.  Nothing is ever run on never-loaded
+        parameters: the engines refuse to pack them."""
         if precision != "bf16":
             raise NotImplementedError("the sm_100a kernels implement the reference's default bf16 path only")
         if model_name != "flux-dev-fill-lora":
@@ -100,22 +128,45 @@ class VisualClozeModel:
         self.max_length, self.lora_rank = max_length, lora_rank
         self.device = torch.device(device if device is not None else "cuda")
         self.dtype = torch.bfloat16
+        import os
+        flux_ckpt = flux_ckpt or os.getenv("FLUX_DEV_FILL")
+        ae_ckpt = ae_ckpt or os.getenv("AE")
         if model is None:
             with torch.device(self.device):
                 model = FluxLoraWrapper(lora_rank=lora_rank, params=flux_dev_fill_params())
+            if flux_ckpt is not None:                               # load_flow_model (models/util.py:406-411)
+                sd = _expand_state_dict(model, _load_file(flux_ckpt, self.device))
+                res = model.load_state_dict(sd, strict=False)
+                if res.unexpected_keys:
+                    raise ValueError(f"{flux_ckpt}: {len(res.unexpected_keys)} keys do not belong to the flux-dev-fill geometry, "
+                                     f"e.g. {res.unexpected_keys[:3]}")
+                del sd
         self.model = model
         if model_path is not None:
-            ckpt = torch.load(model_path, map_location=self.device)
-            self.model.load_state_dict(ckpt, strict=False)          # LoRA tensors on top of the base (visualcloze.py:111-112)
+            ckpt = _load_file(model_path, self.device)
+            res = self.model.load_state_dict(ckpt, strict=False)    # LoRA tensors on top of the base (visualcloze.py:111-112)
+            if res.unexpected_keys:
+                raise ValueError(f"{model_path}: unexpected keys, e.g. {res.unexpected_keys[:3]}")
             del ckpt
+        ae_sd = _load_file(ae_ckpt, self.device) if ae_ckpt is not None and (ae_decoder is None or (ae_encoder is None and encode is None)) else None
         if ae_decoder is None:
             with torch.device(self.device):
                 ae_decoder = AutoEncoderDecoder()
+            if ae_sd is not None:
+                ae_decoder.load_state_dict(ae_sd, strict=True)
         self.ae = ae_decoder
         if ae_encoder is None and encode is None:
             with torch.device(self.device):
                 ae_encoder = AutoEncoderEncoder()
+            if ae_sd is not None:
+                ae_encoder.load_state_dict(ae_sd, strict=True)
         self.ae_encoder = ae_encoder
+        # fail at construction, not at the first image: a drop-in constructor must not leave torch.empty weights behind
+        for what, mod in (("FLUX.1-Fill base weights (flux_ckpt= / $FLUX_DEV_FILL)", self.model), ("VAE decoder (ae_ckpt= / $AE)", self.ae),
+                          ("VAE encoder (ae_ckpt= / $AE, or pass encode=)", self.ae_encoder)):
+            missing = mod.uninitialized() if (mod is not None and hasattr(mod, "uninitialized")) else []
+            if missing:
+                raise RuntimeError(f"VisualClozeModel: {what}: {len(missing)} parameters were never loaded (e.g. {missing[:3]})")
         self.t5, self.clip, self.encode = t5, clip, encode
         self.sampler = Sampler(create_transport("Linear", "velocity", do_shift=True))
         self.sample_fn = self._make_sample_fn(30, True, self.time_shifting_factor, None)

@@ -114,10 +114,11 @@ def denoise(model, img: Tensor, img_ids: Tensor, txt: Tensor, txt_ids: Tensor, v
         t_vec = torch.full((B,), t_curr, dtype=img.dtype, device=img.device)
         pred = model(img=torch.cat((img, img_cond), dim=-1) if img_cond is not None else img, img_ids=img_ids, txt=txt,
                      txt_ids=txt_ids, y=vec, timesteps=t_vec, txt_mask=txt_mask, img_mask=img_mask, guidance=guidance_vec)
-        # img + (t_prev - t_curr) * pred  ==  euler_update with v = -pred, dt = t_prev - t_curr (python float scalar)
-        dt = float(torch.tensor(t_prev - t_curr, dtype=img.dtype))
+        # img + (t_prev - t_curr) * pred (:358): a python-float scalar is an fp32 opmath scalar (NOT rounded to bf16 first, unlike
+        # the 0-dim tensor dt of the torchdiffeq path): bf16(img + bf16(fp32(dt) * pred)).  The kernel computes
+        # x + bf16(dt * (-v)); the sign moves into dt, which is exact.
         new = torch.empty_like(img)
-        ops.euler_update(img.reshape(B * Li, -1), (-pred).reshape(B * Li, -1), dt, new.reshape(B * Li, -1))
+        ops.euler_update(img.reshape(B * Li, -1), pred.reshape(B * Li, -1), -(t_prev - t_curr), new.reshape(B * Li, -1))
         img = new
     return img
 

@@ -126,8 +126,10 @@ def _euler_sample(x, model, model_kwargs, t0, t1, num_steps, do_shift, time_shif
     n_eval = int(num_steps) - 1
     kw = dict(model_kwargs)                       # the caller's dict is not mutated (transport.py:194-196 pops a copy)
     cond = kw.pop("cond", None)
-    # FLUX time fed to the model: ones(B) * t -> 1 - t (integrators.py:109, transport.py:384), fp32
-    t_vec = th.ones(n_eval, B) * t[:-1, None]
+    # FLUX time fed to the model: ones(B) * t -> 1 - t (integrators.py:109, transport.py:384), fp32.  torchdiffeq wraps the
+    # ODE function in _PerturbFunc, which casts the evaluation time to the STATE dtype (t.to(y.abs().dtype)): with the bf16
+    # latent the model sees 1 - bf16(tau_k) (up to ~2 units of 1000 t near tau = 1).  dt keeps the fp32 grid.
+    t_vec = th.ones(n_eval, B) * t[:-1, None].to(x.dtype).float()
     flux_t = th.ones_like(t_vec) * (1 - t_vec)
     # dt is a 0-dim fp32 tensor multiplied into a bf16 tensor: it acts as a bf16 scalar
     dts = [float((t[k + 1] - t[k]).to(th.bfloat16)) for k in range(n_eval)]

@@ -67,6 +67,48 @@ def decoder_param_shapes(p: AutoEncoderParams) -> dict[str, tuple]:
     return sh
 
 
+def diffusers_vae_to_bfl(sd: dict) -> dict:
+    """Rename diffusers ``AutoencoderKL`` keys (FLUX.1-dev ``vae/``; what visualcloze.py:100 loads) to the BFL / in-repo
+    ``AutoEncoder`` names (models/modules/autoencoder.py).  Pure renaming plus the attention projections' Linear [C, C] ->
+    1x1 conv [C, C, 1, 1] view; the up path is numbered in the opposite direction (``up_blocks.i`` == ``up.(n-1-i)``)."""
+    import re
+    n_up = 1 + max([int(m.group(1)) for k in sd for m in [re.match(r"decoder\.up_blocks\.(\d+)\.", k)] if m] or [3])
+    res_names = {"conv_shortcut": "nin_shortcut"}
+    attn_names = {"group_norm": "norm", "to_q": "q", "to_k": "k", "to_v": "v", "to_out.0": "proj_out"}
+    out = {}
+    for k, v in sd.items():
+        m = re.match(r"(encoder|decoder)\.(.*)", k)
+        if not m:
+            continue                                     # quant_conv / post_quant_conv: absent in the FLUX VAE
+        half, rest = m.groups()
+        nk = None
+        if (mm := re.match(r"down_blocks\.(\d+)\.resnets\.(\d+)\.(\w+)\.(weight|bias)", rest)):
+            i, j, what, wb = mm.groups()
+            nk = f"down.{i}.block.{j}.{res_names.get(what, what)}.{wb}"
+        elif (mm := re.match(r"down_blocks\.(\d+)\.downsamplers\.0\.conv\.(weight|bias)", rest)):
+            nk = f"down.{mm.group(1)}.downsample.conv.{mm.group(2)}"
+        elif (mm := re.match(r"up_blocks\.(\d+)\.resnets\.(\d+)\.(\w+)\.(weight|bias)", rest)):
+            i, j, what, wb = mm.groups()
+            nk = f"up.{n_up - 1 - int(i)}.block.{j}.{res_names.get(what, what)}.{wb}"
+        elif (mm := re.match(r"up_blocks\.(\d+)\.upsamplers\.0\.conv\.(weight|bias)", rest)):
+            nk = f"up.{n_up - 1 - int(mm.group(1))}.upsample.conv.{mm.group(2)}"
+        elif (mm := re.match(r"mid_block\.resnets\.(\d+)\.(\w+)\.(weight|bias)", rest)):
+            j, what, wb = mm.groups()
+            nk = f"mid.block_{int(j) + 1}.{res_names.get(what, what)}.{wb}"
+        elif (mm := re.match(r"mid_block\.attentions\.0\.(group_norm|to_q|to_k|to_v|to_out\.0)\.(weight|bias)", rest)):
+            what, wb = mm.groups()
+            nk = f"mid.attn_1.{attn_names[what]}.{wb}"
+            if wb == "weight" and what != "group_norm" and v.dim() == 2:
+                v = v[:, :, None, None]
+        elif (mm := re.match(r"conv_norm_out\.(weight|bias)", rest)):
+            nk = f"norm_out.{mm.group(1)}"
+        elif re.match(r"(conv_in|conv_out)\.(weight|bias)", rest):
+            nk = rest
+        if nk is not None:
+            out[f"{half}.{nk}"] = v
+    return out
+
+
 def _attach(root: nn.Module, dotted: str, param: nn.Parameter) -> None:
     node = root
     parts = dotted.split(".")
@@ -87,6 +129,36 @@ class AutoEncoderDecoder(nn.Module):
         self._h = None
         self._key = None
         self._ws = None
+        self._initialized: set[str] = set()
+
+    # ---- weights: parameters are allocated with torch.empty; packing never-loaded memory must fail loudly ---------------
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """Accepts the BFL ``ae.safetensors`` names (== models/modules/autoencoder.py) restricted to this half's prefix, or
+        diffusers ``AutoencoderKL`` names (what the reference pipeline loads, visualcloze.py:100) -- converted on the fly."""
+        prefix = "encoder." if isinstance(self, AutoEncoderEncoder) else "decoder."
+        sd = dict(state_dict)
+        if any(".up_blocks." in k or ".down_blocks." in k or ".mid_block." in k for k in sd):
+            sd = diffusers_vae_to_bfl(sd)
+        own = {n for n, _ in self.named_parameters()}
+        if not strict:
+            sd = {k: v for k, v in sd.items() if k in own}
+        else:
+            sd = {k: v for k, v in sd.items() if k.startswith(prefix)}
+        res = super().load_state_dict(sd, strict=strict, assign=assign)
+        self._initialized |= own & set(sd.keys())
+        return res
+
+    def mark_initialized(self) -> None:
+        self._initialized = {n for n, _ in self.named_parameters()}
+
+    def uninitialized(self) -> list[str]:
+        return [n for n, _ in self.named_parameters() if n not in self._initialized]
+
+    def _require_weights(self) -> None:
+        missing = self.uninitialized()
+        if missing:
+            raise _lib.VcbError(f"{len(missing)} VAE parameters were never loaded (e.g. {missing[:3]}): pass ae_ckpt= / call "
+                                "load_state_dict or init_synthetic() first")
 
     def init_synthetic(self, seed: int = 0) -> "AutoEncoderDecoder":
         dev = next(self.parameters()).device
@@ -100,6 +172,7 @@ class AutoEncoderDecoder(nn.Module):
                 else:
                     p.copy_(0.02 * torch.randn(p.shape, generator=g, device=dev))
         self._key = None
+        self.mark_initialized()
         return self
 
     # ---- packing --------------------------------------------------------------------------------
@@ -135,6 +208,7 @@ class AutoEncoderDecoder(nn.Module):
         return r
 
     def _engine(self):
+        self._require_weights()
         key = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._h is not None and key == self._key:
             return self._h
@@ -262,8 +336,10 @@ class AutoEncoderEncoder(AutoEncoderDecoder):
         self._h = None
         self._key = None
         self._ws = None
+        self._initialized = set()
 
     def _engine(self):
+        self._require_weights()
         key = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._h is not None and key == self._key:
             return self._h
