@@ -45,14 +45,14 @@ def solver_grid(num_steps: int, seq_len: int, do_shift: bool = True, time_shifti
 def sample_ode(x: torch.Tensor, model_fn, model_kwargs: dict, num_steps: int, do_shift: bool = True,
                time_shifting_factor=None, strength=None) -> torch.Tensor:
     """Returns the whole trajectory [num_steps, B, Li, C] like the reference sampler."""
-    t = solver_grid(num_steps, x.shape[1], do_shift, time_shifting_factor, strength)
+    t = solver_grid(num_steps, x.shape[1], do_shift, time_shifting_factor, strength).to(x.device)   # integrators.py:112
     kw = dict(model_kwargs)
     cond = kw.pop("cond", None)
     ys = [x]
     y = x
     for k in range(num_steps - 1):
         tau = t[k].to(y.dtype)                                     # torchdiffeq _PerturbFunc: t.to(y.abs().dtype)
-        t_vec = torch.ones(y.shape[0]) * tau                       # integrators.py:109
+        t_vec = torch.ones(y.shape[0]).to(y.device) * tau          # integrators.py:109
         t_flux = torch.ones_like(t_vec) * (1 - t_vec)              # transport.py:384
         inp = y if cond is None else torch.cat((y, cond), dim=-1)  # transport.py:194-196
         f = -model_fn(inp, timesteps=t_flux, **kw)

@@ -1,0 +1,205 @@
+"""Parity at BASELINE.json's REAL sizes on the B200, against (a) the UNMODIFIED reference modules of ``oracle/_ref`` executed
+under ``torch.autocast("cuda", bf16)`` with flash-attn -- the authoritative oracle of SURVEY.md 8c -- and (b) the restated
+oracle (``oracle/flux_oracle.py``, ``cuda_bf16`` mode) executed on the same GPU.
+
+  cfg B  full depth 19 + 38, hidden 3072, 24 heads, LoRA r=256, L = 3968: one evaluation and a 3-evaluation trajectory
+  cfg D  L = 7424 (3x4 grid) and cfg E  L = 4608 (SDEdit 1024^2): one evaluation each on the same weights
+  attention alone at 24 heads, L in {3968, 7424}: vcb (exact and fixed-reference softmax) vs flash-attn vs an fp32 reference
+  VAE decode of one cfg-B grid row (latent 16 x 48 x 144 -> 3 x 384 x 1152), mid-block attention over 6912 pixels
+
+Tolerances: forward rel-L2 <= 2e-2, trajectory (final latent) <= 5e-2, decoded image PSNR >= 35 dB.  Every
+comparison is appended to ``gpurun_out/fullsize_parity.json`` together with the reference-vs-reference noise floor (the
+reference on flash-attn vs the restated oracle on fp32-softmax math: two implementations of the same algorithm), which is
+what the tolerances have to be read against.
+"""
+import dataclasses
+import json
+import math
+import os
+
+import pytest
+import torch
+
+from conftest import REPO, rel_l2
+
+pytestmark = pytest.mark.gpu
+BF16 = torch.bfloat16
+REPORT = os.path.join(REPO, "gpurun_out", "fullsize_parity.json")
+
+
+def _record(key, **vals):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    data = json.load(open(REPORT)) if os.path.exists(REPORT) else {}
+    data[key] = {k: (float(v) if isinstance(v, (int, float)) else v) for k, v in vals.items()}
+    json.dump(data, open(REPORT, "w"), indent=1, sort_keys=True)
+    print(f"[fullsize] {key}: " + ", ".join(f"{k}={v:.3e}" if isinstance(v, float) else f"{k}={v}" for k, v in vals.items()))
+
+
+def _cuda(d):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in d.items()}
+
+
+@pytest.fixture(scope="module")
+def full():
+    """ONE full-size model shared by ours, the reference (parameters assigned, not copied) and the restated oracle."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from oracle import flux_oracle as fo
+    from oracle import ref_runner as rr
+    import visualcloze_b200.model as M
+    P = M.flux_dev_fill_params()
+    with torch.device("cuda"):
+        ours = M.FluxLoraWrapper(lora_rank=256, params=P)
+    ours.init_synthetic(0)
+    sd = dict(ours.state_dict())
+    ref = rr.build_flux(dataclasses.asdict(P), 256, sd) if rr.available() else None
+    cfg = fo.FluxConfig(**dataclasses.asdict(P), lora_rank=256)
+    return dict(ours=ours, ref=ref, sd=sd, cfg=cfg, fo=fo, rr=rr)
+
+
+def _inputs(workload, seed=1234):
+    import bench
+    x, kw, Li, Lt = bench.make_inputs(workload, seed)
+    return x, kw, Li, Lt
+
+
+def _one_eval(full, workload, t=0.63):
+    x, kw, Li, Lt = _inputs(workload)
+    cond = kw.pop("cond")
+    inp = _cuda(dict(kw, img=torch.cat((x, cond), dim=-1), timesteps=torch.tensor([t])))
+    out = full["ours"](**inp).float()
+    assert out.shape == (1, Li, 64) and torch.isfinite(out).all()
+    orc = full["fo"].flux_forward(full["sd"], full["cfg"], **inp, mode="cuda_bf16").float()
+    res = dict(tokens=Li + Lt, ours_vs_oracle=rel_l2(out, orc), out_rms=float(out.pow(2).mean().sqrt()))
+    if full["ref"] is not None:
+        ref = full["rr"].flux_forward(full["ref"], **inp).float()
+        res.update(ours_vs_reference=rel_l2(out, ref), noise_floor_oracle_vs_reference=rel_l2(orc, ref))
+    return res
+
+
+def test_cfgB_full_depth_forward_vs_reference_and_oracle(full):
+    r = _one_eval(full, "B")
+    _record("cfgB_forward_19+38_L3968", **r)
+    assert r["ours_vs_oracle"] < 2e-2, r
+    if "ours_vs_reference" in r:
+        # the bar is SURVEY 8c's 2e-2; where two faithful implementations of the reference already differ by more than that
+        # at this depth (the measured floor), ours may not be further from the reference than 1.25 x that floor
+        assert r["ours_vs_reference"] < max(2e-2, 1.25 * r["noise_floor_oracle_vs_reference"]), r
+    else:
+        pytest.skip("oracle/_ref absent: compared with the restated oracle only")
+
+
+@pytest.mark.parametrize("workload", ["D", "E"])
+def test_cfgD_cfgE_forward(full, workload):
+    r = _one_eval(full, workload, t=0.41)
+    _record(f"cfg{workload}_forward_19+38_L{int(r['tokens'])}", **r)
+    assert r["ours_vs_oracle"] < 2e-2, r
+    if "ours_vs_reference" in r:
+        assert r["ours_vs_reference"] < max(2e-2, 1.25 * r["noise_floor_oracle_vs_reference"]), r
+
+
+def test_cfgB_trajectory_3_evaluations_vs_reference_sampler(full):
+    """Sampler.sample_ode(num_steps=4) through the public API vs the reference ``transport`` package (torchdiffeq stand-in)
+    driving the reference model, and vs the restated sampler + model oracle."""
+    import visualcloze_b200.transport as T
+    from oracle import sampler_oracle as so
+    x, kw, Li, Lt = _inputs("B")
+    xg, kwg = x.cuda(), _cuda(kw)
+    fn = T.Sampler(T.create_transport("Linear", "velocity", do_shift=True)).sample_ode(
+        sampling_method="euler", num_steps=4, atol=1e-6, rtol=1e-3, reverse=False, do_shift=True, time_shifting_factor=1)
+    traj = fn(xg, full["ours"].forward, kwg).float()
+    assert traj.shape == (4, 1, Li, 64) and torch.equal(traj[0], xg.float())
+
+    def model_fn(inp, timesteps, **k):
+        return full["fo"].flux_forward(full["sd"], full["cfg"], img=inp, timesteps=timesteps.cuda(), **k, mode="cuda_bf16")
+
+    orc = so.sample_ode(xg, model_fn, kwg, num_steps=4, do_shift=True, time_shifting_factor=1).float()
+    res = dict(final_vs_oracle=rel_l2(traj[-1], orc[-1]), step1_vs_oracle=rel_l2(traj[1], orc[1]))
+    if full["ref"] is not None:
+        ref = full["rr"].sample_ode(full["ref"], xg, kwg, num_steps=4, do_shift=True, time_shifting_factor=1).float()
+        res.update(final_vs_reference=rel_l2(traj[-1], ref[-1]), step1_vs_reference=rel_l2(traj[1], ref[1]),
+                   noise_floor_final_oracle_vs_reference=rel_l2(orc[-1], ref[-1]))
+    _record("cfgB_trajectory_3eval", **res)
+    assert res["final_vs_oracle"] < 5e-2, res
+    if "final_vs_reference" in res:
+        assert res["final_vs_reference"] < 5e-2, res
+
+
+@pytest.mark.parametrize("L", [3968, 7424])
+def test_attention_24_heads_vs_flash_attn_and_fp32(L):
+    """The attention kernel on the headline grid (24 heads; 31 / 58 key tiles), inputs shaped like QK-RMSNorm leaves them,
+    both softmax variants, against flash-attn (what models/math.py:85 calls) and an fp32 softmax reference."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from visualcloze_b200 import ops
+    heads, H = 24, 3072
+    g = torch.Generator(device="cuda").manual_seed(L)
+    qkv = torch.randn(L, 3, heads, 128, generator=g, device="cuda")
+    qa, ka = 1.25, 1.1
+    for i, a in ((0, qa), (1, ka)):
+        qkv[:, i] = a * qkv[:, i] / qkv[:, i].pow(2).mean(-1, keepdim=True).sqrt()
+    qkv = qkv.reshape(L, 3 * H).to(BF16)
+    q, k, v = (qkv[:, i * H:(i + 1) * H].reshape(1, L, heads, 128) for i in range(3))
+    # fp32 reference: softmax(q k^T / sqrt(128)) v with fp32 probabilities
+    truth = torch.nn.functional.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2),
+                                                             v.float().transpose(1, 2)).transpose(1, 2).reshape(L, H)
+    bound = qa * ka * math.sqrt(128.0) * math.log2(math.e) * 1.03
+    res = {}
+    for name, sb in (("exact", 0.0), ("bounded", bound)):
+        out = torch.full((L, H), 7.0, dtype=BF16, device="cuda")
+        ops.attention(qkv, 1, L, heads, out, q_col=0, k_col=H, v_col=2 * H, score_bound_log2=sb)
+        torch.cuda.synchronize()
+        res[f"vcb_{name}_vs_fp32"] = rel_l2(out.float(), truth)
+        res[f"_{name}"] = out
+    try:
+        from oracle import ref_runner as rr
+        fa = rr.flash_attention(q, k, v).reshape(L, H)
+        res["flash_attn_vs_fp32"] = rel_l2(fa.float(), truth)
+        res["vcb_exact_vs_flash_attn"] = rel_l2(res["_exact"].float(), fa.float())
+    except ImportError:
+        pass
+    res["bounded_vs_exact"] = rel_l2(res.pop("_bounded").float(), res.pop("_exact").float())
+    _record(f"attention_24h_L{L}", **res)
+    assert res["vcb_exact_vs_fp32"] < 4e-3 and res["vcb_bounded_vs_fp32"] < 4e-3, res
+    if "flash_attn_vs_fp32" in res:       # no further from the fp32 result than 1.5 x the library the reference calls
+        assert res["vcb_exact_vs_fp32"] < 1.5 * res["flash_attn_vs_fp32"] + 1e-4, res
+        assert res["vcb_bounded_vs_fp32"] < 1.5 * res["flash_attn_vs_fp32"] + 1e-4, res
+
+
+def test_vae_decode_cfgB_row_vs_reference_autoencoder():
+    """One grid row of cfg B (latent 16 x 48 x 144 -> 3 x 384 x 1152; mid-block attention over 6912 pixels) against the reference
+    AutoEncoder (fp32 on the GPU = the arithmetic truth; bf16 = what the pipeline runs, visualcloze.py:100) on the same weights."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from oracle import ref_runner as rr
+    from oracle import vae_oracle as vo
+    from visualcloze_b200 import vae as V
+    dec = V.AutoEncoderDecoder(device="cuda").init_synthetic(5)
+    sd = {k: v for k, v in dec.state_dict().items()}
+    g = torch.Generator().manual_seed(11)
+    z = torch.randn(1, 16, 48, 144, generator=g).cuda()
+    ours = dec.decode(z).float()                                    # [1, 3, 384, 1152], raw decoder output (autoencoder.py:307-309)
+    assert ours.shape == (1, 3, 384, 1152) and torch.isfinite(ours).all()
+    P = dec.params
+    cfg = vo.VaeConfig(ch=P.ch, out_ch=P.out_ch, ch_mult=list(P.ch_mult), num_res_blocks=P.num_res_blocks, z_channels=P.z_channels)
+    orc = vo.decode({k: v.float() for k, v in sd.items()}, cfg, z).float()
+
+    def psnr(a, b):
+        # the pipeline maps the decoder output through (x + 1) / 2 and clamps to [0, 1] (visualcloze.py:431-433): compare the
+        # clamped images, peak-to-peak 2 in decoder units
+        return float(10 * torch.log10(4.0 / (a.clamp(-1, 1) - b.clamp(-1, 1)).pow(2).mean().clamp_min(1e-12)))
+    res = dict(psnr_vs_oracle_fp32=psnr(ours, orc), rel_l2_vs_oracle_fp32=rel_l2(ours, orc))
+    if rr.available():
+        kw = dict(resolution=256, in_channels=3, ch=P.ch, out_ch=P.out_ch, ch_mult=list(P.ch_mult), num_res_blocks=P.num_res_blocks,
+                  z_channels=P.z_channels, scale_factor=P.scale_factor, shift_factor=P.shift_factor)
+        ae32 = rr.build_autoencoder(kw, sd, "cuda", torch.float32)
+        with torch.no_grad():
+            ref32 = ae32.decode(z).float()
+            ae16 = ae32.to(BF16)
+            ref16 = ae16.decode(z.to(BF16)).float()
+        res.update(psnr_vs_reference_fp32=psnr(ours, ref32), psnr_vs_reference_bf16=psnr(ours, ref16),
+                   noise_floor_reference_bf16_vs_fp32_psnr=psnr(ref16, ref32), oracle_vs_reference_fp32=rel_l2(orc, ref32))
+    _record("vae_decode_48x144", **res)
+    assert res["psnr_vs_oracle_fp32"] >= 35.0, res
+    if "psnr_vs_reference_fp32" in res:
+        assert res["psnr_vs_reference_fp32"] >= 35.0, res
