@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define VCB_ABI_VERSION 3
+#define VCB_ABI_VERSION 4
 #define VCB_SP_MAX 8          /* ranks of one sequence-parallel group (one NVSwitch domain) */
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -116,13 +116,19 @@ int vcb_attention_fwd_sp(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t
 /* General form.  score_bound_log2 > 0 promises |q.k| * 128^-0.5 * log2(e) <= score_bound_log2 for every query/key pair (true
  * after QK-RMSNorm: |q| <= max|q_scale| * sqrt(128), layers.py:63-84): softmax is shift invariant, so the kernel then uses
  * exp2(s - bound) with no running row max -- same result up to rounding, shorter dependency chain.  Must be <= 64 (fp32 /
- * bf16 exponent range); 0 = exact online softmax.  out_peers != NULL selects the sequence-parallel output routing. */
+ * bf16 exponent range); 0 = exact online softmax.  out_peers != NULL selects the sequence-parallel output routing.
+ * schedule: AUTO picks the persistent kernel (one CTA per SM, equal contiguous shares of the (query tile x key tile) space,
+ * units cut at a share boundary are folded from fp32 partials) for unpadded batches, else one CTA per query pair. */
+#define VCB_ATTN_SCHED_AUTO 0
+#define VCB_ATTN_SCHED_PER_PAIR 1
+#define VCB_ATTN_SCHED_PERSISTENT 2
 typedef struct vcb_attn_args {
     const void* qkv; int64_t ld_qkv; int32_t q_col, k_col, v_col;
     const int32_t* seqlens; int32_t B, L, heads;
     void* out; int64_t ldo; int32_t out_col_offset;
     void* const* out_peers; int32_t world, rows_per_rank;
     float score_bound_log2;
+    int32_t schedule;            /* VCB_ATTN_SCHED_* ; 0 = auto */
 } vcb_attn_args;
 int vcb_attention_fwd_ex(const vcb_attn_args* args, void* stream);
 

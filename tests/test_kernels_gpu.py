@@ -524,3 +524,55 @@ print("streamk ok", err)
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, VCB_STREAMK="1"), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "streamk ok" in r.stdout, r.stdout + r.stderr
+
+
+# ------------------------------------------------------------------------------------------------
+# attention: persistent schedule (attn4) -- units cut at a CTA's share boundary are folded from fp32 partials
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1, 2, 128), (1, 2, 200), (1, 2, 1088), (1, 3, 1500), (2, 2, 520), (1, 1, 640), (1, 2, 3968)])
+@pytest.mark.parametrize("bounded", [False, True])
+def test_attention_persistent_schedule_matches_per_pair_and_oracle(ops, shape, bounded):
+    """vcb_attn_args.schedule: PERSISTENT (one CTA per SM, equal shares, 1..4 pieces per cut unit) vs PER_PAIR vs the oracle, for
+    both softmax variants; shapes chosen so shares cut units mid-way, across heads, and (L = 200, 1500, 520) at ragged tile edges."""
+    from oracle import flux_oracle as fo
+    B, heads, L = shape
+    H = heads * 128
+    qkv = _randn(B * L, 3 * H, seed=L + heads).float().reshape(B * L, 3, heads, 128)
+    qa, ka = 1.3, 0.9
+    for i, a in ((0, qa), (1, ka)):
+        qkv[:, i] = a * qkv[:, i] / qkv[:, i].pow(2).mean(-1, keepdim=True).sqrt()
+    qkv = qkv.reshape(B * L, 3 * H).to(BF16)
+    sb = qa * ka * math.sqrt(128.0) * math.log2(math.e) * 1.03 if bounded else 0.0
+    outs = {}
+    for sched in (1, 2):
+        out = torch.full((B * L, H), 5.0, dtype=BF16, device="cuda")
+        ops.attention(qkv.cuda(), B, L, heads, out, q_col=0, k_col=H, v_col=2 * H, score_bound_log2=sb, schedule=sched)
+        torch.cuda.synchronize()
+        outs[sched] = out.cpu()
+    q, k, v = fo._split_heads(qkv.reshape(B, L, 3 * H), heads)
+    ref = fo.joint_attention(q, k, v, torch.ones(B, L, 64), torch.zeros(B, L, 64), torch.ones(B, L, dtype=torch.int32),
+                             fo.Numerics("cuda_bf16")).reshape(B * L, H)
+    assert rel_l2(outs[2], ref) < 8e-3, _stats(outs[2], ref)
+    assert rel_l2(outs[2], outs[1]) < 5e-3, _stats(outs[2], outs[1])
+
+
+def test_attention_persistent_back_to_back_launches_reuse_the_workspace(ops):
+    """the per-stream (O, l, m) slots and flags are reused by every launch (epoch-tagged): 20 launches in a row must all agree"""
+    B, heads, L = 1, 4, 2000
+    H = heads * 128
+    qkv = _randn(B * L, 3 * H, seed=77).cuda()
+    outs = []
+    for i in range(20):
+        out = torch.empty(B * L, H, dtype=BF16, device="cuda")
+        ops.attention(qkv, B, L, heads, out, q_col=0, k_col=H, v_col=2 * H, schedule=2)
+        outs.append(out)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
+def test_attention_persistent_rejects_padded_batches(ops):
+    qkv = _randn(2 * 256, 3 * 256, seed=1).cuda()
+    sl = torch.tensor([256, 100], dtype=torch.int32, device="cuda")
+    with pytest.raises(Exception, match="persistent"):
+        ops.attention(qkv, 2, 256, 2, torch.empty(512, 256, dtype=BF16, device="cuda"), q_col=0, k_col=256, v_col=512, seqlens=sl, schedule=2)

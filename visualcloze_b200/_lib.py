@@ -6,7 +6,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvcb200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 SP_MAX = 8
 
 _lib = None
@@ -97,7 +97,7 @@ class AttnArgs(C.Structure):
                 ("seqlens", C.c_void_p), ("B", C.c_int32), ("L", C.c_int32), ("heads", C.c_int32),
                 ("out", C.c_void_p), ("ldo", C.c_int64), ("out_col_offset", C.c_int32),
                 ("out_peers", C.POINTER(C.c_void_p)), ("world", C.c_int32), ("rows_per_rank", C.c_int32),
-                ("score_bound_log2", C.c_float)]
+                ("score_bound_log2", C.c_float), ("schedule", C.c_int32)]
 
 
 class FluxConfigC(C.Structure):

@@ -11,6 +11,7 @@
 #include "attn_sm100.cuh"
 #include "attn2_sm100.cuh"
 #include "attn3_sm100.cuh"
+#include "attn4_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm_sm100.cuh"
 #include "host_util.cuh"
@@ -336,9 +337,33 @@ extern "C" int vcb_conv3x3_nhwc(const void* x, const void* w, const float* bias,
 // attention
 // ------------------------------------------------------------------------------------------------
 namespace {
+// workspace of the persistent attention kernel (attn4): one (O, l, m) slot and one flag per CTA, per stream; allocated on
+// first use (call once before CUDA-graph capture)
+struct AttnScratch { float* ws = nullptr; int* flags = nullptr; int epoch = 0; };
+inline AttnScratch* attn_scratch(cudaStream_t st) {
+    static std::mutex mu;
+    static std::map<cudaStream_t, AttnScratch> pool;
+    std::lock_guard<std::mutex> lk(mu);
+    AttnScratch& s = pool[st];
+    if (!s.ws) {
+        const size_t n = 160;                                  // >= number of SMs
+        if (cudaMalloc(&s.ws, n * kAttn4SlotFloats * sizeof(float)) != cudaSuccess) return nullptr;
+        if (cudaMalloc(&s.flags, n * sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(s.flags, 0, n * sizeof(int));
+    }
+    return &s;
+}
+// VCB_ATTN_PERSIST: unset = auto (persistent kernel whenever it applies), 0 = never (one CTA per query pair, attn3), 1 = same as auto
+inline int attn_persist_mode() {
+    static const int m = [] { const char* e = getenv("VCB_ATTN_PERSIST"); return e ? (atoi(e) ? 1 : 0) : -1; }();
+    return m;
+}
+
 int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_col, int32_t v_col,
                      const int32_t* seqlens, int32_t B, int32_t L, int32_t heads, void* out, int64_t ldo,
-                     int32_t out_col_offset, void* const* out_peers, int32_t world, int32_t rows_per_rank, float bound, void* stream) {
+                     int32_t out_col_offset, void* const* out_peers, int32_t world, int32_t rows_per_rank, float bound, int32_t schedule,
+                     void* stream) {
+    if (schedule < VCB_ATTN_SCHED_AUTO || schedule > VCB_ATTN_SCHED_PERSISTENT) return set_error("attention: unknown schedule %d", schedule);
     if (bound < 0.f || bound > 64.f) return set_error("attention: score_bound_log2 must be in [0, 64] (0 = exact online softmax)");
     if (!qkv || (!out && !out_peers) || B <= 0 || L <= 0 || heads <= 0) return set_error("attention: bad arguments");
     if (ld_qkv % 8 || ldo % 8 || q_col % 8 || k_col % 8 || v_col % 8 || out_col_offset % 8)
@@ -363,6 +388,10 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
             attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(attn_fwd4_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn4SmemBytes);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(attn_fwd4_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn4SmemBytes);
         const char* e = getenv("VCB_ATTN_V1");
         use_v1 = e ? atoi(e) : 0;
         e = getenv("VCB_ATTN_V2");
@@ -405,6 +434,28 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         count_launch();
         return 0;
     }
+    // Persistent schedule (attn4): unpadded batches with enough (query tile x key tile) work to give every SM a share of at
+    // least a few key tiles; right-padded batches, the sequence-parallel routing and the A/B variants stay on attn3.
+    const long long n_qt = (L + kAttnTile - 1) / kAttnTile;
+    const long long T = (long long)B * heads * n_qt * n_qt;
+    int pgrid = num_sms();
+    if (T / pgrid < 8) pgrid = (int)(T / 8 > 0 ? T / 8 : 1);           // tiny problems: fewer CTAs, >= 8 half-iterations each
+    // segments per CTA <= units per CTA + 2; beyond the kernel's list capacity (huge batches of short sequences) use attn3
+    const bool persist_ok = !seqlens && !out_peers && !use_v1 && !use_v2 && !pchunks4 && num_sms() <= 160 &&
+                            (long long)B * heads * ((n_qt + 1) / 2) / pgrid + 3 <= kAttn4MaxSegs;
+    if (schedule == VCB_ATTN_SCHED_PERSISTENT && !persist_ok)
+        return set_error("attention: the persistent schedule takes unpadded batches (seqlens == NULL), no sequence-parallel routing");
+    if (persist_ok && (schedule == VCB_ATTN_SCHED_PERSISTENT || (schedule == VCB_ATTN_SCHED_AUTO && attn_persist_mode() != 0))) {
+        const int grid = pgrid;
+        AttnScratch* sc = attn_scratch((cudaStream_t)stream);
+        if (!sc) return set_error("attention: workspace allocation failed");
+        AttnSkParams skp{sc->ws, sc->flags, ++sc->epoch};
+        cudaError_t e = fixed ? launch_pdl(attn_fwd4_tcgen05_kernel<true>, dim3(grid), dim3(kAttn3Threads), (size_t)kAttn4SmemBytes, (cudaStream_t)stream, 1, tm, p, skp)
+                              : launch_pdl(attn_fwd4_tcgen05_kernel<false>, dim3(grid), dim3(kAttn3Threads), (size_t)kAttn4SmemBytes, (cudaStream_t)stream, 1, tm, p, skp);
+        if (e != cudaSuccess) return set_error("attention (persistent) launch: %s", cudaGetErrorString(e));
+        count_launch();
+        return 0;
+    }
     if (use_v1) {
         dim3 grid((L + kAttnTile - 1) / kAttnTile, heads, B);
         attn_fwd_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmemBytes, (cudaStream_t)stream>>>(tm, p);
@@ -427,14 +478,15 @@ extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col,
                                  const int32_t* seqlens, int32_t B, int32_t L, int32_t heads, void* out, int64_t ldo,
                                  int32_t out_col_offset, void* stream) {
     if (!out) return set_error("attention: bad arguments");
-    return attention_launch(qkv, ld_qkv, q_col, k_col, v_col, seqlens, B, L, heads, out, ldo, out_col_offset, nullptr, 0, 0, 0.f, stream);
+    return attention_launch(qkv, ld_qkv, q_col, k_col, v_col, seqlens, B, L, heads, out, ldo, out_col_offset, nullptr, 0, 0, 0.f,
+                            VCB_ATTN_SCHED_AUTO, stream);
 }
 
 extern "C" int vcb_attention_fwd_ex(const vcb_attn_args* a, void* stream) {
     if (!a) return set_error("attention: null args");
     if (!a->out_peers && !a->out) return set_error("attention: bad arguments");
     return attention_launch(a->qkv, a->ld_qkv, a->q_col, a->k_col, a->v_col, a->seqlens, a->out_peers ? 1 : a->B, a->L, a->heads, a->out,
-                            a->ldo, a->out_col_offset, a->out_peers, a->world, a->rows_per_rank, a->score_bound_log2, stream);
+                            a->ldo, a->out_col_offset, a->out_peers, a->world, a->rows_per_rank, a->score_bound_log2, a->schedule, stream);
 }
 
 extern "C" int vcb_attention_fwd_sp(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_col, int32_t v_col, int32_t L,
@@ -442,7 +494,7 @@ extern "C" int vcb_attention_fwd_sp(const void* qkv, int64_t ld_qkv, int32_t q_c
                                     int32_t out_col_offset, void* stream) {
     if (!out_peers) return set_error("attention (sp): out_peers is null");
     return attention_launch(qkv, ld_qkv, q_col, k_col, v_col, nullptr, 1, L, heads, nullptr, ldo, out_col_offset, out_peers, world,
-                            rows_per_rank, 0.f, stream);
+                            rows_per_rank, 0.f, VCB_ATTN_SCHED_AUTO, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -91,14 +91,16 @@ def gemm_args(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: 
 
 
 def attention(qkv: torch.Tensor, B: int, L: int, heads: int, out: torch.Tensor, *, q_col: int, k_col: int, v_col: int,
-              seqlens: torch.Tensor | None = None, out_col_offset: int = 0, score_bound_log2: float = 0.0) -> torch.Tensor:
+              seqlens: torch.Tensor | None = None, out_col_offset: int = 0, score_bound_log2: float = 0.0,
+              schedule: int = 0) -> torch.Tensor:
     """qkv [B*L, ld] bf16 (post RoPE / QK-norm) -> out [B*L, ldo]; models/math.py:63-99.
     ``score_bound_log2`` > 0: promised bound of the scaled scores (vcb_attn_args) -> softmax without a running row max."""
     _req(qkv, BF16, "qkv"); _req(out, BF16, "out")
     if seqlens is not None:
         _req(seqlens, torch.int32, "seqlens")
-    if score_bound_log2:
+    if score_bound_log2 or schedule:
         a = _lib.AttnArgs()
+        a.schedule = int(schedule)
         a.qkv, a.ld_qkv, a.q_col, a.k_col, a.v_col = qkv.data_ptr(), qkv.stride(0), q_col, k_col, v_col
         a.seqlens, a.B, a.L, a.heads = _p(seqlens), B, L, heads
         a.out, a.ldo, a.out_col_offset, a.score_bound_log2 = out.data_ptr(), out.stride(0), out_col_offset, float(score_bound_log2)
