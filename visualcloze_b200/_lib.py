@@ -45,6 +45,8 @@ _SIGNATURES = {
     "vcb_reset_launch_count": (None, []),
     "vcb_profile_begin": (C.c_int, []),
     "vcb_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "vcb_profile_end_ex": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int32, C.c_void_p, C.c_int64,
+                                     C.POINTER(C.c_int64)]),
     "vcb_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "vcb_gemm_bf16_grouped": (C.c_int, [C.POINTER(GemmArgs), C.POINTER(GemmArgs), C.c_void_p]),
     "vcb_conv3x3_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
@@ -98,6 +100,25 @@ class AttnArgs(C.Structure):
                 ("out", C.c_void_p), ("ldo", C.c_int64), ("out_col_offset", C.c_int32),
                 ("out_peers", C.POINTER(C.c_void_p)), ("world", C.c_int32), ("rows_per_rank", C.c_int32),
                 ("score_bound_log2", C.c_float), ("schedule", C.c_int32)]
+
+
+class ProfRecord(C.Structure):
+    """struct vcb_prof_record (include/vcb200.h)."""
+    _fields_ = [("category", C.c_int32), ("ms", C.c_float), ("info", C.c_int32 * 4)]
+
+
+PROF_CATEGORIES = ("gemm", "attention", "ln_modulate", "other", "vae_conv3x3", "vae_elementwise")
+
+
+def profile_end(max_records: int = 0):
+    """-> ({category: (ms, launches)}, [ProfRecord...]) for everything launched since vcb_profile_begin (synchronises)."""
+    ms, n = (C.c_double * 6)(), (C.c_longlong * 6)()
+    recs = (ProfRecord * max_records)() if max_records else None
+    cnt = C.c_int64(0)
+    check(lib().vcb_profile_end_ex(ms, n, 6, C.cast(recs, C.c_void_p) if recs is not None else None, max_records, C.byref(cnt)),
+          "vcb_profile_end_ex")
+    out = {name: (ms[i], int(n[i])) for i, name in enumerate(PROF_CATEGORIES)}
+    return out, ([] if recs is None else list(recs[:min(int(cnt.value), max_records)]))
 
 
 class FluxConfigC(C.Structure):

@@ -245,7 +245,7 @@ int gemm_dispatch(const vcb_gemm_args* a, const vcb_gemm_args* a1, void* stream)
     float rate;
     pick_tile(batch, a->rows_per_batch + (a1 ? a1->M / batch : 0), a->N, a->K, head, a->cta_group ? a->cta_group : forced_cta_group(),
               a->block_n, &cg, &bn, &rate);
-    ProfScope prof(PROF_GEMM, stream);
+    ProfScope prof(PROF_GEMM, stream, a->M + (a1 ? a1->M : 0), a->N, a->K, a->epilogue | (bn << 8) | (cg << 16));
     Problem g0, g1;
     if (int rc = build_problem(a, bn, cg, &g0)) return rc;
     if (a1) {
@@ -311,7 +311,7 @@ extern "C" int vcb_conv3x3_nhwc(const void* x, const void* w, const float* bias,
     const int Ho = H / stride, Wo = W / stride;
     if (cin % 64 || cout % 8) return set_error("conv3x3: Cin must be a multiple of 64 and Cout of 8 (pad the weights)");
     if (int rc = ensure_device()) return rc;
-    ProfScope prof(PROF_GEMM, stream);
+    ProfScope prof(PROF_CONV, stream, n * Ho * Wo, cout, 9 * cin, stride);
     GemmParams p{};
     p.N = cout; p.K = 9 * cin; p.batch = n;
     p.rows_per_batch = Ho * Wo; p.out_batch_rows = Ho * Wo; p.out_row_offset = 0;
@@ -419,7 +419,7 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
             p.sp_out[r] = (__nv_bfloat16*)out_peers[r];
         }
     }
-    ProfScope prof(PROF_ATTN, stream);
+    ProfScope prof(PROF_ATTN, stream, B, L, heads, fixed ? 1 : 0);
     static const bool pchunks4 = [] { const char* e = getenv("VCB_ATTN_PCHUNKS"); return e && atoi(e) == 4; }();
     static const bool sp_direct = [] { const char* e = getenv("VCB_SP_ATTN_DIRECT"); return e && atoi(e); }();
     if (out_peers && !sp_direct) {
@@ -447,6 +447,7 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         return set_error("attention: the persistent schedule takes unpadded batches (seqlens == NULL), no sequence-parallel routing");
     if (persist_ok && (schedule == VCB_ATTN_SCHED_PERSISTENT || (schedule == VCB_ATTN_SCHED_AUTO && attn_persist_mode() != 0))) {
         const int grid = pgrid;
+        prof.set_info(3, (fixed ? 1 : 0) | 2);
         AttnScratch* sc = attn_scratch((cudaStream_t)stream);
         if (!sc) return set_error("attention: workspace allocation failed");
         AttnSkParams skp{sc->ws, sc->flags, ++sc->epoch};
@@ -587,7 +588,12 @@ int ln_launch(const vcb_ln_args* a0, const vcb_ln_args* a1, int64_t ldx, int64_t
     ProfScope prof(PROF_LN, stream);
     const int br = batch_rows > 0 ? batch_rows : p[0].rows_per_batch;
     const dim3 grid(p[0].blocks + p[1].blocks), block(kLnWarps * 32);
-    cudaError_t e = hidden <= 12 * 256
+    // VCB_LN_ONEPASS=1: the round-1 kernel (row held in registers, 3 blocks per SM) for A/B; default = two-pass, 6 blocks per SM
+    static const bool onepass = [] { const char* e = getenv("VCB_LN_ONEPASS"); return e && atoi(e); }();
+    cudaError_t e = !onepass
+        ? launch_pdl(ln_modulate2_kernel, grid, block, (size_t)hidden * 4, (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx,
+                     (long long)ldy, (long long)mod_stride, (int)hidden, br)
+        : hidden <= 12 * 256
         ? launch_pdl(ln_modulate_kernel<12, 3>, grid, block, (size_t)hidden * 4, (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx,
                      (long long)ldy, (long long)mod_stride, (int)hidden, br)
         : launch_pdl(ln_modulate_kernel<kLnMaxChunks, 2>, grid, block, (size_t)hidden * 4, (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx,
@@ -708,22 +714,40 @@ extern "C" int vcb_profile_begin(void) {
     p.on = true;
     return 0;
 }
-extern "C" int vcb_profile_end(double* ms, long long* launches) {
+namespace {
+// categories beyond the caller's array fold into "other" (3), so the 4-entry form keeps summing every launch
+int profile_collect(double* ms, long long* launches, int ncat, vcb_prof_record* recs, int64_t cap, int64_t* n_out) {
+    if (!ms || !launches || ncat < 4 || ncat > PROF_NCAT) return set_error("profile_end: ncat must be in [4, %d]", (int)PROF_NCAT);
     Profiler& p = profiler();
     p.on = false;
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return set_error("profile_end: %s", cudaGetErrorString(e));
-    for (int i = 0; i < PROF_NCAT; ++i) { ms[i] = 0.0; launches[i] = 0; }
+    for (int i = 0; i < ncat; ++i) { ms[i] = 0.0; launches[i] = 0; }
+    int64_t n = 0;
     for (auto& r : p.recs) {
         float t = 0.f;
         cudaEventElapsedTime(&t, r.a, r.b);
-        ms[r.cat] += t;
-        launches[r.cat] += 1;
+        const int c = r.cat < ncat ? r.cat : (int)PROF_OTHER;
+        ms[c] += t;
+        launches[c] += 1;
+        if (recs && n < cap) {
+            recs[n].category = r.cat;
+            recs[n].ms = t;
+            for (int k = 0; k < 4; ++k) recs[n].info[k] = r.info[k];
+        }
+        ++n;
         p.pool.push_back(r.a);
         p.pool.push_back(r.b);
     }
+    if (n_out) *n_out = n;
     p.recs.clear();
     return 0;
+}
+}  // namespace
+extern "C" int vcb_profile_end(double* ms, long long* launches) { return profile_collect(ms, launches, 4, nullptr, 0, nullptr); }
+extern "C" int vcb_profile_end_ex(double* ms, long long* launches, int32_t ncat, vcb_prof_record* records, int64_t capacity,
+                                  int64_t* n_records) {
+    return profile_collect(ms, launches, ncat, records, capacity, n_records);
 }
 extern "C" int vcb_abi_version(void) { return VCB_ABI_VERSION; }
 extern "C" const char* vcb_last_error(void) { return error_buf(); }

@@ -109,6 +109,86 @@ ln_modulate_kernel(const LnProblem p0, const LnProblem p1, long long ldx, long l
         }
 }
 
+// Two-pass variant (default): the row is NOT kept in registers between the statistics and the modulation -- pass 2 re-reads
+// it (L1 / L2 hits: the warp has just touched those lines).  That frees ~48 registers per thread, so 6 blocks x 8 warps fit an
+// SM and 148 x 48 = 7104 warps are resident: every row of a cfg-B sequence (3968) is in flight in ONE round.  The one-pass
+// kernel above holds 3 blocks per SM = 3552 warps: 3968 rows took two rounds of which the second was 12 % full -- that, not
+// bandwidth, was its 25 us (ncu: 13.7 % DRAM throughput).  Same arithmetic in the same order: results are bit-identical.
+__global__ void __launch_bounds__(kLnWarps * 32, 6)
+ln_modulate2_kernel(const LnProblem p0, const LnProblem p1, long long ldx, long long ldy, long long mod_stride, int H, int batch_rows) {
+    extern __shared__ uint4 ln_smem[];                 // [2][H / 8] : shift, scale of sample b0
+    pdl_launch_dependents();
+    pdl_wait();
+    const bool second = (int)blockIdx.x >= p0.blocks;
+    const LnProblem& P = second ? p1 : p0;
+    const int rows = P.rows, rows_per_batch = P.rows_per_batch;
+    const int row0 = ((int)blockIdx.x - (second ? p0.blocks : 0)) * kLnWarps;
+    const int b0 = row0 / rows_per_batch;
+    const int nvec = H >> 3;
+    const int row = row0 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int nchunks = H >> 8;                    // H % 256 == 0
+    const bool active = row < rows;
+    const int b = active ? row / rows_per_batch : b0;
+    const long long prow = (long long)b * batch_rows + (row - b * rows_per_batch);
+    const uint4* xr = reinterpret_cast<const uint4*>(P.x + prow * ldx) + lane;
+    // pass 1: statistics, four 16-byte loads in flight per lane (48 warps per SM keep ~100 KB in flight)
+    float sum = 0.f, sq = 0.f;
+    if (active) {
+#pragma unroll 4
+        for (int c = 0; c < nchunks; ++c) {
+            const uint4 v = xr[c * 32];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 f = unpack_bf16x2(w[e]);
+                sum += f.x + f.y;
+                sq = fmaf(f.x, f.x, fmaf(f.y, f.y, sq));
+            }
+        }
+    }
+    for (int i = threadIdx.x; i < 2 * nvec; i += blockDim.x) {
+        const __nv_bfloat16* src = (i < nvec ? P.shift : P.scale) + (long long)b0 * mod_stride;
+        ln_smem[i] = __ldg(reinterpret_cast<const uint4*>(src) + (i < nvec ? i : i - nvec));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    __syncthreads();                                // modulation vectors staged
+    if (!active) return;
+    const float mean = sum / (float)H;
+    const float var = fmaxf(sq / (float)H - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + 1e-6f);
+    const bool staged = (b == b0);
+    const uint4* sh_g = reinterpret_cast<const uint4*>(P.shift + (long long)b * mod_stride);
+    const uint4* sc_g = reinterpret_cast<const uint4*>(P.scale + (long long)b * mod_stride);
+    uint4* yr = reinterpret_cast<uint4*>(P.y + prow * ldy) + lane;
+    // pass 2: re-read, modulate, write
+#pragma unroll 4
+    for (int c = 0; c < nchunks; ++c) {
+        const int vi = c * 32 + lane;
+        const uint4 xv = xr[c * 32];
+        const uint4 hu = staged ? ln_smem[vi] : __ldg(sh_g + vi);
+        const uint4 su = staged ? ln_smem[nvec + vi] : __ldg(sc_g + vi);
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+        const uint32_t sw[4] = {su.x, su.y, su.z, su.w};
+        const uint32_t hw[4] = {hu.x, hu.y, hu.z, hu.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float2 xf = unpack_bf16x2(xw[e]);
+            float2 s2 = unpack_bf16x2(sw[e]);
+            float2 h2 = unpack_bf16x2(hw[e]);
+            float a0 = bf16_round(1.0f + s2.x), a1 = bf16_round(1.0f + s2.y);
+            float n0 = (xf.x - mean) * rstd, n1 = (xf.y - mean) * rstd;
+            ow[e] = pack_bf16x2(__fadd_rn(__fmul_rn(a0, n0), h2.x), __fadd_rn(__fmul_rn(a1, n1), h2.y));
+        }
+        yr[c * 32] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // small per-step / per-image helpers
 // ------------------------------------------------------------------------------------------------

@@ -38,8 +38,10 @@ inline int check_launch(const char* what) {
 }
 
 // ---- optional per-category device timing (bench.py roofline numbers): CUDA events around every launch ------------
-enum ProfCat : int { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_OTHER = 3, PROF_NCAT = 4 };
-struct ProfRec { int cat; cudaEvent_t a, b; };
+enum ProfCat : int { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_OTHER = 3, PROF_CONV = 4, PROF_VAE_EW = 5, PROF_NCAT = 6 };
+// info: what was launched -- GEMM {M, N, K, epilogue | block_n << 8 | cta_group << 16}, conv {pixels, cout, 9 cin, stride},
+// attention {B, L, heads, fixed-reference softmax | persistent << 1}, others zero
+struct ProfRec { int cat; cudaEvent_t a, b; int info[4]; };
 struct Profiler {
     bool on = false;
     std::vector<ProfRec> recs;
@@ -58,13 +60,18 @@ inline Profiler& profiler() {
 struct ProfScope {
     cudaStream_t st;
     cudaEvent_t b = nullptr;
-    ProfScope(int cat, void* stream) : st((cudaStream_t)stream) {
+    size_t idx = 0;
+    ProfScope(int cat, void* stream, int i0 = 0, int i1 = 0, int i2 = 0, int i3 = 0) : st((cudaStream_t)stream) {
         Profiler& p = profiler();
         if (!p.on) return;
         cudaEvent_t a = p.get();
         b = p.get();
         cudaEventRecord(a, st);
-        p.recs.push_back({cat, a, b});
+        idx = p.recs.size();
+        p.recs.push_back({cat, a, b, {i0, i1, i2, i3}});
+    }
+    void set_info(int k, int v) {
+        if (b) profiler().recs[idx].info[k] = v;
     }
     ~ProfScope() {
         if (b) cudaEventRecord(b, st);

@@ -76,7 +76,7 @@ int group_norm(const Ws& ws, const uint16_t* x, uint16_t* y, const vcb_gn_w& g, 
     if (C % 32 || C > 512 || C % 8) return set_error("vae: GroupNorm needs C %% 32 == 0 and C <= 512 (got %d)", C);
     const int chunks = (int)((P + kGnPixelsPerBlock - 1) / kGnPixelsPerBlock);
     {
-        ProfScope ps(PROF_LN, st);
+        ProfScope ps(PROF_VAE_EW, st);
         gn_partial_kernel<<<dim3(chunks, n), kGnThreads, 0, st>>>((const __nv_bfloat16*)x, ws.gn_part, (int)P, C);
         if (int rc = check_launch("gn_partial")) return rc;
         gn_finalize_kernel<<<dim3(kGnGroups, n), 32, 0, st>>>(ws.gn_part, ws.gn_stats, chunks, P * (C / kGnGroups));
@@ -155,7 +155,7 @@ int mid_attention(const Ws& ws, const vcb_gn_w& norm, const vcb_conv_w& wq, cons
             if ((rc = vcb_gemm_bf16(&g, stream))) return rc;
         }
         {
-            ProfScope ps(PROF_OTHER, stream);
+            ProfScope ps(PROF_VAE_EW, stream);
             softmax_rows_kernel<<<(unsigned)P, 256, 0, st>>>(ws.scores, (__nv_bfloat16*)ws.probs, (int)P, Ppad, Ppad, scale);
             if ((rc = check_launch("softmax_rows"))) return rc;
         }
@@ -209,7 +209,7 @@ extern "C" int vcb_vae_decode(vcb_vae* v, void* workspace, int64_t workspace_byt
     int rc;
     // latent tokens -> NHWC (64-channel padded) with z / scale + shift
     {
-        ProfScope ps(PROF_OTHER, stream);
+        ProfScope ps(PROF_VAE_EW, stream);
         const int64_t per = (int64_t)H * W * kZPad;
         tokens_to_nhwc_kernel<<<dim3((unsigned)((per + 255) / 256), n), 256, 0, st>>>((const __nv_bfloat16*)tokens, (__nv_bfloat16*)ws.a, h, w,
                                                                                       c.z_channels, kZPad, c.scale_factor, c.shift_factor);
@@ -234,7 +234,7 @@ extern "C" int vcb_vae_decode(vcb_vae* v, void* workspace, int64_t workspace_byt
         if (lvl != 0) {
             const vcb_conv_w& uw = v->ups[ui++];
             {
-                ProfScope ps(PROF_OTHER, stream);
+                ProfScope ps(PROF_VAE_EW, stream);
                 const int64_t per = (int64_t)(2 * H) * (2 * W) * (uw.cin / 8);
                 upsample2x_kernel<<<dim3((unsigned)((per + 255) / 256), n), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)t1, H, W, uw.cin);
                 if ((rc = check_launch("upsample2x"))) return rc;
@@ -249,7 +249,7 @@ extern "C" int vcb_vae_decode(vcb_vae* v, void* workspace, int64_t workspace_byt
     if ((rc = group_norm(ws, x, t1, v->w.norm_out, n, (int64_t)H * W, Cl, true, st))) return rc;
     if ((rc = conv3(t1, v->w.conv_out, nullptr, y, n, H, W, stream))) return rc;
     {
-        ProfScope ps(PROF_OTHER, stream);
+        ProfScope ps(PROF_VAE_EW, stream);
         const int64_t per = (int64_t)c.out_ch * H * W;
         nhwc_to_image_kernel<<<dim3((unsigned)((per + 255) / 256), n), 256, 0, st>>>((const __nv_bfloat16*)y, raw, img, H, W,
                                                                                      v->w.conv_out.cout, c.out_ch);
@@ -306,7 +306,7 @@ extern "C" int vcb_vae_encode(vcb_vae_enc* e, void* workspace, int64_t workspace
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     {
-        ProfScope ps(PROF_OTHER, stream);
+        ProfScope ps(PROF_VAE_EW, stream);
         const int64_t per = (int64_t)H * W * 64;
         image_to_nhwc_kernel<<<dim3((unsigned)((per + 255) / 256), n), 256, 0, st>>>(image, (__nv_bfloat16*)ws.a, H, W, 3, 64);
         if ((rc = check_launch("image_to_nhwc"))) return rc;
@@ -335,7 +335,7 @@ extern "C" int vcb_vae_encode(vcb_vae_enc* e, void* workspace, int64_t workspace
     if ((rc = group_norm(ws, x, t1, e->w.norm_out, n, (int64_t)h * w, e->w.conv_out.cin, true, st))) return rc;
     if ((rc = conv3(t1, e->w.conv_out, nullptr, y, n, h, w, stream))) return rc;
     {
-        ProfScope ps(PROF_OTHER, stream);
+        ProfScope ps(PROF_VAE_EW, stream);
         const int64_t per = (int64_t)h * w * c.z_channels;
         moments_to_tokens_kernel<<<dim3((unsigned)((per + 255) / 256), n), 256, 0, st>>>((const __nv_bfloat16*)y, noise, (__nv_bfloat16*)tokens,
                                                                                          moments, h, w, c.z_channels, c.scale_factor, c.shift_factor);
