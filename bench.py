@@ -16,8 +16,13 @@ inputs of the reference's shapes with random-init weights of the reference's geo
           the host cores on a bounded sample (1 double + 1 single block at full width and full token count),
           extrapolated to images/sec -- a reported baseline, not the target.
 
-`--impl reference` times that CPU port as the reference arm (the reference itself is pure PyTorch+flash-attn and
-cannot run on CPU as shipped, nor travel to the GPU box).
+`--impl reference` times the reference arm: the UNMODIFIED reference modules of oracle/_ref (DoubleStreamBlock /
+SingleStreamBlock of models/modules/layers.py with LoRA r=256, bf16 autocast, attention through SDPA because flash-attn is
+CUDA-only) on the host cores -- `cpu_baseline.kind` "reference"; the restated oracle ("port") only if oracle/_ref is absent.
+
+With N > 1 GPUs the default line is replica throughput (weak scaling, the contract's line); after it the same process group
+runs the sequence-parallel single-image mode for a few images and reports it under `extra.sp` (strong scaling, one image over
+the N GPUs), so the driver's scaling record also carries the NVLink path.
 """
 from __future__ import annotations
 
@@ -132,9 +137,13 @@ class ClockSampler:
 # CPU port of the reference (oracle) on a bounded sample
 # ------------------------------------------------------------------------------------------------------
 def cpu_reference_sample(workload: str, threads: int):
-    """Times 1 DoubleStreamBlock + 1 SingleStreamBlock of the reference's algorithm (oracle/flux_oracle.py, un-merged LoRA
-    r=256, CUDA-autocast bf16 semantics) at full width on the workload's token count; extrapolates to one image."""
+    """Times 1 DoubleStreamBlock + 1 SingleStreamBlock of the reference at full width on the workload's token count and
+    extrapolates to one image (x 19 / x 38 blocks x NFE; embedders, final layer and the VAE decode -- together < 0.5 % of the
+    image's FLOPs, SURVEY.md 8 -- are not in the sample).  Preferred: the UNMODIFIED reference modules from oracle/_ref under
+    ``torch.autocast("cpu", bf16)`` (kind "reference"); fallback: the restated oracle (kind "port")."""
+    import contextlib
     from oracle import flux_oracle as fo
+    from oracle import ref_runner as rr
     torch.set_num_threads(threads)
     gh, gw, res, num_steps, *_ = WORKLOADS[workload]
     cfg = fo.FluxConfig(depth=1, depth_single_blocks=1, lora_rank=256)
@@ -154,18 +163,40 @@ def cpu_reference_sample(workload: str, threads: int):
     ids = torch.zeros(1, L, 3)
     ids[0, Lt:, 1] = torch.arange(Li) // 72
     ids[0, Lt:, 2] = torch.arange(Li) % 72
-    cos, sin = fo.rope_table(ids, cfg.axes_dim, cfg.theta)
     mask = torch.ones(1, L, dtype=torch.int32)
-    nm = fo.Numerics("cuda_bf16")
-    with torch.no_grad():
+    kind = "port"
+    if rr.available():
+        kind = "reference"
+        rr.apply_cpu_patches()
+        _, ref_layers, _, _ = rr._import()
+        from models.modules.lora import replace_linear_with_lora
+        dbl = ref_layers.DoubleStreamBlock(H, cfg.num_heads, mlp_ratio=cfg.mlp_ratio, qkv_bias=True)
+        sgl = ref_layers.SingleStreamBlock(H, cfg.num_heads, mlp_ratio=cfg.mlp_ratio)
+        for blk, pre in ((dbl, "double_blocks.0."), (sgl, "single_blocks.0.")):
+            replace_linear_with_lora(blk, max_rank=256, scale=1.0)
+            blk.load_state_dict({k[len(pre):]: v for k, v in p.items() if k.startswith(pre)}, strict=True)
+            blk.to(BF16).eval().requires_grad_(False)
+        pe = ref_layers.EmbedND(dim=128, theta=cfg.theta, axes_dim=list(cfg.axes_dim))(ids)
+        ctx = torch.autocast("cpu", dtype=BF16)
+    else:
+        cos, sin = fo.rope_table(ids, cfg.axes_dim, cfg.theta)
+        nm = fo.Numerics("cuda_bf16")
+        ctx = contextlib.nullcontext()
+    with torch.no_grad(), ctx:
         t0 = time.perf_counter()
-        img2, txt2 = fo.double_block(p, 0, cfg, img, txt, vec, cos, sin, mask, nm, 1.0)
+        if kind == "reference":
+            img2, txt2 = dbl(img=img, txt=txt, vec=vec, pe=pe, img_mask=mask[:, Lt:], txt_mask=mask[:, :Lt])
+        else:
+            img2, txt2 = fo.double_block(p, 0, cfg, img, txt, vec, cos, sin, mask, nm, 1.0)
         t1 = time.perf_counter()
-        fo.single_block(p, 0, cfg, torch.cat((txt2, img2), 1), vec, cos, sin, mask, nm, 1.0)
+        if kind == "reference":
+            sgl(torch.cat((txt2, img2), 1), vec=vec, pe=pe, attn_mask=mask)
+        else:
+            fo.single_block(p, 0, cfg, torch.cat((txt2, img2), 1), vec, cos, sin, mask, nm, 1.0)
         t2 = time.perf_counter()
     nfe = num_steps - 1
     sec_per_image = nfe * (19 * (t1 - t0) + 38 * (t2 - t1))
-    return 1.0 / sec_per_image, dict(double_block_s=t1 - t0, single_block_s=t2 - t1, tokens=L)
+    return 1.0 / sec_per_image, dict(double_block_s=t1 - t0, single_block_s=t2 - t1, tokens=L, kind=kind)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -199,19 +230,20 @@ def main():
         if rank != 0:
             return
         cores = os.cpu_count() or 1
-        vals = []
-        for _ in range(max(1, args.warmup)):
+        # one bounded sample per group: one warm-up sample (thread pools, allocator), ONE timed sample -- the result is an
+        # extrapolation of two block timings, repeating it --steps times would only multiply ~25 s of host time
+        if args.warmup > 0:
             cpu_reference_sample(args.workload, cores)
-        for _ in range(max(1, args.steps)):
-            v, info = cpu_reference_sample(args.workload, cores)
-            vals.append(v)
-        v = sum(vals) / len(vals)
-        sample = "1 DoubleStreamBlock + 1 SingleStreamBlock of the reference algorithm (CPU oracle port, un-merged LoRA r=256) at " \
-                 f"hidden 3072 on {info['tokens']} tokens, extrapolated x(19,38) blocks x {nfe} evaluations; VAE decode excluded"
+        v, info = cpu_reference_sample(args.workload, cores)
+        sample = f"1 DoubleStreamBlock + 1 SingleStreamBlock ({'UNMODIFIED reference modules from oracle/_ref, autocast cpu bf16, SDPA attention' if info['kind'] == 'reference' else 'restated oracle'}, " \
+                 f"un-merged LoRA r=256) at hidden 3072 on {info['tokens']} tokens: {info['double_block_s']:.2f}s + {info['single_block_s']:.2f}s, " \
+                 f"extrapolated x(19,38) blocks x {nfe} evaluations; embedders / final layer / VAE decode (< 0.5 % of the image's FLOPs) not in the sample; " \
+                 "timed once after one warm-up sample"
         print(json.dumps({"impl": "reference", "metric": "images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+                          "sample_repeats": 1,
+                          "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": info["kind"], "sample": sample},
                           "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -297,13 +329,58 @@ def main():
     d2h_t = finish(fn(x_d, model.forward, kw_d)[-1])
     d2h = d2h_t.numel() * d2h_t.element_size()
 
-    # one instrumented image: CUDA events around every launch, per kernel category
-    import ctypes as C
-    lib.vcb_profile_begin()
+    # one instrumented image: CUDA events around every launch, per kernel category and per launch
+    eng = model.engine()
+
+    def instrumented():
+        lib.vcb_profile_begin()
+        step_resident()
+        return _lib.profile_end(max_records=20000)
+
+    cat, recs = instrumented()
+    variants = eng.softmax_variants()
+    # the same image with every block on the exact online-max softmax (what a checkpoint whose QK-norm scales leave the safe
+    # range runs; the synthetic scales 1 + 0.1 N(0,1) put every block on the fixed-reference variant)
+    eng.use_score_bounds(False)
     step_resident()
-    pms, pl = (C.c_double * 4)(), (C.c_longlong * 4)()
-    lib.vcb_profile_end(pms, pl)
+    ms_exact = timed(step_resident, 2) / 2
+    cat_x, _ = instrumented()
+    eng.use_score_bounds(True)
+
+    # ---- sequence-parallel single-image mode on the same process group (strong scaling; N > 1 only) ----
+    sp_extra = None
+    if world > 1 and not sp_mode:
+        from visualcloze_b200.parallel import SequenceParallel
+        try:
+            x_s, kw_s, _, _ = make_inputs(args.workload, 1234)              # every rank: the SAME sample
+            x_sd, kw_sd = x_s.to(dev), {k: v.to(dev) for k, v in kw_s.items()}
+            model.enable_sequence_parallel(SequenceParallel(timeout_ms=20000))
+
+            def step_sp():
+                latent = fn(x_sd, model.forward, kw_sd)[-1]
+                q = latent[:, Li - row_tokens:, :]
+                return decoder.decode_packed(q, res // 16, gw * res // 16) if decoder is not None else q
+
+            step_sp(); step_sp()
+            n_sp = 3
+            ms_sp = timed(step_sp, n_sp) / n_sp
+            lib.vcb_profile_begin()
+            step_sp()
+            cat_s, _ = _lib.profile_end()
+            Lq, Hh = Li + Lt, 3072
+            sent = 57 * ((Lq // world) * 3 * Hh * 2 + Lq * (Hh // world) * 2) * (world - 1) / world
+            sp_extra = {"ms_per_image": ms_sp, "images_per_s": 1000.0 / ms_sp, "timed_images": n_sp, "scaling": "strong",
+                        "gemm_ms": cat_s["gemm"][0], "attention_ms": cat_s["attention"][0], "ln_modulate_ms": cat_s["ln_modulate"][0],
+                        "barrier_and_other_ms": cat_s["other"][0], "vae_ms": cat_s["vae_conv3x3"][0] + cat_s["vae_elementwise"][0],
+                        "nvlink_bytes_per_eval_per_rank": int(sent),
+                        "note": "ONE image, token rows sharded over the GPUs; q/k/v and attention-output all-to-alls are TMA tile stores into "
+                                "peer memory from the GEMM / attention epilogues; per-rank kernel times are rank 0's"}
+            model.enable_sequence_parallel(None)
+        except Exception as e:  # noqa: BLE001  (the replica line must survive a failure of the extra measurement)
+            sp_extra = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     pk = peaks()
     gemm_fl, attn_fl = flops_per_image(Li, Lt, nfe)
@@ -317,36 +394,74 @@ def main():
     if tps:
         traffic = json.load(open(tps[-1]))
         traffic["source"] = os.path.relpath(tps[-1], REPO)
+    pms = [cat[k][0] for k in _lib.PROF_CATEGORIES]
+    pl = [cat[k][1] for k in _lib.PROF_CATEGORIES]
+    # the GEMM category also holds the VAE decoder's 1x1 convolutions / mid-attention GEMMs (M = pixels): split them off by shape
+    EPI = {0: "bias", 1: "bias_gelu", 2: "gate_res", 3: "qkv_rmsnorm_rope", 4: "linear1_split", 5: "bias_f32"}
+    shapes, conv_fl, conv_ms, vae_gemm_ms, vae_gemm_fl = {}, 0.0, 0.0, 0.0, 0.0
+    for r in recs:
+        i = list(r.info)
+        if r.category == 0:
+            fl = 2.0 * i[0] * i[1] * i[2]
+            if (i[3] >> 24) & 1:                                             # launched from inside the VAE engine
+                vae_gemm_ms += r.ms; vae_gemm_fl += fl
+                continue
+            key = (i[0], i[1], i[2], i[3] & 255, (i[3] >> 8) & 255, (i[3] >> 16) & 255)
+            e = shapes.setdefault(key, [0, 0.0, fl])
+            e[0] += 1; e[1] += r.ms
+        elif r.category == 4:
+            conv_fl += 2.0 * i[0] * i[1] * i[2]; conv_ms += r.ms
+    shape_rows = [{"M": k[0], "N": k[1], "K": k[2], "epilogue": EPI.get(k[3], str(k[3])), "block_n": k[4], "cta_group": k[5], "launches": v[0],
+                   "avg_us": 1e3 * v[1] / v[0], "tflops": v[2] / (v[1] / v[0]) / 1e9, "frac_of_sustained_peak": v[2] / (v[1] / v[0]) / 1e9 / pk["tf"],
+                   "share_of_gemm_time": v[1] / max(pms[0], 1e-9)}
+                  for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1]) if v[1] > 0.002 * pms[0]]
+    dit_gemm_ms = pms[0] - vae_gemm_ms
     jobs = 1 if sp_mode else world    # images per step over the whole job
     value = jobs * args.steps / (ms / 1000.0)
+    attn_ms_x = cat_x["attention"][0]
     out = {
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sp_mode else "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": jobs * args.steps / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
-        "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all fused-epilogue GEMMs of one image)", "bound": "tensor",
-                     "achieved": gemm_fl / (pms[0] / 1000.0) / 1e12, "peak": pk["tf"], "unit": "TFLOP/s",
-                     "frac": gemm_fl / (pms[0] / 1000.0) / 1e12 / pk["tf"],
+        "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all fused-epilogue GEMMs of the FLUX-DiT for one image)", "bound": "tensor",
+                     "achieved": gemm_fl / (dit_gemm_ms / 1000.0) / 1e12, "peak": pk["tf"], "unit": "TFLOP/s",
+                     "frac": gemm_fl / (dit_gemm_ms / 1000.0) / 1e12 / pk["tf"],
                      "traffic": traffic.get("gemm", {}).get("avg_dram_bytes_per_launch"), "traffic_source": traffic.get("source"), "peak_source": pk["src"] + " sustained",
                      "launches": int(pl[0]), "avg_launch_ms": pms[0] / max(1, pl[0]), "flops_per_image": gemm_fl},
-        "roofline_attention": {"kernel": "attn_fwd3_tcgen05_kernel (fixed-reference softmax variant when the QK-norm bound applies)", "bound": "tensor", "achieved": attn_fl / (pms[1] / 1000.0) / 1e12,
+        "roofline_attention": {"kernel": "attn_fwd4_tcgen05_kernel (persistent schedule; fixed-reference softmax where the block's QK-norm bound applies)",
+                               "bound": "tensor", "achieved": attn_fl / (pms[1] / 1000.0) / 1e12,
                                "peak": pk["tf"], "unit": "TFLOP/s", "frac": attn_fl / (pms[1] / 1000.0) / 1e12 / pk["tf"],
-                               "launches": int(pl[1]), "avg_launch_ms": pms[1] / max(1, pl[1]),
+                               "launches": int(pl[1]), "avg_launch_ms": pms[1] / max(1, pl[1]), "softmax_variant_per_block": variants,
                                "traffic": traffic.get("attention", {}).get("avg_dram_bytes_per_launch")},
-        "roofline_ln_modulate": {"kernel": "ln_modulate_kernel", "bound": "hbm", "unit": "GB/s", "peak": pk["hbm"],
+        "roofline_ln_modulate": {"kernel": "ln_modulate2_kernel", "bound": "hbm", "unit": "GB/s", "peak": pk["hbm"],
                                  "achieved": ln_bytes / (pms[2] / 1000.0) / 1e9, "frac": ln_bytes / (pms[2] / 1000.0) / 1e9 / pk["hbm"],
                                  "launches": int(pl[2]), "avg_launch_ms": pms[2] / max(1, pl[2]),
-                                 "note": "algorithmic bytes = read + write of the normalised rows; ~10 us of every launch is fixed cost"},
-        "kernel_time_share": {"gemm_ms": pms[0], "attention_ms": pms[1], "ln_modulate_ms": pms[2], "other_ms": pms[3]},
+                                 "note": "algorithmic bytes = read + write of the normalised rows (the second read of the two-pass kernel hits L1/L2)"},
+        "roofline_vae": {"kernel": "gemm_bf16_tcgen05_kernel<A_CONV3X3> (implicit-GEMM 3x3 convolutions of the decoder, query row)",
+                         "bound": "tensor", "unit": "TFLOP/s", "peak": pk["tf"], "achieved": conv_fl / max(conv_ms, 1e-9) / 1e9,
+                         "frac": conv_fl / max(conv_ms, 1e-9) / 1e9 / pk["tf"], "launches": int(pl[4]), "conv_ms": conv_ms,
+                         "conv_flops": conv_fl, "other_gemm_ms": vae_gemm_ms, "other_gemm_flops": vae_gemm_fl,
+                         "elementwise_ms": pms[5], "elementwise_launches": int(pl[5]),
+                         "decode_ms_total": conv_ms + vae_gemm_ms + pms[5]},
+        "kernel_time_share": {"gemm_ms": dit_gemm_ms, "attention_ms": pms[1], "ln_modulate_ms": pms[2], "other_ms": pms[3],
+                              "vae_conv_ms": conv_ms, "vae_gemm_ms": vae_gemm_ms, "vae_elementwise_ms": pms[5]},
+        "gemm_shapes": shape_rows,
+        "extra": {"attention_exact_softmax": {"ms_per_step": ms_exact, "images_per_s": jobs * 1000.0 / ms_exact,
+                                              "attention_tflops": attn_fl / (attn_ms_x / 1000.0) / 1e12,
+                                              "attention_frac": attn_fl / (attn_ms_x / 1000.0) / 1e12 / pk["tf"],
+                                              "note": "same image with every block on the exact online-max softmax (score bounds disabled)"}},
     }
+    if sp_extra is not None:
+        out["extra"]["sp"] = sp_extra
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         v, info = cpu_reference_sample(args.workload, cores)
-        out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                               "sample": "1 double + 1 single block of the reference algorithm (CPU oracle, un-merged LoRA) at hidden "
-                                         f"3072 on {info['tokens']} tokens: {info['double_block_s']:.2f}s + {info['single_block_s']:.2f}s, "
-                                         f"extrapolated x(19,38) blocks x {nfe} evaluations; VAE decode excluded"}
+        out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": info["kind"],
+                               "sample": "1 DoubleStreamBlock + 1 SingleStreamBlock (" + ("UNMODIFIED reference modules from oracle/_ref, autocast cpu bf16" if info["kind"] == "reference" else "restated oracle") +
+                                         f", un-merged LoRA r=256) at hidden 3072 on {info['tokens']} tokens: {info['double_block_s']:.2f}s + {info['single_block_s']:.2f}s, "
+                                         f"extrapolated x(19,38) blocks x {nfe} evaluations; embedders / final layer / VAE decode (< 0.5 % of the FLOPs) not in the sample"}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

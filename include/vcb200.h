@@ -38,7 +38,7 @@ int         vcb_profile_begin(void);
 int         vcb_profile_end(double ms[4], long long launches[4]);
 /* Extended form: ncat in [4, 6] categories (4 = VAE 3x3 convolutions, 5 = VAE GroupNorm / upsample / softmax / layout; with
  * ncat == 4 they fold into "other"), and optionally one record per launch in launch order.
- * info: GEMM {M, N, K, epilogue | block_n << 8 | cta_group << 16}; conv {output pixels, cout, 9 * cin, stride};
+ * info: GEMM {M, N, K, epilogue | block_n << 8 | cta_group << 16 | issued-by-the-VAE-engine << 24}; conv {output pixels, cout, 9 * cin, stride};
  * attention {B, L, heads, fixed-reference softmax | persistent schedule << 1}. */
 typedef struct vcb_prof_record { int32_t category; float ms; int32_t info[4]; } vcb_prof_record;
 int         vcb_profile_end_ex(double* ms, long long* launches, int32_t ncat, vcb_prof_record* records, int64_t capacity,
@@ -206,6 +206,9 @@ typedef struct vcb_flux vcb_flux;       /* opaque */
 
 int  vcb_flux_create(const vcb_flux_config* cfg, const vcb_flux_weights* w, vcb_flux** out);
 void vcb_flux_destroy(vcb_flux* f);
+/* enable (default) / disable the per-block attn_score_bound: disabled, every block runs the exact online-max softmax -- what a
+ * checkpoint whose QK-norm scales leave the safe range gets anyway; used to measure that path on any weights */
+int  vcb_flux_use_score_bounds(vcb_flux* f, int32_t enable);
 /* bytes of device workspace for B samples of Li image + Lt text tokens and n_evals model evaluations */
 int64_t vcb_flux_workspace_bytes(const vcb_flux* f, int32_t B, int32_t Li, int32_t Lt, int32_t n_evals);
 /* Step-invariant work, once per image (txt_in, RoPE table, and the AdaLN modulation vectors of

@@ -178,6 +178,7 @@ _OPTIONAL: dict = {
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "vcb_flux_create": (C.c_int, [C.POINTER(FluxConfigC), C.POINTER(FluxWeightsC), C.POINTER(C.c_void_p)]),
     "vcb_flux_destroy": (None, [C.c_void_p]),
+    "vcb_flux_use_score_bounds": (C.c_int, [C.c_void_p, C.c_int32]),
     "vcb_flux_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "vcb_flux_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

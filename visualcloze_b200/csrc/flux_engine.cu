@@ -23,6 +23,7 @@ struct vcb_flux {
     // prepared state
     bool prepared = false;
     int B = 0, Li = 0, Lt = 0, L = 0, E = 0;
+    bool use_score_bounds = true;     // false: every block runs the exact online-max softmax (vcb_flux_use_score_bounds)
     const int32_t* seqlens = nullptr;
     float2* rope = nullptr;
     uint16_t *txt0 = nullptr, *temb_t = nullptr, *temb_g = nullptr, *h1 = nullptr, *e_time = nullptr, *e_guid = nullptr,
@@ -120,6 +121,12 @@ extern "C" int vcb_flux_create(const vcb_flux_config* cfg, const vcb_flux_weight
 }
 
 extern "C" void vcb_flux_destroy(vcb_flux* f) { delete f; }
+
+extern "C" int vcb_flux_use_score_bounds(vcb_flux* f, int32_t enable) {
+    if (!f) return set_error("flux_use_score_bounds: null engine");
+    f->use_score_bounds = enable != 0;
+    return 0;
+}
 
 extern "C" int64_t vcb_flux_workspace_bytes(const vcb_flux* f, int32_t B, int32_t Li, int32_t Lt, int32_t n_evals) {
     if (!f || B <= 0 || Li <= 0 || Lt < 0 || n_evals <= 0) return -1;
@@ -238,7 +245,7 @@ int joint_attention(vcb_flux* f, int64_t ldc, float score_bound, void* stream) {
     const vcb_flux_config& c = f->cfg;
     const int H = c.hidden;
     vcb_attn_args a{};
-    a.score_bound_log2 = score_bound;
+    a.score_bound_log2 = f->use_score_bounds ? score_bound : 0.f;
     a.ldo = ldc;
     if (f->sp_world <= 1) {
         a.qkv = f->qkv; a.ld_qkv = 3 * H; a.q_col = 0; a.k_col = H; a.v_col = 2 * H;

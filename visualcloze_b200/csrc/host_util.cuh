@@ -57,6 +57,17 @@ inline Profiler& profiler() {
     static Profiler p;
     return p;
 }
+// launches issued from inside the VAE engine are marked (bit 24 of a GEMM record's info[3]): the decoder's 1x1 convolutions and
+// mid-block attention products run on the same GEMM entry point as the FLUX-DiT's Linears
+inline int& prof_context() {
+    static thread_local int c = 0;
+    return c;
+}
+struct ProfContext {
+    int prev;
+    explicit ProfContext(int c) : prev(prof_context()) { prof_context() = c; }
+    ~ProfContext() { prof_context() = prev; }
+};
 struct ProfScope {
     cudaStream_t st;
     cudaEvent_t b = nullptr;
@@ -68,7 +79,7 @@ struct ProfScope {
         b = p.get();
         cudaEventRecord(a, st);
         idx = p.recs.size();
-        p.recs.push_back({cat, a, b, {i0, i1, i2, i3}});
+        p.recs.push_back({cat, a, b, {i0, i1, i2, cat == PROF_GEMM ? (i3 | (prof_context() << 24)) : i3}});
     }
     void set_info(int k, int v) {
         if (b) profiler().recs[idx].info[k] = v;

@@ -199,6 +199,7 @@ extern "C" int64_t vcb_vae_workspace_bytes(const vcb_vae* v, int32_t n, int32_t 
 extern "C" int vcb_vae_decode(vcb_vae* v, void* workspace, int64_t workspace_bytes, const void* tokens, int32_t n, int32_t h,
                               int32_t w, float* raw, uint8_t* img, void* stream) {
     if (!v || !workspace || !tokens || (!raw && !img) || n <= 0 || h <= 0 || w <= 0) return set_error("vae_decode: bad arguments");
+    ProfContext in_vae(1);
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return set_error("vae_decode: workspace must be 256-byte aligned");
     if (int rc = ensure_device()) return rc;
     const vcb_vae_config& c = v->cfg;
@@ -296,6 +297,7 @@ extern "C" int64_t vcb_vae_enc_workspace_bytes(const vcb_vae_enc* e, int32_t n, 
 extern "C" int vcb_vae_encode(vcb_vae_enc* e, void* workspace, int64_t workspace_bytes, const float* image, int32_t n, int32_t H,
                               int32_t W, const float* noise, void* tokens, float* moments, void* stream) {
     if (!e || !workspace || !image || !tokens || n <= 0) return set_error("vae_encode: bad arguments");
+    ProfContext in_vae(1);
     const vcb_vae_config& c = e->cfg;
     const int f = 1 << (c.n_levels - 1);
     if (H <= 0 || W <= 0 || H % (2 * f) || W % (2 * f)) return set_error("vae_encode: H and W must be multiples of %d", 2 * f);

@@ -132,6 +132,18 @@ class FluxEngine:
         check(self.lib.vcb_flux_create(C.byref(cfg), C.byref(w), C.byref(h)), "vcb_flux_create")
         self._h = h
 
+    def use_score_bounds(self, enable: bool) -> None:
+        """False: every block runs the exact online-max softmax kernel (what a checkpoint whose QK-norm scales leave the safe
+        range gets anyway); True (default): blocks with a packed bound use the fixed-reference softmax."""
+        check(self.lib.vcb_flux_use_score_bounds(self._h, int(bool(enable))), "vcb_flux_use_score_bounds")
+
+    def softmax_variants(self) -> dict:
+        """how many blocks carry a usable score bound (-> fixed-reference softmax) vs none (-> exact online max)"""
+        b = [self._dbl[i].attn_score_bound for i in range(self.params.depth)] + \
+            [self._sgl[i].attn_score_bound for i in range(self.params.depth_single_blocks)]
+        return {"fixed_reference": sum(1 for v in b if v > 0), "exact_online_max": sum(1 for v in b if not v > 0),
+                "max_bound_log2": max(b) if b else 0.0}
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
