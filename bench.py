@@ -208,6 +208,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="B", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp8"],
+                    help="bf16 = the reference's numerics (the headline); fp8 = opt-in e4m3 projections for the LayerNorm-fed Linears "
+                         "(a separate line with its own tolerance contract, never the headline)")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sp"],
                     help="N>1: 'replicas' = one image per GPU (throughput, weak scaling; the default and the contract's line); "
                          "'sp' = ONE image sharded by token rows over the N GPUs (latency, strong scaling; SURVEY.md 8f-2)")
@@ -260,6 +263,10 @@ def main():
     with torch.device(dev):
         model = M.FluxLoraWrapper(lora_rank=256, params=M.flux_dev_fill_params())
     model.init_synthetic(0)
+    if args.precision == "fp8":
+        model.set_linear_precision("fp8")
+        config["precision"] = ("fp8: qkv / mlp.0 / linear1 (58 % of the GEMM FLOPs) on e4m3 operands (tcgen05 kind::f8f6f4, per-row activation "
+                               "and per-channel weight scales); everything else bf16.  NOT the reference's numerics: tests/test_fp8_gpu.py")
     model.engine()
     decoder = None
     try:
@@ -422,7 +429,8 @@ def main():
     out = {
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sp_mode else "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clk, "gpu_launches": int(launches),
+        "dtype": "bf16" if args.precision == "bf16" else "fp8(e4m3 projections)+bf16", "data": "synthetic", "config": config, "clocks": clk,
+        "gpu_launches": int(launches),
         "e2e": {"value": jobs * args.steps / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
         "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all fused-epilogue GEMMs of the FLUX-DiT for one image)", "bound": "tensor",

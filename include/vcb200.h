@@ -89,7 +89,16 @@ typedef struct vcb_gemm_args {
        `out` is then unused for the q/k/v columns. */
     int32_t sp_world, sp_row_offset;
     void* sp_out[VCB_SP_MAX];
+    /* FP8 operands (opt-in; VCB_EPI_BIAS / BIAS_GELU / QKV / LINEAR1, plain matrices): operand_dtype = VCB_DTYPE_E4M3 makes A
+       and W e4m3 bytes (lda / ldw / a_batch_stride in elements = bytes, multiples of 16), multiplied on the tensor cores with
+       tcgen05.mma kind::f8f6f4; the fp32 accumulator is rescaled by a_scale[mapped OUTPUT row] * w_scale[column] before the
+       bias (per-row activation scales as written by vcb_ln_modulate_fp8, per-output-channel weight scales; NULL = 1). */
+    int32_t operand_dtype;           /* VCB_DTYPE_BF16 (0) or VCB_DTYPE_E4M3 (1) */
+    const float* a_scale;
+    const float* w_scale;
 } vcb_gemm_args;
+#define VCB_DTYPE_BF16 0
+#define VCB_DTYPE_E4M3 1
 
 int vcb_gemm_bf16(const vcb_gemm_args* args, void* stream);
 /* Two problems with the same N, K and epilogue (their own A, W, bias, outputs, row mapping) in ONE persistent launch:
@@ -153,6 +162,12 @@ typedef struct vcb_ln_args { const void* x; void* y; const void* shift; const vo
 int vcb_ln_modulate_grouped(const vcb_ln_args* a0, const vcb_ln_args* a1, int64_t ldx, int64_t ldy, int64_t mod_stride,
                             int32_t hidden, int32_t batch_rows, void* stream);
 
+/* FP8 form (opt-in fp8 projections): same LayerNorm + modulation, but the output row is e4m3 bytes (y8 [*, ld8], bytes) with one
+ * fp32 scale per row, row_scale[physical row] = max|y| / 448 -- the a_scale of the fp8 GEMM that consumes it.  One or two
+ * problems per launch (a1 may be NULL); vcb_ln_args.y is then the e4m3 destination of that problem. */
+int vcb_ln_modulate_fp8(const vcb_ln_args* a0, const vcb_ln_args* a1, float* row_scale0, float* row_scale1, int64_t ldx, int64_t ld8,
+                        int64_t mod_stride, int32_t hidden, int32_t batch_rows, void* stream);
+
 /* ---- small helpers --------------------------------------------------------------------------------------- */
 /* layers.py:28-49; t_scaled = time_factor * t already in the reference's dtype; freqs[128] fp32; out [n,256] bf16 */
 int vcb_timestep_embedding(const float* t_scaled, const float* freqs, void* out, int32_t n, void* stream);
@@ -174,7 +189,9 @@ int vcb_copy_cols(const void* src, int64_t lds, void* dst, int64_t ldd, int32_t 
 /* ---- FLUX-DiT engine: the whole Flux.forward (models/model.py:85-124) and the Euler loop around it -----------
  * Weights are the reference's tensors with LoRA merged (W' = W + s*B*A, b' = b + s*b_B; lora.py:92-98), bf16
  * weights [out, in], fp32 biases.  The engine keeps pointers only; the caller owns weights and workspace. */
-typedef struct vcb_linear_w { const void* w; const float* b; } vcb_linear_w;
+/* w8 / w8_scale (optional): the same merged weight quantised to e4m3 with one fp32 scale per output channel (w ~= w8 * scale),
+ * used by the opt-in fp8 projections (vcb_flux_set_fp8) of the LayerNorm-fed Linears (qkv, mlp.0, linear1); NULL = bf16 only. */
+typedef struct vcb_linear_w { const void* w; const float* b; const void* w8; const float* w8_scale; } vcb_linear_w;
 
 typedef struct vcb_stream_w {           /* one stream of a DoubleStreamBlock (layers.py:129-156) */
     vcb_linear_w mod, qkv, proj, mlp0, mlp2;
@@ -209,6 +226,11 @@ void vcb_flux_destroy(vcb_flux* f);
 /* enable (default) / disable the per-block attn_score_bound: disabled, every block runs the exact online-max softmax -- what a
  * checkpoint whose QK-norm scales leave the safe range gets anyway; used to measure that path on any weights */
 int  vcb_flux_use_score_bounds(vcb_flux* f, int32_t enable);
+/* opt-in FP8 (e4m3) projections: the Linears fed by an AdaLN LayerNorm (double blocks: img/txt qkv and mlp.0; single blocks:
+ * linear1 -- 58 % of the step's GEMM FLOPs) run on tcgen05.mma kind::f8f6f4 with per-row activation scales (written by the
+ * LayerNorm kernel) and per-output-channel weight scales; everything else stays bf16.  Needs the w8 / w8_scale members of those
+ * weights.  NOT the reference's numerics: a separate tolerance contract applies (tests/test_fp8_gpu.py). */
+int  vcb_flux_set_fp8(vcb_flux* f, int32_t enable);
 /* bytes of device workspace for B samples of Li image + Lt text tokens and n_evals model evaluations */
 int64_t vcb_flux_workspace_bytes(const vcb_flux* f, int32_t B, int32_t Li, int32_t Lt, int32_t n_evals);
 /* Step-invariant work, once per image (txt_in, RoPE table, and the AdaLN modulation vectors of

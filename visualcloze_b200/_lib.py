@@ -35,6 +35,7 @@ class GemmArgs(C.Structure):
         ("out2", C.c_void_p), ("ldo2", C.c_int64), ("out2_col_offset", C.c_int32),
         ("block_n", C.c_int32), ("cta_group", C.c_int32),
         ("sp_world", C.c_int32), ("sp_row_offset", C.c_int32), ("sp_out", C.c_void_p * SP_MAX),
+        ("operand_dtype", C.c_int32), ("a_scale", C.c_void_p), ("w_scale", C.c_void_p),
     ]
 
 
@@ -70,7 +71,7 @@ _SIGNATURES = {
 }
 
 class LinearW(C.Structure):
-    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p)]
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("w8", C.c_void_p), ("w8_scale", C.c_void_p)]
 
 
 class StreamW(C.Structure):
@@ -179,6 +180,7 @@ _OPTIONAL: dict = {
     "vcb_flux_create": (C.c_int, [C.POINTER(FluxConfigC), C.POINTER(FluxWeightsC), C.POINTER(C.c_void_p)]),
     "vcb_flux_destroy": (None, [C.c_void_p]),
     "vcb_flux_use_score_bounds": (C.c_int, [C.c_void_p, C.c_int32]),
+    "vcb_flux_set_fp8": (C.c_int, [C.c_void_p, C.c_int32]),
     "vcb_flux_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "vcb_flux_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -190,6 +192,8 @@ _OPTIONAL: dict = {
     "vcb_attention_fwd_ex": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
     "vcb_ln_modulate_grouped": (C.c_int, [C.POINTER(LnArgs), C.POINTER(LnArgs), C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                           C.c_int32, C.c_void_p]),
+    "vcb_ln_modulate_fp8": (C.c_int, [C.POINTER(LnArgs), C.POINTER(LnArgs), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                      C.c_int32, C.c_int32, C.c_void_p]),
     "vcb_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "vcb_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "vcb_peer_close": (C.c_int, [C.c_void_p]),

@@ -1,12 +1,12 @@
 // attn3_sm100.cuh -- joint attention forward, two 128-query tiles per CTA, ROW-SPLIT softmax (16 softmax warps).
 //
-// Same pipeline as attn2_sm100.cuh, but every query row is handled by TWO threads (64 key columns each; the two warps of a
+// Two 128-query tiles per CTA share one K/V stream, and every query row is handled by TWO threads (64 key columns each; the two warps of a
 // pair share a TMEM lane quarter and exchange the row max through shared memory with a 64-thread named barrier).  The
-// per-tile softmax latency -- the serial link S_t(j) -> P_t(j) -> PV_t(j) -> QK_t(j+1) that bounded attn2 (ncu: 34 % of
-// samples waiting on s_full, tensor pipe 51 %) -- is halved, and each SM sub-partition hosts 4 softmax warps instead of 2.
+// per-tile softmax latency -- the serial link S_t(j) -> P_t(j) -> PV_t(j) -> QK_t(j+1) that bounded the thread-per-row version
+// (ncu: 34 % of samples waiting on s_full, tensor pipe 51 %) -- is halved, and each SM sub-partition hosts 4 softmax warps.
 //
-// Same contract as attn_sm100.cuh (models/math.py:63-99; per-sample seqlens instead of unpad/pad), restructured so the
-// tensor pipe is fed from two independent softmax pipelines that share one K/V stream:
+// Contract: attn_common.cuh (models/math.py:63-99; per-sample seqlens instead of unpad/pad).  The tensor pipe is fed from two
+// independent softmax pipelines that share one K/V stream:
 //   warp 0       TMA producer   Q0, Q1 once; K/V tiles through a ring of 32 KB slots in the order K0 V0 K1 V1 ...
 //   warp 1       MMA issuer     S_t = Q_t K_j^T (SS) ; O_t += P_t V_j (TS, P from TMEM, V MN-major), issue order
 //                               QK0(0) QK1(0) | PV0(j) QK0(j+1) PV1(j) QK1(j+1) | ...  so while group t does its softmax the
@@ -21,12 +21,12 @@
 //     exchange between the two threads of a row, no O rescaling.
 // kSp (sequence parallelism): the epilogue ships O to the row owners' buffers with TMA tile stores (NVLink for peers).
 #pragma once
-#include "attn2_sm100.cuh"
+#include "attn_common.cuh"
 
 namespace vcb {
 
 constexpr int kAttn3Threads = 576;          // TMA warp + MMA warp + 2 tiles x 8 softmax warps
-constexpr int kAttn3Slots = 4;              // K/V ring (one slot less than attn2: room for the exchange buffer)
+constexpr int kAttn3Slots = 4;              // K/V ring of 32 KB slots
 constexpr int kAttn3SmemBytes = (2 + kAttn3Slots) * kSlotBytes + 1024 + 256 + 4096;
 
 // Sequence-parallel output maps (kSp): m[r] = rank r's [rows_per_rank, ldo] output buffer (all columns), box 64 columns x

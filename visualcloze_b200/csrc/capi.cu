@@ -8,8 +8,6 @@
 #include <mutex>
 
 #include "../../include/vcb200.h"
-#include "attn_sm100.cuh"
-#include "attn2_sm100.cuh"
 #include "attn3_sm100.cuh"
 #include "attn4_sm100.cuh"
 #include "elementwise.cuh"
@@ -70,11 +68,11 @@ inline bool streamk_wanted(long tiles, int slots, float tile_us) {
     return mode == 1 || idle / waves >= 0.2f;
 }
 
-template <int BN, int CG, int EPI, bool SP = false>
+template <int BN, int CG, int EPI, bool SP = false, bool FP8 = false>
 int launch_gemm_inst(const Problem& g0, const Problem& g1, float rate, cudaStream_t st) {
     const CUtensorMap& ta = g0.ta; const CUtensorMap& tb = g0.tb; const GemmParams& p = g0.p;
     using Cfg = GemmCfg<BN, CG>;
-    auto kern = gemm_bf16_tcgen05_kernel<BN, CG, EPI, A_MATRIX, SP>;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, CG, EPI, A_MATRIX, SP, FP8>;
     constexpr int kSmem = Cfg::kSmemBytes + (SP ? kSpStageBytes : 0);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -88,7 +86,7 @@ int launch_gemm_inst(const Problem& g0, const Problem& g1, float rate, cudaStrea
     int clusters = num_sms() / CG;
     // stream-K tail: the tiles of the partial last wave are cut along K into one equal range per CTA (pair)
     StreamKParams skp{nullptr, nullptr, 0, 0};
-    const bool sk = streamk_wanted(tiles, clusters, tile_time_us(BN, p.K, rate));
+    const bool sk = streamk_wanted(tiles, clusters, tile_time_us(BN, p.K, rate) * (FP8 ? 0.5f : 1.0f));
     if (tiles < clusters && !sk) clusters = tiles;
     if (sk) {
         SkScratch* sc = sk_scratch(st);
@@ -103,6 +101,18 @@ int launch_gemm_inst(const Problem& g0, const Problem& g1, float rate, cudaStrea
     if (e != cudaSuccess) return set_error("gemm launch (BN=%d CG=%d EPI=%d): %s", BN, CG, EPI, cudaGetErrorString(e));
     count_launch();
     return 0;
+}
+
+// fp8 operands: the LayerNorm-fed projections of the FLUX blocks (qkv, mlp-up, linear1) and plain bias GEMMs
+template <int BN, int CG>
+int launch_gemm_epi_fp8(int epi, const Problem& g0, const Problem& g1, float rate, cudaStream_t st) {
+    if (epi == EPI_BIAS) return launch_gemm_inst<BN, CG, EPI_BIAS, false, true>(g0, g1, rate, st);
+    if (epi == EPI_BIAS_GELU) return launch_gemm_inst<BN, CG, EPI_BIAS_GELU, false, true>(g0, g1, rate, st);
+    if constexpr (BN % 128 == 0) {
+        if (epi == EPI_QKV) return launch_gemm_inst<BN, CG, EPI_QKV, false, true>(g0, g1, rate, st);
+        if (epi == EPI_LINEAR1) return launch_gemm_inst<BN, CG, EPI_LINEAR1, false, true>(g0, g1, rate, st);
+    }
+    return set_error("gemm (fp8): epilogue %d not available for block_n %d", epi, BN);
 }
 
 template <int BN, int CG>
@@ -199,6 +209,14 @@ int check_gemm_args(const vcb_gemm_args* a) {
     const int64_t a_bstride = a->a_batch_stride ? a->a_batch_stride : (int64_t)a->rows_per_batch * a->lda;
     if (a_bstride % 8) return set_error("gemm: a_batch_stride must be a multiple of 8");
     if (a->cta_group < 0 || a->cta_group > 2) return set_error("gemm: cta_group must be 0 (auto), 1 or 2");
+    if (a->operand_dtype != VCB_DTYPE_BF16 && a->operand_dtype != VCB_DTYPE_E4M3) return set_error("gemm: unknown operand_dtype %d", a->operand_dtype);
+    if (a->operand_dtype == VCB_DTYPE_E4M3) {
+        if (a->lda % 16 || a->ldw % 16 || a_bstride % 16) return set_error("gemm (fp8): lda / ldw / a_batch_stride must be multiples of 16 bytes");
+        if (a->sp_world > 1) return set_error("gemm (fp8): the sequence-parallel routing takes bf16 operands");
+        if (a->epilogue == VCB_EPI_GATE_RES || a->epilogue == VCB_EPI_BIAS_F32)
+            return set_error("gemm (fp8): epilogue %d is bf16-only (its A operand is produced by a GEMM epilogue, not by the LayerNorm)", a->epilogue);
+        if (a->block_n && a->block_n != 128 && a->block_n != 256) return set_error("gemm (fp8): block_n must be 128 or 256");
+    }
     return 0;
 }
 
@@ -217,10 +235,13 @@ int build_problem(const vcb_gemm_args* a, int bn, int cg, Problem* out) {
     p.rope = (const float2*)a->rope; p.rope_rows = a->rope_rows;
     p.out2 = (__nv_bfloat16*)a->out2; p.ldo2 = a->ldo2; p.out2_col_offset = a->out2_col_offset;
     p.sp_world = a->sp_world > 1 ? a->sp_world : 0; p.sp_row_offset = a->sp_row_offset;
+    const bool fp8 = a->operand_dtype == VCB_DTYPE_E4M3;
+    const int eb = fp8 ? 1 : 2;                    // operand bytes per element; a k-block is 128 bytes of K either way
+    p.a_scale = fp8 ? a->a_scale : nullptr; p.w_scale = fp8 ? a->w_scale : nullptr;
     for (int r = 0; r < kSpMaxRanks; ++r) p.sp_out[r] = r < p.sp_world ? (__nv_bfloat16*)a->sp_out[r] : nullptr;
     if (int rc = make_tmap_3d(&out->ta, a->A, (uint64_t)a->K, (uint64_t)a->rows_per_batch, (uint64_t)batch, (uint64_t)a->lda,
-                              (uint64_t)a_bstride, 64, 128)) return rc;
-    if (int rc = make_tmap_2d(&out->tb, a->W, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldw, 64, (uint32_t)(bn / cg))) return rc;
+                              (uint64_t)a_bstride, 128 / eb, 128, eb)) return rc;
+    if (int rc = make_tmap_2d(&out->tb, a->W, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldw, 128 / eb, (uint32_t)(bn / cg), eb)) return rc;
     // sequence-parallel destinations: this problem's rows of every rank's [W * rows, 3 * hidden / W] qkv buffer
     for (int r = 0; r < p.sp_world; ++r) {
         const int64_t ld = 3LL * (a->hidden / a->sp_world);
@@ -234,8 +255,9 @@ int gemm_dispatch(const vcb_gemm_args* a, const vcb_gemm_args* a1, void* stream)
     if (int rc = check_gemm_args(a)) return rc;
     if (a1) {
         if (int rc = check_gemm_args(a1)) return rc;
-        if (a1->N != a->N || a1->K != a->K || a1->epilogue != a->epilogue || (a1->sp_world > 1) != (a->sp_world > 1))
-            return set_error("gemm (grouped): both problems need the same N, K, epilogue and sequence-parallel mode");
+        if (a1->N != a->N || a1->K != a->K || a1->epilogue != a->epilogue || (a1->sp_world > 1) != (a->sp_world > 1) ||
+            a1->operand_dtype != a->operand_dtype)
+            return set_error("gemm (grouped): both problems need the same N, K, epilogue, operand dtype and sequence-parallel mode");
     }
     if (int rc = ensure_device()) return rc;
     const bool head = a->epilogue == VCB_EPI_QKV || a->epilogue == VCB_EPI_LINEAR1;
@@ -243,7 +265,8 @@ int gemm_dispatch(const vcb_gemm_args* a, const vcb_gemm_args* a1, void* stream)
     // tile choice for the combined tile count (the second problem only adds tiles of the same shape)
     const int batch = a->M / a->rows_per_batch;
     float rate;
-    pick_tile(batch, a->rows_per_batch + (a1 ? a1->M / batch : 0), a->N, a->K, head, a->cta_group ? a->cta_group : forced_cta_group(),
+    const bool fp8 = a->operand_dtype == VCB_DTYPE_E4M3;
+    pick_tile(batch, a->rows_per_batch + (a1 ? a1->M / batch : 0), a->N, a->K, head || fp8, a->cta_group ? a->cta_group : forced_cta_group(),
               a->block_n, &cg, &bn, &rate);
     ProfScope prof(PROF_GEMM, stream, a->M + (a1 ? a1->M : 0), a->N, a->K, a->epilogue | (bn << 8) | (cg << 16));
     Problem g0, g1;
@@ -255,6 +278,16 @@ int gemm_dispatch(const vcb_gemm_args* a, const vcb_gemm_args* a1, void* stream)
         g1.p = GemmParams{};            // batch == 0: no second problem
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (fp8) {
+#define VCB_GEMM_CASE8(BN, CG) \
+    if (bn == BN && cg == CG) return launch_gemm_epi_fp8<BN, CG>(a->epilogue, g0, g1, rate, st);
+        VCB_GEMM_CASE8(128, 1)
+        VCB_GEMM_CASE8(256, 1)
+        VCB_GEMM_CASE8(128, 2)
+        VCB_GEMM_CASE8(256, 2)
+#undef VCB_GEMM_CASE8
+        return set_error("gemm (fp8): unsupported (block_n=%d, cta_group=%d)", bn, cg);
+    }
 #define VCB_GEMM_CASE(BN, CG) \
     if (bn == BN && cg == CG) return launch_gemm_epi<BN, CG>(a->epilogue, g0, g1, rate, st);
     VCB_GEMM_CASE(64, 1)
@@ -371,15 +404,8 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
     if (int rc = ensure_device()) return rc;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    static int use_v1 = 0, use_v2 = 0;
     std::call_once(once, [&] {
-        attr_err = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(attn_fwd2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
+        attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
         if (attr_err == cudaSuccess)
@@ -387,15 +413,9 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
         if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
-        if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(attn_fwd4_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn4SmemBytes);
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(attn_fwd4_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn4SmemBytes);
-        const char* e = getenv("VCB_ATTN_V1");
-        use_v1 = e ? atoi(e) : 0;
-        e = getenv("VCB_ATTN_V2");
-        use_v2 = e ? atoi(e) : 0;
     });
     if (attr_err != cudaSuccess) return set_error("cudaFuncSetAttribute(attn): %s", cudaGetErrorString(attr_err));
     CUtensorMap tm;
@@ -408,11 +428,9 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
     static const bool no_bound = [] { const char* e = getenv("VCB_ATTN_EXACT_MAX"); return e && atoi(e); }();
     const bool fixed = bound > 0.f && !no_bound;
     p.fixed_max = fixed ? bound : 0.f;
-    if (fixed && (use_v1 || use_v2)) return set_error("attention: score_bound_log2 needs the default kernel (attn_fwd3)");
     if (out_peers) {
         if (world < 2 || world > VCB_SP_MAX || B != 1 || seqlens || rows_per_rank <= 0 || (int64_t)rows_per_rank * world != L)
             return set_error("attention (sp): needs one unpadded sample with L == world * rows_per_rank, 2 <= world <= %d", VCB_SP_MAX);
-        if (use_v1 || use_v2) return set_error("attention (sp): only the default kernel (attn_fwd3) routes to peers");
         p.sp_world = world; p.sp_rows = rows_per_rank;
         for (int r = 0; r < world; ++r) {
             if (!out_peers[r]) return set_error("attention (sp): out_peers[%d] is null", r);
@@ -420,7 +438,6 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         }
     }
     ProfScope prof(PROF_ATTN, stream, B, L, heads, fixed ? 1 : 0);
-    static const bool pchunks4 = [] { const char* e = getenv("VCB_ATTN_PCHUNKS"); return e && atoi(e) == 4; }();
     static const bool sp_direct = [] { const char* e = getenv("VCB_SP_ATTN_DIRECT"); return e && atoi(e); }();
     if (out_peers && !sp_direct) {
         // staged TMA tile stores into the row owners' buffers (NVLink for remote owners)
@@ -441,7 +458,7 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
     int pgrid = num_sms();
     if (T / pgrid < 8) pgrid = (int)(T / 8 > 0 ? T / 8 : 1);           // tiny problems: fewer CTAs, >= 8 half-iterations each
     // segments per CTA <= units per CTA + 2; beyond the kernel's list capacity (huge batches of short sequences) use attn3
-    const bool persist_ok = !seqlens && !out_peers && !use_v1 && !use_v2 && !pchunks4 && num_sms() <= 160 &&
+    const bool persist_ok = !seqlens && !out_peers && num_sms() <= 160 &&
                             (long long)B * heads * ((n_qt + 1) / 2) / pgrid + 3 <= kAttn4MaxSegs;
     if (schedule == VCB_ATTN_SCHED_PERSISTENT && !persist_ok)
         return set_error("attention: the persistent schedule takes unpadded batches (seqlens == NULL), no sequence-parallel routing");
@@ -457,21 +474,14 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         count_launch();
         return 0;
     }
-    if (use_v1) {
-        dim3 grid((L + kAttnTile - 1) / kAttnTile, heads, B);
-        attn_fwd_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmemBytes, (cudaStream_t)stream>>>(tm, p);
-    } else {
+    {
         dim3 grid((L + 2 * kAttnTile - 1) / (2 * kAttnTile), heads, B);
-        cudaError_t e = use_v2 ? launch_pdl(attn_fwd2_tcgen05_kernel, grid, dim3(kAttn2Threads), (size_t)kAttn2SmemBytes, (cudaStream_t)stream, 1, tm, p)
-                               : (fixed && pchunks4) ? launch_pdl(attn_fwd3_tcgen05_kernel<false, 4, true>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{})
-                               : fixed ? launch_pdl(attn_fwd3_tcgen05_kernel<false, 2, true>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{})
-                               : (pchunks4 ? launch_pdl(attn_fwd3_tcgen05_kernel<false, 4>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{})
-                                           : launch_pdl(attn_fwd3_tcgen05_kernel<false, 2>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{}));
+        cudaError_t e = fixed ? launch_pdl(attn_fwd3_tcgen05_kernel<false, 2, true>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{})
+                              : launch_pdl(attn_fwd3_tcgen05_kernel<false, 2>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, AttnSpMapsT<false>{});
         if (e != cudaSuccess) return set_error("attention launch: %s", cudaGetErrorString(e));
         count_launch();
         return 0;
     }
-    return check_launch("attention");
 }
 }  // namespace
 
@@ -616,6 +626,35 @@ extern "C" int vcb_ln_modulate_grouped(const vcb_ln_args* a0, const vcb_ln_args*
     if (!a0 || !a1) return set_error("ln_modulate (grouped): null problem");
     if (batch_rows <= 0) return set_error("ln_modulate (grouped): batch_rows (rows of one sample in the joint buffer) is required");
     return ln_launch(a0, a1, ldx, ldy, mod_stride, hidden, batch_rows, stream);
+}
+
+extern "C" int vcb_ln_modulate_fp8(const vcb_ln_args* a0, const vcb_ln_args* a1, float* row_scale0, float* row_scale1, int64_t ldx,
+                                   int64_t ld8, int64_t mod_stride, int32_t hidden, int32_t batch_rows, void* stream) {
+    if (!a0 || !row_scale0 || (a1 && !row_scale1)) return set_error("ln_modulate_fp8: null problem / row_scale");
+    if (hidden % 256 || hidden > 256 * kLnMaxChunks) return set_error("ln_modulate_fp8: hidden must be a multiple of 256, <= %d", 256 * kLnMaxChunks);
+    if (ldx % 8 || ld8 % 16 || mod_stride % 8) return set_error("ln_modulate_fp8: ldx / mod_stride must be multiples of 8, ld8 of 16");
+    if (batch_rows <= 0) return set_error("ln_modulate_fp8: batch_rows (rows of one sample in the joint buffer) is required");
+    LnFp8Problem p[2] = {};
+    const vcb_ln_args* a[2] = {a0, a1};
+    float* rs[2] = {row_scale0, row_scale1};
+    for (int i = 0; i < 2; ++i) {
+        if (!a[i]) continue;
+        if (!a[i]->x || !a[i]->y || !a[i]->shift || !a[i]->scale || a[i]->rows <= 0 || a[i]->rows_per_batch <= 0)
+            return set_error("ln_modulate_fp8: bad arguments");
+        p[i] = LnFp8Problem{(const __nv_bfloat16*)a[i]->x, (uint8_t*)a[i]->y, rs[i], (const __nv_bfloat16*)a[i]->shift,
+                            (const __nv_bfloat16*)a[i]->scale, a[i]->rows, a[i]->rows_per_batch, (a[i]->rows + kLnWarps - 1) / kLnWarps};
+    }
+    if (int rc = ensure_device()) return rc;
+    ProfScope prof(PROF_LN, stream);
+    const dim3 grid(p[0].blocks + p[1].blocks), block(kLnWarps * 32);
+    cudaError_t e = hidden <= 12 * 256
+        ? launch_pdl(ln_modulate_fp8_kernel<12>, grid, block, (size_t)hidden * 4, (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx,
+                     (long long)ld8, (long long)mod_stride, (int)hidden, (int)batch_rows)
+        : launch_pdl(ln_modulate_fp8_kernel<kLnMaxChunks>, grid, block, (size_t)hidden * 4, (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx,
+                     (long long)ld8, (long long)mod_stride, (int)hidden, (int)batch_rows);
+    if (e != cudaSuccess) return set_error("ln_modulate_fp8 launch: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
 }
 
 extern "C" int vcb_timestep_embedding(const float* t_scaled, const float* freqs, void* out, int32_t n, void* stream) {

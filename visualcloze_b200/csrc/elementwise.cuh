@@ -189,6 +189,117 @@ ln_modulate2_kernel(const LnProblem p0, const LnProblem p1, long long ldx, long 
     }
 }
 
+// FP8 variant (opt-in fp8 projections): same statistics and modulation, but the row leaves as e4m3 bytes with ONE fp32 scale per
+// row: s = max|y| / 448, y8 = e4m3(y / s).  The fp8 GEMM multiplies its accumulator by s (a_scale) again.  The modulated row is
+// kept in registers between the amax and the quantisation (one warp per row, 3 blocks per SM like the one-pass bf16 kernel).
+VCB_DEVICE uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+    uint16_t lo, hi;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));      // first source -> upper byte
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+    return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+struct LnFp8Problem {
+    const __nv_bfloat16* x; uint8_t* y8; float* row_scale;        // row_scale is indexed by the PHYSICAL row of the joint buffer
+    const __nv_bfloat16* shift; const __nv_bfloat16* scale;
+    int rows, rows_per_batch, blocks;
+};
+template <int kChunks>
+__global__ void __launch_bounds__(kLnWarps * 32, 3)
+ln_modulate_fp8_kernel(const LnFp8Problem p0, const LnFp8Problem p1, long long ldx, long long ldy, long long mod_stride, int H,
+                       int batch_rows) {
+    extern __shared__ uint4 ln_smem[];                 // [2][H / 8] : shift, scale of sample b0
+    pdl_launch_dependents();
+    pdl_wait();
+    const bool second = (int)blockIdx.x >= p0.blocks;
+    const LnFp8Problem& P = second ? p1 : p0;
+    const int rows = P.rows, rows_per_batch = P.rows_per_batch;
+    const int row0 = ((int)blockIdx.x - (second ? p0.blocks : 0)) * kLnWarps;
+    const int b0 = row0 / rows_per_batch;
+    const int nvec = H >> 3;
+    for (int i = threadIdx.x; i < 2 * nvec; i += blockDim.x) {
+        const __nv_bfloat16* src = (i < nvec ? P.shift : P.scale) + (long long)b0 * mod_stride;
+        ln_smem[i] = __ldg(reinterpret_cast<const uint4*>(src) + (i < nvec ? i : i - nvec));
+    }
+    const int row = row0 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int nchunks = H >> 8;
+    const bool active = row < rows;
+    const int b = active ? row / rows_per_batch : b0;
+    const long long prow = (long long)b * batch_rows + (row - b * rows_per_batch);
+    uint4 v[kChunks];
+    float sum = 0.f, sq = 0.f;
+    if (active) {
+        const __nv_bfloat16* xr = P.x + prow * ldx;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c)
+            if (c < nchunks) v[c] = *reinterpret_cast<const uint4*>(xr + c * 256 + lane * 8);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c)
+            if (c < nchunks) {
+                const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float2 f = unpack_bf16x2(w[e]);
+                    sum += f.x + f.y;
+                    sq = fmaf(f.x, f.x, fmaf(f.y, f.y, sq));
+                }
+            }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    __syncthreads();                                // modulation vectors staged
+    if (!active) return;
+    const float mean = sum / (float)H;
+    const float var = fmaxf(sq / (float)H - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + 1e-6f);
+    const bool staged = (b == b0);
+    const uint4* sh_g = reinterpret_cast<const uint4*>(P.shift + (long long)b * mod_stride);
+    const uint4* sc_g = reinterpret_cast<const uint4*>(P.scale + (long long)b * mod_stride);
+    // modulate in place (v <- bf16(y), the value the bf16 path would hand to the GEMM), tracking the row's max |y|
+    float amax = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c)
+        if (c < nchunks) {
+            const int vi = c * 32 + lane;
+            const uint4 hu = staged ? ln_smem[vi] : __ldg(sh_g + vi);
+            const uint4 su = staged ? ln_smem[nvec + vi] : __ldg(sc_g + vi);
+            const uint32_t xw[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+            const uint32_t sw[4] = {su.x, su.y, su.z, su.w};
+            const uint32_t hw[4] = {hu.x, hu.y, hu.z, hu.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 xf = unpack_bf16x2(xw[e]);
+                float2 s2 = unpack_bf16x2(sw[e]);
+                float2 h2 = unpack_bf16x2(hw[e]);
+                float a0 = bf16_round(1.0f + s2.x), a1 = bf16_round(1.0f + s2.y);
+                float n0 = (xf.x - mean) * rstd, n1 = (xf.y - mean) * rstd;
+                const float y0 = __fadd_rn(__fmul_rn(a0, n0), h2.x), y1 = __fadd_rn(__fmul_rn(a1, n1), h2.y);
+                ow[e] = pack_bf16x2(y0, y1);
+                amax = fmaxf(amax, fmaxf(fabsf(y0), fabsf(y1)));
+            }
+            v[c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float s = fmaxf(amax, 1e-12f) * (1.0f / 448.0f);
+    const float inv = 1.0f / s;
+    if (lane == 0) P.row_scale[prow] = s;
+    uint8_t* yr = P.y8 + prow * ldy;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c)
+        if (c < nchunks) {
+            const float2 f0 = unpack_bf16x2(v[c].x), f1 = unpack_bf16x2(v[c].y), f2 = unpack_bf16x2(v[c].z), f3 = unpack_bf16x2(v[c].w);
+            uint2 o;
+            o.x = pack_e4m3x4(f0.x * inv, f0.y * inv, f1.x * inv, f1.y * inv);
+            o.y = pack_e4m3x4(f2.x * inv, f2.y * inv, f3.x * inv, f3.y * inv);
+            *reinterpret_cast<uint2*>(yr + c * 256 + lane * 8) = o;
+        }
+}
+
 // ------------------------------------------------------------------------------------------------
 // small per-step / per-image helpers
 // ------------------------------------------------------------------------------------------------

@@ -23,7 +23,10 @@ struct vcb_flux {
     // prepared state
     bool prepared = false;
     int B = 0, Li = 0, Lt = 0, L = 0, E = 0;
-    bool use_score_bounds = true;     // false: every block runs the exact online-max softmax (vcb_flux_use_score_bounds)
+    bool use_score_bounds = true;
+    bool fp8 = false;                 // vcb_flux_set_fp8: LayerNorm-fed projections on e4m3 operands
+    uint8_t* xm8 = nullptr;           // [B, L, H] e4m3 LayerNorm output (fp8 mode)
+    float* row_scale = nullptr;       // [B * L] fp32 per-row activation scale (fp8 mode)     // false: every block runs the exact online-max softmax (vcb_flux_use_score_bounds)
     const int32_t* seqlens = nullptr;
     float2* rope = nullptr;
     uint16_t *txt0 = nullptr, *temb_t = nullptr, *temb_g = nullptr, *h1 = nullptr, *e_time = nullptr, *e_guid = nullptr,
@@ -73,6 +76,8 @@ int64_t carve(vcb_flux* f, uint8_t* base, int B, int Li, int Lt, int E) {
     uint16_t* mod_final = cv.take<uint16_t>(EB * 2 * H);
     uint16_t* x = cv.take<uint16_t>((int64_t)B * L * H);
     uint16_t* xm = cv.take<uint16_t>((int64_t)B * L * H);
+    uint8_t* xm8 = cv.take<uint8_t>((int64_t)B * L * H);
+    float* row_scale = cv.take<float>((int64_t)B * L);
     // sequence-parallel: qkv [W*L, 3H/W] and cat [L, H+mlp] are the caller's peer-mapped allocations (same sizes)
     const bool sp = f->sp_world > 1;
     uint16_t* qkv = sp ? static_cast<uint16_t*>(f->sp_qkv[f->sp_rank]) : cv.take<uint16_t>((int64_t)B * L * 3 * H);
@@ -80,7 +85,7 @@ int64_t carve(vcb_flux* f, uint8_t* base, int B, int Li, int Lt, int E) {
     if (base) {
         f->rope = rope; f->txt0 = txt0; f->temb_t = temb_t; f->temb_g = temb_g; f->h1 = h1; f->e_time = e_time;
         f->e_guid = e_guid; f->e_vec = e_vec; f->vec = vec; f->svec = svec; f->mod_dbl = md; f->mod_sgl = ms;
-        f->mod_final = mod_final; f->x = x; f->xm = xm; f->qkv = qkv; f->cat = cat;
+        f->mod_final = mod_final; f->x = x; f->xm = xm; f->qkv = qkv; f->cat = cat; f->xm8 = xm8; f->row_scale = row_scale;
     }
     return cv.off;
 }
@@ -121,6 +126,21 @@ extern "C" int vcb_flux_create(const vcb_flux_config* cfg, const vcb_flux_weight
 }
 
 extern "C" void vcb_flux_destroy(vcb_flux* f) { delete f; }
+
+extern "C" int vcb_flux_set_fp8(vcb_flux* f, int32_t enable) {
+    if (!f) return set_error("flux_set_fp8: null engine");
+    if (enable) {
+        if (f->sp_world > 1) return set_error("flux_set_fp8: the sequence-parallel mode runs bf16 projections");
+        for (const auto& d : f->dbl)
+            for (const vcb_stream_w* s : {&d.img, &d.txt})
+                if (!s->qkv.w8 || !s->qkv.w8_scale || !s->mlp0.w8 || !s->mlp0.w8_scale)
+                    return set_error("flux_set_fp8: double-block qkv / mlp.0 weights carry no e4m3 copy (w8, w8_scale)");
+        for (const auto& g : f->sgl)
+            if (!g.linear1.w8 || !g.linear1.w8_scale) return set_error("flux_set_fp8: linear1 weights carry no e4m3 copy (w8, w8_scale)");
+    }
+    f->fp8 = enable != 0;
+    return 0;
+}
 
 extern "C" int vcb_flux_use_score_bounds(vcb_flux* f, int32_t enable) {
     if (!f) return set_error("flux_use_score_bounds: null engine");
@@ -232,6 +252,13 @@ vcb_gemm_args stream_args(const vcb_flux* f, const StreamView& sv, const uint16_
     g.gate = gate; g.gate_stride = gate_stride; g.res = out; g.ld_res = ldo;
     g.hidden = f->cfg.hidden; g.q_scale = q_scale; g.k_scale = k_scale; g.rope = f->rope; g.rope_rows = (int64_t)f->B * f->L;
     g.out2 = out2; g.ldo2 = ldo2; g.out2_col_offset = out2_col;
+    if (f->fp8 && a_buf == f->xm && w.w8) {
+        // fp8 projection: A = the e4m3 LayerNorm output (same [B, L, H] row layout, one byte per element), W = the e4m3 weight
+        g.operand_dtype = VCB_DTYPE_E4M3;
+        g.A = f->xm8 + (int64_t)sv.off * lda + a_col;
+        g.W = w.w8;
+        g.a_scale = f->row_scale; g.w_scale = w.w8_scale;
+    }
     if (f->sp_world > 1 && (epi == VCB_EPI_QKV || epi == VCB_EPI_LINEAR1)) {
         g.sp_world = f->sp_world; g.sp_row_offset = f->sp_rank * f->L;
         for (int r = 0; r < f->sp_world; ++r) g.sp_out[r] = f->sp_qkv[r];
@@ -273,9 +300,14 @@ int stream_gemm(const vcb_flux* f, const StreamView& sv, const uint16_t* a_buf, 
     return vcb_gemm_bf16(&g, stream);
 }
 
+// fp8: the LayerNorm feeds an fp8 projection -> e4m3 rows + per-row scales instead of bf16 rows
 int stream_ln(const vcb_flux* f, const StreamView& sv, const uint16_t* shift, const uint16_t* scale, int64_t mod_stride,
-              void* stream) {
+              void* stream, bool fp8 = false) {
     const int H = f->cfg.hidden;
+    if (fp8) {
+        vcb_ln_args a{f->x + (int64_t)sv.off * H, f->xm8 + (int64_t)sv.off * H, shift, scale, f->B * sv.rows, sv.rows};
+        return vcb_ln_modulate_fp8(&a, nullptr, f->row_scale + sv.off, nullptr, H, H, mod_stride, H, f->L, stream);
+    }
     return vcb_ln_modulate(f->x + (int64_t)sv.off * H, H, f->xm + (int64_t)sv.off * H, H, shift, scale, mod_stride,
                            f->B * sv.rows, H, sv.rows, f->L, stream);
 }
@@ -284,6 +316,12 @@ int stream_ln(const vcb_flux* f, const StreamView& sv, const uint16_t* shift, co
 int double_ln(const vcb_flux* f, const StreamView* const sv[2], const uint16_t* const mod[2], int mod_col, void* stream) {
     const int H = f->cfg.hidden;
     vcb_ln_args a[2];
+    if (f->fp8) {
+        for (int s = 0; s < 2; ++s)
+            a[s] = vcb_ln_args{f->x + (int64_t)sv[s]->off * H, f->xm8 + (int64_t)sv[s]->off * H, mod[s] + mod_col, mod[s] + mod_col + H,
+                               f->B * sv[s]->rows, sv[s]->rows};
+        return vcb_ln_modulate_fp8(&a[0], &a[1], f->row_scale + sv[0]->off, f->row_scale + sv[1]->off, H, H, 6 * H, H, f->L, stream);
+    }
     for (int s = 0; s < 2; ++s)
         a[s] = vcb_ln_args{f->x + (int64_t)sv[s]->off * H, f->xm + (int64_t)sv[s]->off * H, mod[s] + mod_col, mod[s] + mod_col + H,
                            f->B * sv[s]->rows, sv[s]->rows};
@@ -363,7 +401,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
     for (int i = 0; i < c.depth_single; ++i) {
         const vcb_single_w& w = f->sgl[i];
         const uint16_t* mod = f->mod_sgl[i] + erow * 3 * H;
-        if ((rc = stream_ln(f, s_all, mod + 0, mod + H, 3 * H, stream))) return rc;
+        if ((rc = stream_ln(f, s_all, mod + 0, mod + H, 3 * H, stream, f->fp8))) return rc;
         if ((rc = stream_gemm(f, s_all, f->xm, H, 0, H, w.linear1, 3 * H + mlp, VCB_EPI_LINEAR1, f->qkv, 3 * H, 0, nullptr, 0,
                               nullptr, w.q_scale, w.k_scale, f->cat, ldc, H, stream))) return rc;
         if ((rc = joint_attention(f, ldc, w.attn_score_bound, stream))) return rc;

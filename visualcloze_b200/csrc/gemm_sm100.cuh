@@ -44,6 +44,10 @@ struct GemmParams {
     int out_batch_rows;
     int out_row_offset;
     const float* bias;           // [N] fp32 (may be null)
+    // FP8 (e4m3) operands (kFp8 instantiations): acc is rescaled by a_scale[mapped output row] * w_scale[column] before the bias --
+    // per-row activation scales written by the producing LayerNorm kernel, per-output-channel weight scales from packing time
+    const float* a_scale;        // [rows of the joint buffer] fp32 (null = 1)
+    const float* w_scale;        // [N] fp32 (null = 1)
     __nv_bfloat16* out;          // primary output
     long long ldo;               // elements
     int out_col_offset;
@@ -171,11 +175,20 @@ VCB_DEVICE void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int n0, 
     }
 }
 
-VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, int n0, int N, float (&v)[32]) {
+// sa: this thread's row scale (1 for bf16 operands); ws: per-column weight scales or null.  fp8: acc * sa * ws[n] + bias
+VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, int n0, int N, float (&v)[32], float sa = 1.0f,
+                              const float* __restrict__ ws = nullptr) {
     uint32_t r[32];
     __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge after predicated stores
     tmem_ld_x32(taddr, r);
     tmem_wait_ld();
+    if (ws != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float sw = (n0 + j < N) ? __ldg(ws + n0 + j) : 0.0f;
+            r[j] = __float_as_uint(__uint_as_float(r[j]) * (sa * sw));
+        }
+    }
     if (bias != nullptr && n0 + 32 <= N) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -197,13 +210,18 @@ VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, in
 // ----------------------------------------------------------------------------------------------
 // the kernel
 // ----------------------------------------------------------------------------------------------
-template <int BLOCK_N, int kCtaGroup, int kEpi, int kAMode = A_MATRIX, bool kSp = false>
+// kFp8: both operands are e4m3 bytes (K-major, 128 elements per 128-byte swizzle row); tcgen05.mma kind::f8f6f4, UMMA K = 32.
+// A k-block is 128 bytes of K in either mode, so the pipeline (stage bytes, 4 MMAs of 32 bytes of K per k-block, descriptor
+// advance) is unchanged; only the element count per k-block, the MMA kind and the epilogue's rescaling differ.
+template <int BLOCK_N, int kCtaGroup, int kEpi, int kAMode = A_MATRIX, bool kSp = false, bool kFp8 = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p, const __grid_constant__ CUtensorMap tmap_a1,
                          const __grid_constant__ CUtensorMap tmap_b1, const GemmParams p1, const StreamKParams skp,
                          const __grid_constant__ SpMapsT<kSp> spm) {
     static_assert(!kSp || kEpi == EPI_QKV || kEpi == EPI_LINEAR1, "sequence-parallel routing lives in the head-structured epilogues");
+    static_assert(!kFp8 || (kAMode == A_MATRIX && !kSp), "fp8 operands: plain matrices, single-GPU path");
+    constexpr int kBlockKEl = kFp8 ? 2 * kBlockK : kBlockK;          // elements of K per k-block (128 bytes either way)
     // Grouped launch: an optional second problem (p1.batch > 0) with the same N, K and epilogue but its own operands --
     // the txt stream of a DoubleStreamBlock rides in the img stream's launch and fills its partial last wave.
     using Cfg = GemmCfg<BLOCK_N, kCtaGroup>;
@@ -263,7 +281,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int m_per_sample1 = (p1.rows_per_batch + tile_m - 1) / tile_m;
     const int num_m1 = p1.batch > 0 ? m_per_sample1 * p1.batch : 0;
     const int num_tiles = tiles0 + num_m1 * num_n;
-    const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+    const int num_kb = (p.K + kBlockKEl - 1) / kBlockKEl;
     const int cluster_id = blockIdx.x / kCtaGroup;
     const int num_clusters = gridDim.x / kCtaGroup;
 
@@ -296,10 +314,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         tma_load_4d<false>(ta, &full_bar[stage], smem_a + stage * Cfg::kABytes, cb * kBlockK, x0, y0, bi,
                                            kEvictNormal);
                     } else {
-                        tma_load_3d<kCtaGroup == 2>(ta, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBlockK,
+                        tma_load_3d<kCtaGroup == 2>(ta, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBlockKEl,
                                                     m0, bi, kEvictNormal);
                     }
-                    tma_load_2d<kCtaGroup == 2>(tb, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBlockK,
+                    tma_load_2d<kCtaGroup == 2>(tb, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBlockKEl,
                                                 n0, kEvictNormal);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -310,7 +328,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // ===================== MMA issuer (leader CTA) =====================
         // The warp runs the loop convergently (descriptors in uniform registers); one elected lane issues tcgen05 ops.
         if (is_leader) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCtaGroup, BLOCK_N, 0, 0);
+            constexpr uint32_t idesc = kFp8 ? make_idesc_e4m3(kBlockM * kCtaGroup, BLOCK_N) : make_idesc_bf16(kBlockM * kCtaGroup, BLOCK_N, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -330,8 +348,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                             // advance 16 bf16 = 32 B inside the 128B swizzle span: +2 in the (addr >> 4) field
-                            umma_ss<kCtaGroup>(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                                               (kb > kb0 || k != 0) ? 1u : 0u);
+                            umma_ss<kCtaGroup, kFp8>(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                                                     (kb > kb0 || k != 0) ? 1u : 0u);
                         }
                         umma_commit<kCtaGroup>(&empty_bar[stage]);
                         if (kb == kb1 - 1) umma_commit<kCtaGroup>(&tmem_full[acc]);
@@ -376,6 +394,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 row_ok = i < P.rows_per_batch;
             }
             const long long orow = (long long)b * P.out_batch_rows + P.out_row_offset + (row_ok ? i : 0);
+            [[maybe_unused]] const float sa = (kFp8 && P.a_scale) ? __ldg(P.a_scale + orow) : 1.0f;
+            [[maybe_unused]] const float* ws = kFp8 ? P.w_scale : nullptr;
 
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -476,7 +496,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const int n0 = n_tile0 + cc * 32;
                     if (n0 >= P.N) break;
                     float v[32];
-                    load_acc_bias(taddr + cc * 32, P.bias, n0, P.N, v);
+                    load_acc_bias(taddr + cc * 32, P.bias, n0, P.N, v, sa, ws);
                     if (row_ok) {
                         if constexpr (kEpi == EPI_BIAS_GELU) {
 #pragma unroll
@@ -564,7 +584,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         for (int c = 0; c < 4; ++c) {
                             const int n0 = ng + c * 32;
                             float v[32];
-                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v);
+                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v, sa, ws);
                             if (kEpi == EPI_LINEAR1 && region >= 3) {
                                 if (row_ok) {
 #pragma unroll
@@ -583,7 +603,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll 1
                         for (int c = 0; c < 4; ++c) {
                             float v[32];
-                            load_acc_bias(tg + c * 32, P.bias, ng + c * 32, P.N, v);
+                            load_acc_bias(tg + c * 32, P.bias, ng + c * 32, P.N, v, sa, ws);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
                         }
@@ -596,7 +616,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         for (int c = 0; c < 4; ++c) {
                             const int n0 = ng + c * 32;
                             float v[32];
-                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v);
+                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v, sa, ws);
                             if (row_ok) {
                                 uint32_t sw[16];
 #pragma unroll

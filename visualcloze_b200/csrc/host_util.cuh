@@ -167,8 +167,9 @@ inline PFN_encodeTiled encode_fn() {
 }
 
 // bf16 tensor, dims given innermost-first; strides in ELEMENTS for dims 1.. ; 128-byte swizzle; OOB reads give zeros
+// elem_bytes: 2 = bf16 (default), 1 = 8-bit (e4m3 operands of the fp8 GEMM)
 inline int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                     const uint32_t* box, const uint32_t* elem_strides = nullptr) {
+                     const uint32_t* box, const uint32_t* elem_strides = nullptr, int elem_bytes = 2) {
     PFN_encodeTiled fn = encode_fn();
     if (!fn) return set_error("cuTensorMapEncodeTiled entry point not available");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error("TMA base pointer must be 16-byte aligned");
@@ -180,30 +181,30 @@ inline int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
         gbox[i] = box[i];
         estr[i] = elem_strides ? elem_strides[i] : 1;
         if (i > 0) {
-            gstr[i - 1] = strides_elems[i - 1] * 2;
+            gstr[i - 1] = strides_elems[i - 1] * (uint64_t)elem_bytes;
             if (gstr[i - 1] % 16) return set_error("TMA stride must be a multiple of 16 bytes");
         }
     }
-    if (box[0] * 2 > 128) return set_error("TMA inner box exceeds the 128-byte swizzle span");
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
+    if (box[0] * (uint32_t)elem_bytes > 128) return set_error("TMA inner box exceeds the 128-byte swizzle span");
+    CUresult r = fn(m, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return 0;
 }
 inline int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols,
-                        uint32_t box_rows) {
+                        uint32_t box_rows, int elem_bytes = 2) {
     const uint64_t dims[2] = {cols, rows};
     const uint64_t str[1] = {ld};
     const uint32_t box[2] = {box_cols, box_rows};
-    return make_tmap(m, base, 2, dims, str, box);
+    return make_tmap(m, base, 2, dims, str, box, nullptr, elem_bytes);
 }
 inline int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld,
-                        uint64_t batch_stride, uint32_t box_cols, uint32_t box_rows) {
+                        uint64_t batch_stride, uint32_t box_cols, uint32_t box_rows, int elem_bytes = 2) {
     const uint64_t dims[3] = {cols, rows, batch};
     const uint64_t str[2] = {ld, batch_stride};
     const uint32_t box[3] = {box_cols, box_rows, 1};
-    return make_tmap(m, base, 3, dims, str, box);
+    return make_tmap(m, base, 3, dims, str, box, nullptr, elem_bytes);
 }
 inline int make_tmap_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_elems[3],
                         const uint32_t box[4], const uint32_t* elem_strides = nullptr) {

@@ -216,6 +216,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f8f6f4 with both operands e4m3 (format code 0 in [7,10) and [10,13)), fp32 accumulate, K-major x K-major
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // Shared-memory matrix descriptor (PTX ISA "Matrix descriptor", sm_100 version field = 1).
 //   [0,14) start address >> 4   [16,30) leading-dim byte offset >> 4   [32,46) stride-dim byte offset >> 4
 //   [46,48) version = 1         [61,64) swizzle: 0 none, 2 = 128B, 4 = 64B, 6 = 32B
@@ -230,10 +235,26 @@ VCB_DEVICE uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t 
 }
 constexpr uint32_t kSwizzle128B = 2;
 
-// D[tmem] (+)= A[smem] * B[smem]
-template <int kCtaGroup>
+// D[tmem] (+)= A[smem] * B[smem]; kFp8: kind::f8f6f4 (8-bit operands, K = 32 per instruction) instead of kind::f16
+template <int kCtaGroup, bool kFp8 = false>
 VCB_DEVICE void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    if constexpr (kCtaGroup == 1) {
+    if constexpr (kFp8) {
+        if constexpr (kCtaGroup == 1) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                : "memory");
+        } else {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                : "memory");
+        }
+    } else if constexpr (kCtaGroup == 1) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"

@@ -25,7 +25,7 @@ def _freqs() -> Tensor:
 
 
 class FluxEngine:
-    def __init__(self, params, named_params: dict[str, Tensor], lora_scale: float = 1.0):
+    def __init__(self, params, named_params: dict[str, Tensor], lora_scale: float = 1.0, fp8: bool = False):
         some = next(iter(named_params.values()))
         if not some.is_cuda:
             raise _lib.VcbError("FluxEngine needs the model on a CUDA device: the hot path has no CPU fallback")
@@ -35,6 +35,7 @@ class FluxEngine:
         self._keep: list[Tensor] = []          # packed tensors referenced by the C structs
         self._p = named_params
         self._scale = float(lora_scale)
+        self.fp8 = bool(fp8)
         self.H = params.hidden_size
         self.mlp = int(params.hidden_size * params.mlp_ratio)
         with torch.no_grad():
@@ -57,24 +58,35 @@ class FluxEngine:
         self._shape = None
 
     # ---- weight packing -----------------------------------------------------------------------
-    def _linear(self, name: str) -> LinearW:
+    def _linear(self, name: str, fp8: bool = False) -> LinearW:
+        """``fp8``: also keep an e4m3 copy of the merged weight with one fp32 scale per output channel (amax / 448) for the
+        opt-in fp8 projections (quantised from the fp32 merged weight, not from its bf16 rounding)."""
         p = self._p
         w = p[name + ".weight"]
         a = p.get(name + ".lora_A.weight")
         b = p.get(name + ".bias")
+        w32 = None
         if a is not None:
             # merged LoRA (lora.py:92-98): W' = W + s * B A in fp32, rounded once to bf16
-            w = (w.float() + self._scale * (p[name + ".lora_B.weight"].float() @ a.float())).to(BF16)
+            w32 = w.float() + self._scale * (p[name + ".lora_B.weight"].float() @ a.float())
+            w = w32.to(BF16)
         else:
             w = w.to(BF16)
         w = w.contiguous()
+        w8 = w8s = None
+        if fp8:
+            w32 = w.float() if w32 is None else w32
+            w8s = (w32.abs().amax(dim=1).clamp_min(1e-12) / 448.0).contiguous()
+            w8 = (w32 / w8s[:, None]).to(torch.float8_e4m3fn).contiguous()
+            self._keep += [w8, w8s]
+        del w32
         bias = torch.zeros(w.shape[0], dtype=torch.float32, device=w.device) if b is None else b.float()
         bb = p.get(name + ".lora_B.bias")
         if bb is not None:
             bias = bias + self._scale * bb.float()
         bias = bias.contiguous()
         self._keep += [w, bias]
-        return LinearW(w.data_ptr(), bias.data_ptr())
+        return LinearW(w.data_ptr(), bias.data_ptr(), 0 if w8 is None else w8.data_ptr(), 0 if w8s is None else w8s.data_ptr())
 
     def _scale_vec(self, name: str) -> int:
         t = self._p[name].to(BF16).contiguous()
@@ -112,8 +124,8 @@ class FluxEngine:
         for i in range(P.depth):
             for s, dst in (("img", dbl[i].img), ("txt", dbl[i].txt)):
                 b = f"double_blocks.{i}.{s}"
-                dst.mod, dst.qkv, dst.proj = self._linear(b + "_mod.lin"), self._linear(b + "_attn.qkv"), self._linear(b + "_attn.proj")
-                dst.mlp0, dst.mlp2 = self._linear(b + "_mlp.0"), self._linear(b + "_mlp.2")
+                dst.mod, dst.qkv, dst.proj = self._linear(b + "_mod.lin"), self._linear(b + "_attn.qkv", self.fp8), self._linear(b + "_attn.proj")
+                dst.mlp0, dst.mlp2 = self._linear(b + "_mlp.0", self.fp8), self._linear(b + "_mlp.2")
                 dst.q_scale = self._scale_vec(b + "_attn.norm.query_norm.scale")
                 dst.k_scale = self._scale_vec(b + "_attn.norm.key_norm.scale")
             dbl[i].attn_score_bound = self._score_bound(
@@ -122,7 +134,7 @@ class FluxEngine:
         sgl = (SingleW * max(1, P.depth_single_blocks))()
         for i in range(P.depth_single_blocks):
             b = f"single_blocks.{i}"
-            sgl[i].mod, sgl[i].linear1, sgl[i].linear2 = self._linear(b + ".modulation.lin"), self._linear(b + ".linear1"), self._linear(b + ".linear2")
+            sgl[i].mod, sgl[i].linear1, sgl[i].linear2 = self._linear(b + ".modulation.lin"), self._linear(b + ".linear1", self.fp8), self._linear(b + ".linear2")
             sgl[i].q_scale = self._scale_vec(b + ".norm.query_norm.scale")
             sgl[i].k_scale = self._scale_vec(b + ".norm.key_norm.scale")
             sgl[i].attn_score_bound = self._score_bound([b + ".norm.query_norm.scale"], [b + ".norm.key_norm.scale"])
@@ -131,6 +143,8 @@ class FluxEngine:
         h = C.c_void_p()
         check(self.lib.vcb_flux_create(C.byref(cfg), C.byref(w), C.byref(h)), "vcb_flux_create")
         self._h = h
+        if self.fp8:
+            check(self.lib.vcb_flux_set_fp8(h, 1), "vcb_flux_set_fp8")
 
     def use_score_bounds(self, enable: bool) -> None:
         """False: every block runs the exact online-max softmax kernel (what a checkpoint whose QK-norm scales leave the safe

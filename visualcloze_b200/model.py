@@ -122,6 +122,7 @@ class Flux(nn.Module):
         # names of the parameters that have received values (load_state_dict / init_synthetic / mark_initialized): base weights
         # are allocated with torch.empty, and packing an engine from never-loaded memory must fail loudly, not render garbage
         self._initialized: set[str] = set()
+        self.linear_precision = "bf16"
         kw = dict(device=device, dtype=dtype)
         for name, fin, fout in linear_table(params):
             _attach(self, name + ".weight", nn.Parameter(torch.empty(fout, fin, **kw), requires_grad=False))
@@ -177,13 +178,22 @@ class Flux(nn.Module):
             from ._lib import VcbError
             raise VcbError(f"{len(missing)} base parameters were never loaded (e.g. {missing[:3]}): load the FLUX.1-Fill checkpoint "
                            "(VisualClozeModel(flux_ckpt=...) / load_state_dict) or call init_synthetic() before running the model")
-        key = (self.lora_scale,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (self.lora_scale, self.linear_precision) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._engine is None or key != self._packed_key:
-            self._engine = FluxEngine(self.params, dict(self.named_parameters()), self.lora_scale)
+            self._engine = None                     # release the previous packing before building the next one
+            self._engine = FluxEngine(self.params, dict(self.named_parameters()), self.lora_scale, fp8=self.linear_precision == "fp8")
             self._packed_key = key
             if getattr(self, "_sp", None) is not None:
                 self._engine.enable_sequence_parallel(self._sp)
         return self._engine
+
+    def set_linear_precision(self, precision: str) -> None:
+        """"bf16" (default; the reference's numerics) or "fp8": the LayerNorm-fed projections (qkv, mlp.0, linear1 -- 58 % of the
+        step's GEMM FLOPs) run on e4m3 operands with per-row activation / per-channel weight scales.  Opt-in, NOT the reference's
+        numerics: see DESIGN.md (fp8 contract) for the measured deviation.  No counterpart in the reference."""
+        if precision not in ("bf16", "fp8"):
+            raise ValueError("linear precision must be 'bf16' or 'fp8'")
+        self.linear_precision = precision
 
     def enable_sequence_parallel(self, sp) -> None:
         """Single-image latency mode over several GPUs (``parallel.SequenceParallel``; None switches it off).  No counterpart
