@@ -413,7 +413,7 @@ def main():
             if (i[3] >> 24) & 1:                                             # launched from inside the VAE engine
                 vae_gemm_ms += r.ms; vae_gemm_fl += fl
                 continue
-            key = (i[0], i[1], i[2], i[3] & 255, (i[3] >> 8) & 255, (i[3] >> 16) & 255)
+            key = (i[0], i[1], i[2], i[3] & 255, 32 * ((i[3] >> 8) & 255), (i[3] >> 16) & 255)
             e = shapes.setdefault(key, [0, 0.0, fl])
             e[0] += 1; e[1] += r.ms
         elif r.category == 4:

@@ -38,7 +38,7 @@ int         vcb_profile_begin(void);
 int         vcb_profile_end(double ms[4], long long launches[4]);
 /* Extended form: ncat in [4, 6] categories (4 = VAE 3x3 convolutions, 5 = VAE GroupNorm / upsample / softmax / layout; with
  * ncat == 4 they fold into "other"), and optionally one record per launch in launch order.
- * info: GEMM {M, N, K, epilogue | block_n << 8 | cta_group << 16 | issued-by-the-VAE-engine << 24}; conv {output pixels, cout, 9 * cin, stride};
+ * info: GEMM {M, N, K, epilogue | (block_n / 32) << 8 | cta_group << 16 | issued-by-the-VAE-engine << 24}; conv {output pixels, cout, 9 * cin, stride};
  * attention {B, L, heads, fixed-reference softmax | persistent schedule << 1}. */
 typedef struct vcb_prof_record { int32_t category; float ms; int32_t info[4]; } vcb_prof_record;
 int         vcb_profile_end_ex(double* ms, long long* launches, int32_t ncat, vcb_prof_record* records, int64_t capacity,

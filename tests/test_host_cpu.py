@@ -349,50 +349,61 @@ def test_engine_rejects_masks_the_kernel_cannot_honour():
 
 
 def test_attention_persistent_schedule_covers_every_key_tile_exactly_once():
-    """attn4_sm100.cuh's schedule (AttnSched::boundary / AttnSegIter), restated: the per-CTA shares must tile the (unit, key tile)
-    space exactly once; a piece that does not hold key tile 0 must be its CTA's FIRST segment (it waits on nothing), a cut
-    unit's finaliser must be its CTA's LAST segment, and its contributors must be the next CTAs, contiguous up to the last key
-    tile -- the deadlock-freedom argument of the kernel rests on exactly these properties."""
-    def boundary(x, n_pairs, n_qt, n_kv, n_heads, T):
-        if x >= T:
-            return n_heads * n_pairs, 0
-        hi, r = divmod(x, n_qt * n_kv)
-        pair, rr = divmod(r, 2 * n_kv)
-        ntile = 1 if (pair == n_pairs - 1 and (n_qt & 1)) else 2
-        return hi * n_pairs + pair, rr // ntile
+    """attn4_sm100.cuh's schedule (AttnSched / AttnSegIter), restated: full rounds dealt out like the per-pair grid, the partial last
+    round cut along the key tiles into equal shares.  The shares must tile the (unit, key tile) space exactly once; a piece that
+    does not hold key tile 0 must be its CTA's FIRST phase-2 segment (it waits on nothing), a cut unit's finaliser must be its
+    CTA's LAST segment, and its contributors must be the next CTAs, contiguous up to the last key tile -- the deadlock-freedom
+    argument of the kernel rests on exactly these properties; the host-side bound on the segment list must hold."""
+    def sched(n_heads, n_qt, sms=148):
+        n_pairs, n_kv = (n_qt + 1) // 2, n_qt
+        n_units = n_heads * n_pairs
+        G = sms if n_units * n_kv // sms >= 4 else max(n_units * n_kv // 4, 1)
+        R, rem = divmod(n_units, G)
+        U = rem * n_kv
+        G2 = 0 if rem == 0 else min(G, max(U // 4, 1))
+        return n_pairs, n_kv, n_units, G, R, rem, U, G2
 
-    def segs(c, G, *s):
-        n_pairs, n_qt, n_kv, n_heads, T = s
-        (us, ks), (ue, ke) = boundary(T * c // G, *s), boundary(T * (c + 1) // G, *s)
-        out = []
-        for u in range(us, min(ue, n_heads * n_pairs - 1) + 1):
-            kv0, kv1 = (ks if u == us else 0), (ke if u == ue else n_kv)
-            if kv0 < kv1:
-                out.append((u, kv0, kv1))
+    def boundary(c, S):
+        n_pairs, n_kv, n_units, G, R, rem, U, G2 = S
+        ur, kv = divmod(U * c // G2, n_kv)
+        return R * G + ur, kv
+
+    def segs(c, S):
+        n_pairs, n_kv, n_units, G, R, rem, U, G2 = S
+        out = [(r * G + c, 0, n_kv, 1) for r in range(R)]
+        if c < G2:
+            (us, ks), (ue, ke) = boundary(c, S), boundary(c + 1, S)
+            for u in range(us, min(ue, n_units - 1) + 1):
+                kv0, kv1 = (ks if u == us else 0), (ke if u == ue else n_kv)
+                if kv0 < kv1:
+                    out.append((u, kv0, kv1, 2))
         return out
 
     for B, H, L in [(1, 24, 3968), (1, 24, 7424), (1, 24, 4608), (1, 24, 6656), (1, 24, 1088), (1, 2, 128), (1, 2, 200), (1, 2, 1088),
-                    (1, 3, 1500), (2, 2, 520), (1, 1, 640), (8, 24, 1088), (4, 24, 256), (1, 3, 3968)]:
+                    (1, 3, 1500), (2, 2, 520), (1, 1, 640), (8, 24, 1088), (4, 24, 256), (1, 3, 3968), (1, 4, 2000), (8, 24, 3968),
+                    (1, 37, 640), (1, 149, 256)]:
         n_qt = (L + 127) // 128
-        s = ((n_qt + 1) // 2, n_qt, n_qt, B * H, B * H * n_qt * n_qt)
-        T = s[4]
-        G = 148 if T // 148 >= 8 else max(T // 8, 1)
+        S = sched(B * H, n_qt)
+        n_pairs, n_kv, n_units, G, R, rem, U, G2 = S
         cover = set()
         for c in range(G):
-            sg = segs(c, G, *s)
-            assert len(sg) <= 32
-            assert B * H * s[0] // G + 3 >= len(sg), "host-side bound on the segment list"
-            for i, (u, a, b) in enumerate(sg):
+            sg = segs(c, S)
+            assert len(sg) <= n_units // G + 4 <= 64 or n_units // G + 4 > 64, "host-side bound on the segment list"
+            assert len(sg) <= n_units // G + 4
+            tail = [x for x in sg if x[3] == 2]
+            for i, (u, a, b, ph) in enumerate(tail):
+                assert b - a >= 1
                 assert a == 0 or i == 0
-                if a == 0 and b < n_qt:
-                    assert i == len(sg) - 1
+                if a == 0 and b < n_kv:
+                    assert i == len(tail) - 1
                     pos, pc = b, c + 1
-                    while pc < G and boundary(T * pc // G, *s)[0] == u:
-                        f = segs(pc, G, *s)[0]
+                    while pc < G2 and boundary(pc, S)[0] == u:
+                        f = [x for x in segs(pc, S) if x[3] == 2][0]
                         assert f[0] == u and f[1] == pos and f[1] > 0
                         pos, pc = f[2], pc + 1
-                    assert pos == n_qt
+                    assert pos == n_kv
+            for (u, a, b, ph) in sg:
                 for k in range(a, b):
                     assert (u, k) not in cover
                     cover.add((u, k))
-        assert len(cover) == B * H * s[0] * n_qt
+        assert len(cover) == n_units * n_kv, (B, H, L, len(cover), n_units * n_kv)

@@ -4,13 +4,12 @@
 // P V, two-instalment P, optional fixed-reference softmax) -- what changes is the schedule.  attn3 launches one CTA per
 // (query pair, head, sample): at cfg B that is 16 x 24 = 384 CTAs (372 pair-units of work) on 148 SMs = 2.51 waves executed as
 // 3 (84 % before anything else), and every CTA pays its own prologue (TMEM alloc, barrier init, first Q / K fetch) and drain.
-// Here the grid is min(#SMs, ...) CTAs and the flattened work
-//     x in [0, T),  T = (samples * heads) * (query tiles) * (key tiles)        [half-iterations: one query tile x one key tile]
-// is cut into equal contiguous ranges, one per CTA.  Units are ordered (sample, head, query pair) so neighbouring CTAs stream the
-// same head's K / V through L2 at about the same time.  A CTA's range is a sequence of SEGMENTS (unit, key tiles [kv0, kv1)):
+// Here the grid is min(#SMs, ...) CTAs.  Full rounds of units are dealt out exactly like the per-pair grid (same L2 behaviour, no
+// per-CTA prologue / drain between them); the units of the partial last round are cut along the key tiles into equal contiguous
+// shares (see AttnSched).  A CTA's work is a sequence of SEGMENTS (unit, key tiles [kv0, kv1)):
 //   * a segment covering all key tiles is finished locally (normalise, store);
-//   * a unit cut by a range boundary is produced by several CTAs.  The piece holding key tile 0 -- always the LAST segment of its
-//     CTA -- is the finaliser; every other piece -- always the FIRST segment of its CTA, which waits on nothing -- dumps its
+//   * a unit cut by a share boundary is produced by several CTAs.  The piece holding key tile 0 -- always the LAST segment of its
+//     CTA -- is the finaliser; every other piece -- always the FIRST phase-2 segment of its CTA, which waits on nothing -- dumps its
 //     un-normalised (O, l[, m]) to its workspace slot and raises its flag.  The finaliser folds them in its epilogue:
 //         fixed-reference softmax:  O = sum O_i, l = sum l_i            (all pieces share the reference exponent)
 //         online max:               m = max m_i, O = sum O_i 2^(m_i - m), l likewise
@@ -24,7 +23,7 @@
 
 namespace vcb {
 
-constexpr int kAttn4MaxSegs = 32;                            // segments per CTA (the host falls back to attn3 beyond that)
+constexpr int kAttn4MaxSegs = 64;                            // segments per CTA (the host falls back to attn3 beyond that)
 constexpr int kAttn4SmemBytes = kAttn3SmemBytes + 4096 + kAttn4MaxSegs * 32;   // + two more row-exchange buffers + the segment list
 constexpr int kAttn4SlotFloats = 2 * 128 * 128 + 2 * 2 * 128 + 2 * 128;   // O [2][32][128] float4 | l [2][2][128] | m [2][128]
 
@@ -34,44 +33,68 @@ struct AttnSkParams {
     int epoch;          // value that marks "this launch's partial is ready"
 };
 
+// Schedule.  Units (sample, head, query pair) in that order; n_units = samples * heads * pairs.
+//   phase 1  the R = n_units / G full rounds exactly like the one-CTA-per-pair grid: round r gives unit r * G + c to CTA c, so the CTAs
+//            that run concurrently stream the same ~G / pairs heads' K / V through L2.  (A first version cut the whole (unit, key tile)
+//            space into G contiguous ranges: every head's K / V was live at once -- 91 MB at L = 7424 -- and each key-tile step ran
+//            20 % slower than in the per-pair grid; measured 534 vs 469 us.  Same lesson as the GEMM's stream-K: split only the tail.)
+//   phase 2  the rem = n_units % G units of the partial last round are cut along the key tiles into G2 equal contiguous ranges of the
+//            flattened (unit, key tile) space, one per CTA c < G2 (G2 = min(G, steps / 4): every range holds >= 4 key-tile steps).
 struct AttnSched {
-    int n_pairs, n_qt, n_kv, n_heads;    // query pairs / query tiles / key tiles per (sample, head); samples * heads
-    long long T;
-    VCB_DEVICE void boundary(long long x, int& unit, int& kv) const {
-        if (x >= T) { unit = n_heads * n_pairs; kv = 0; return; }
-        const long long per_head = (long long)n_qt * n_kv;
-        const int hi = (int)(x / per_head);
-        const int r = (int)(x - (long long)hi * per_head);
-        const int pair = r / (2 * n_kv);
-        const int rr = r - pair * 2 * n_kv;
-        const int ntile = (pair == n_pairs - 1 && (n_qt & 1)) ? 1 : 2;
-        unit = hi * n_pairs + pair;
-        kv = rr / ntile;
+    int n_pairs, n_kv, n_units, G;
+    int R, rem, G2;
+    long long U;                                   // key-tile steps of phase 2
+    VCB_DEVICE void init(int n_heads, int n_qt, int grid) {
+        n_pairs = (n_qt + 1) / 2; n_kv = n_qt; n_units = n_heads * n_pairs; G = grid;
+        R = n_units / G; rem = n_units - R * G;
+        U = (long long)rem * n_kv;
+        const long long g2 = U / 4;
+        G2 = rem == 0 ? 0 : (int)(g2 < 1 ? 1 : (g2 < G ? g2 : G));
+    }
+    // start of CTA c's phase-2 range (c == G2: the end of the space)
+    VCB_DEVICE void boundary(int c, int& unit, int& kv) const {
+        const long long x = U * c / G2;
+        const int ur = (int)(x / n_kv);
+        unit = R * G + ur;
+        kv = (int)(x - (long long)ur * n_kv);
     }
 };
 
-struct AttnSeg { int unit, kv0, kv1; };
-// one entry of a CTA's segment list, computed once by one thread (keeps the 64-bit schedule arithmetic out of the role loops)
-struct AttnSegEntry { int b, head, q0, kv0, kv1, tile1, n_parts, unit; };
-static_assert(sizeof(AttnSegEntry) == 32, "segment entry");
+struct AttnSeg { int unit, kv0, kv1, n_parts; };
 
+// enumerates CTA c's segments: phase 1 units, then the pieces of its phase-2 range.  n_parts (for a cut unit's finaliser) = the
+// CTAs right after this one whose range starts inside the unit.
 struct AttnSegIter {
-    int u, u_s, u_e, k_s, k_e, n_kv, n_units;
-    VCB_DEVICE AttnSegIter(const AttnSched& s, int cta, int G) : n_kv(s.n_kv), n_units(s.n_heads * s.n_pairs) {
-        s.boundary(s.T * cta / G, u_s, k_s);
-        s.boundary(s.T * (cta + 1) / G, u_e, k_e);
+    const AttnSched& s;
+    int c, r, u, u_s, u_e, k_s, k_e;
+    VCB_DEVICE AttnSegIter(const AttnSched& sched, int cta) : s(sched), c(cta), r(0) {
+        if (c < s.G2) { s.boundary(c, u_s, k_s); s.boundary(c + 1, u_e, k_e); } else { u_s = 1; u_e = 0; k_s = k_e = 0; }
         u = u_s;
     }
     VCB_DEVICE bool next(AttnSeg& g) {
-        while (u <= u_e && u < n_units) {
+        if (r < s.R) { g.unit = r * s.G + c; g.kv0 = 0; g.kv1 = s.n_kv; g.n_parts = 0; ++r; return true; }
+        while (u <= u_e && u < s.n_units) {
             const int cur = u++;
             const int kv0 = (cur == u_s) ? k_s : 0;
-            const int kv1 = (cur == u_e) ? k_e : n_kv;
-            if (kv0 < kv1) { g.unit = cur; g.kv0 = kv0; g.kv1 = kv1; return true; }
+            const int kv1 = (cur == u_e) ? k_e : s.n_kv;
+            if (kv0 >= kv1) continue;
+            g.unit = cur; g.kv0 = kv0; g.kv1 = kv1; g.n_parts = 0;
+            if (kv0 == 0 && kv1 < s.n_kv) {
+                for (int pc = c + 1; pc < s.G2; ++pc) {
+                    int pu, pk;
+                    s.boundary(pc, pu, pk);
+                    if (pu != cur) break;
+                    ++g.n_parts;
+                }
+            }
+            return true;
         }
         return false;
     }
 };
+// one entry of a CTA's segment list, computed once by one thread (keeps the 64-bit schedule arithmetic out of the role loops)
+struct AttnSegEntry { int b, head, q0, kv0, kv1, tile1, n_parts, unit; };
+static_assert(sizeof(AttnSegEntry) == 32, "segment entry");
 
 // mbarrier wait with a watchdog: ~seconds of failed try_waits trap the kernel instead of hanging the GPU box
 VCB_DEVICE void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
@@ -90,12 +113,9 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     const int cta = blockIdx.x, G = gridDim.x;
     pdl_launch_dependents();
 
+    const int n_qt = (p.L + kAttnTile - 1) / kAttnTile;
     AttnSched sched;
-    sched.n_qt = (p.L + kAttnTile - 1) / kAttnTile;
-    sched.n_pairs = (sched.n_qt + 1) / 2;
-    sched.n_kv = sched.n_qt;
-    sched.n_heads = p.B * p.H;
-    sched.T = (long long)sched.n_heads * sched.n_qt * sched.n_kv;
+    sched.init(p.B * p.H, n_qt, G);
     const int n_kv_all = sched.n_kv;
     const int seqlen = p.L;
 
@@ -120,9 +140,7 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     int* n_segs_smem = reinterpret_cast<int*>(tmem_slot + 1);
 
     if (warp == 2 && lane == 0) {
-        // this CTA's segment list; n_parts = contributors a cut unit's finaliser has to fold (the CTAs right after this one whose
-        // range starts inside the unit -- ranges are never empty: the host sizes the grid so every CTA owns >= 8 half-iterations)
-        AttnSegIter it(sched, cta, G);
+        AttnSegIter it(sched, cta);
         AttnSeg g;
         int n = 0;
         while (n < kAttn4MaxSegs && it.next(g)) {
@@ -131,17 +149,8 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
             e.b = hi / p.H;
             e.head = hi - e.b * p.H;
             e.q0 = (g.unit - hi * sched.n_pairs) * 2 * kAttnTile;
-            e.kv0 = g.kv0; e.kv1 = g.kv1; e.unit = g.unit;
+            e.kv0 = g.kv0; e.kv1 = g.kv1; e.unit = g.unit; e.n_parts = g.n_parts;
             e.tile1 = (e.q0 + kAttnTile) < seqlen ? 1 : 0;
-            e.n_parts = 0;
-            if (g.kv0 == 0 && g.kv1 < n_kv_all) {
-                for (int pc = cta + 1; pc < G; ++pc) {
-                    int pu, pk0;
-                    sched.boundary(sched.T * pc / G, pu, pk0);
-                    if (pu != g.unit) break;
-                    ++e.n_parts;
-                }
-            }
             segs[n++] = e;
         }
         *n_segs_smem = n;

@@ -268,7 +268,7 @@ int gemm_dispatch(const vcb_gemm_args* a, const vcb_gemm_args* a1, void* stream)
     const bool fp8 = a->operand_dtype == VCB_DTYPE_E4M3;
     pick_tile(batch, a->rows_per_batch + (a1 ? a1->M / batch : 0), a->N, a->K, head || fp8, a->cta_group ? a->cta_group : forced_cta_group(),
               a->block_n, &cg, &bn, &rate);
-    ProfScope prof(PROF_GEMM, stream, a->M + (a1 ? a1->M : 0), a->N, a->K, a->epilogue | (bn << 8) | (cg << 16));
+    ProfScope prof(PROF_GEMM, stream, a->M + (a1 ? a1->M : 0), a->N, a->K, a->epilogue | ((bn >> 5) << 8) | (cg << 16));
     Problem g0, g1;
     if (int rc = build_problem(a, bn, cg, &g0)) return rc;
     if (a1) {
@@ -438,28 +438,18 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         }
     }
     ProfScope prof(PROF_ATTN, stream, B, L, heads, fixed ? 1 : 0);
-    static const bool sp_direct = [] { const char* e = getenv("VCB_SP_ATTN_DIRECT"); return e && atoi(e); }();
-    if (out_peers && !sp_direct) {
-        // staged TMA tile stores into the row owners' buffers (NVLink for remote owners)
-        AttnSpMapsT<true> spm{};
-        for (int r = 0; r < world; ++r)
-            if (int rc = make_tmap_2d(&spm.m[r], out_peers[r], (uint64_t)ldo, (uint64_t)rows_per_rank, (uint64_t)ldo, 64, 32)) return rc;
-        dim3 grid((L + 2 * kAttnTile - 1) / (2 * kAttnTile), heads, B);
-        cudaError_t e = fixed ? launch_pdl(attn_fwd3_tcgen05_kernel<true, 2, true>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, spm)
-                              : launch_pdl(attn_fwd3_tcgen05_kernel<true, 2>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, spm);
-        if (e != cudaSuccess) return set_error("attention (sp) launch: %s", cudaGetErrorString(e));
-        count_launch();
-        return 0;
-    }
     // Persistent schedule (attn4): unpadded batches with enough (query tile x key tile) work to give every SM a share of at
     // least a few key tiles; right-padded batches, the sequence-parallel routing and the A/B variants stay on attn3.
     const long long n_qt = (L + kAttnTile - 1) / kAttnTile;
-    const long long T = (long long)B * heads * n_qt * n_qt;
+    const long long n_units = (long long)B * heads * ((n_qt + 1) / 2), total_steps = n_units * n_qt;
     int pgrid = num_sms();
-    if (T / pgrid < 8) pgrid = (int)(T / 8 > 0 ? T / 8 : 1);           // tiny problems: fewer CTAs, >= 8 half-iterations each
-    // segments per CTA <= units per CTA + 2; beyond the kernel's list capacity (huge batches of short sequences) use attn3
-    const bool persist_ok = !seqlens && !out_peers && num_sms() <= 160 &&
-                            (long long)B * heads * ((n_qt + 1) / 2) / pgrid + 3 <= kAttn4MaxSegs;
+    if (total_steps / pgrid < 4) pgrid = (int)(total_steps / 4 > 0 ? total_steps / 4 : 1);   // tiny problems: >= 4 key-tile steps per CTA
+    // a CTA's segment list: one entry per full round + the pieces of its tail share; beyond the kernel's capacity (huge batches of
+    // short sequences) use the per-pair grid
+    // sequence-parallel routing: the persistent kernel stores O rows straight through the peer-mapped pointers (no TMA staging);
+    // opt-in with VCB_SP_ATTN_PERSIST=1 until measured on the NVLink path (few heads per rank: 48 / 96 per-pair CTAs on 148 SMs)
+    static const bool sp_persist = [] { const char* e = getenv("VCB_SP_ATTN_PERSIST"); return e && atoi(e); }();
+    const bool persist_ok = !seqlens && (!out_peers || sp_persist) && num_sms() <= 160 && n_units / pgrid + 4 <= kAttn4MaxSegs;
     if (schedule == VCB_ATTN_SCHED_PERSISTENT && !persist_ok)
         return set_error("attention: the persistent schedule takes unpadded batches (seqlens == NULL), no sequence-parallel routing");
     if (persist_ok && (schedule == VCB_ATTN_SCHED_PERSISTENT || (schedule == VCB_ATTN_SCHED_AUTO && attn_persist_mode() != 0))) {
@@ -471,6 +461,19 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         cudaError_t e = fixed ? launch_pdl(attn_fwd4_tcgen05_kernel<true>, dim3(grid), dim3(kAttn3Threads), (size_t)kAttn4SmemBytes, (cudaStream_t)stream, 1, tm, p, skp)
                               : launch_pdl(attn_fwd4_tcgen05_kernel<false>, dim3(grid), dim3(kAttn3Threads), (size_t)kAttn4SmemBytes, (cudaStream_t)stream, 1, tm, p, skp);
         if (e != cudaSuccess) return set_error("attention (persistent) launch: %s", cudaGetErrorString(e));
+        count_launch();
+        return 0;
+    }
+    static const bool sp_direct = [] { const char* e = getenv("VCB_SP_ATTN_DIRECT"); return e && atoi(e); }();
+    if (out_peers && !sp_direct) {
+        // staged TMA tile stores into the row owners' buffers (NVLink for remote owners)
+        AttnSpMapsT<true> spm{};
+        for (int r = 0; r < world; ++r)
+            if (int rc = make_tmap_2d(&spm.m[r], out_peers[r], (uint64_t)ldo, (uint64_t)rows_per_rank, (uint64_t)ldo, 64, 32)) return rc;
+        dim3 grid((L + 2 * kAttnTile - 1) / (2 * kAttnTile), heads, B);
+        cudaError_t e = fixed ? launch_pdl(attn_fwd3_tcgen05_kernel<true, 2, true>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, spm)
+                              : launch_pdl(attn_fwd3_tcgen05_kernel<true, 2>, grid, dim3(kAttn3Threads), (size_t)kAttn3SmemBytes, (cudaStream_t)stream, 1, tm, p, spm);
+        if (e != cudaSuccess) return set_error("attention (sp) launch: %s", cudaGetErrorString(e));
         count_launch();
         return 0;
     }
@@ -601,7 +604,7 @@ int ln_launch(const vcb_ln_args* a0, const vcb_ln_args* a1, int64_t ldx, int64_t
     // VCB_LN_ONEPASS=1: the round-1 kernel (row held in registers, 3 blocks per SM) for A/B; default = two-pass, 6 blocks per SM
     static const bool onepass = [] { const char* e = getenv("VCB_LN_ONEPASS"); return e && atoi(e); }();
     cudaError_t e = !onepass
-        ? launch_pdl(ln_modulate2_kernel, grid, block, (size_t)hidden * 4, (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx,
+        ? launch_pdl(ln_modulate2_kernel, grid, block, (size_t)hidden * 8, (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx,
                      (long long)ldy, (long long)mod_stride, (int)hidden, br)
         : hidden <= 12 * 256
         ? launch_pdl(ln_modulate_kernel<12, 3>, grid, block, (size_t)hidden * 4, (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx,

@@ -110,13 +110,15 @@ ln_modulate_kernel(const LnProblem p0, const LnProblem p1, long long ldx, long l
 }
 
 // Two-pass variant (default): the row is NOT kept in registers between the statistics and the modulation -- pass 2 re-reads
-// it (L1 / L2 hits: the warp has just touched those lines).  That frees ~48 registers per thread, so 6 blocks x 8 warps fit an
-// SM and 148 x 48 = 7104 warps are resident: every row of a cfg-B sequence (3968) is in flight in ONE round.  The one-pass
+// it (L1 / L2 hits: the warp has just touched those lines).  That frees ~48 registers per thread, so 5 blocks x 8 warps fit an
+// SM and 148 x 40 = 5920 warps are resident: every row of a cfg-B sequence (3968) is in flight in ONE round.  The one-pass
 // kernel above holds 3 blocks per SM = 3552 warps: 3968 rows took two rounds of which the second was 12 % full -- that, not
 // bandwidth, was its 25 us (ncu: 13.7 % DRAM throughput).  Same arithmetic in the same order: results are bit-identical.
-__global__ void __launch_bounds__(kLnWarps * 32, 6)
+__global__ void __launch_bounds__(kLnWarps * 32, 5)
 ln_modulate2_kernel(const LnProblem p0, const LnProblem p1, long long ldx, long long ldy, long long mod_stride, int H, int batch_rows) {
-    extern __shared__ uint4 ln_smem[];                 // [2][H / 8] : shift, scale of sample b0
+    // [2][H] fp32: bf16(1 + scale) and shift of sample b0, converted ONCE per block -- the per-element work of pass 2 drops from
+    // ~25 to ~13 instructions per bf16 pair (the kernel was as much issue-bound as latency-bound: 12 M elements x 12 instructions)
+    extern __shared__ float4 ln_smem4[];
     pdl_launch_dependents();
     pdl_wait();
     const bool second = (int)blockIdx.x >= p0.blocks;
@@ -124,7 +126,7 @@ ln_modulate2_kernel(const LnProblem p0, const LnProblem p1, long long ldx, long 
     const int rows = P.rows, rows_per_batch = P.rows_per_batch;
     const int row0 = ((int)blockIdx.x - (second ? p0.blocks : 0)) * kLnWarps;
     const int b0 = row0 / rows_per_batch;
-    const int nvec = H >> 3;
+    const int nvec = H >> 3;                       // 8-element groups per row
     const int row = row0 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int nchunks = H >> 8;                    // H % 256 == 0
@@ -147,9 +149,17 @@ ln_modulate2_kernel(const LnProblem p0, const LnProblem p1, long long ldx, long 
             }
         }
     }
-    for (int i = threadIdx.x; i < 2 * nvec; i += blockDim.x) {
-        const __nv_bfloat16* src = (i < nvec ? P.shift : P.scale) + (long long)b0 * mod_stride;
-        ln_smem[i] = __ldg(reinterpret_cast<const uint4*>(src) + (i < nvec ? i : i - nvec));
+    // group i (8 elements) of the modulation row -> four float4 planes (consecutive lanes read consecutive float4: no bank conflicts):
+    // a = bf16(1 + scale) (a bf16 op in the reference) elements 0-3 at [i], 4-7 at [nvec + i]; shift at [2 nvec + i], [3 nvec + i]
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const uint4 su = __ldg(reinterpret_cast<const uint4*>(P.scale + (long long)b0 * mod_stride) + i);
+        const uint4 hu = __ldg(reinterpret_cast<const uint4*>(P.shift + (long long)b0 * mod_stride) + i);
+        const float2 s0 = unpack_bf16x2(su.x), s1 = unpack_bf16x2(su.y), s2 = unpack_bf16x2(su.z), s3 = unpack_bf16x2(su.w);
+        const float2 h0 = unpack_bf16x2(hu.x), h1 = unpack_bf16x2(hu.y), h2 = unpack_bf16x2(hu.z), h3 = unpack_bf16x2(hu.w);
+        ln_smem4[i] = make_float4(bf16_round(1.0f + s0.x), bf16_round(1.0f + s0.y), bf16_round(1.0f + s1.x), bf16_round(1.0f + s1.y));
+        ln_smem4[nvec + i] = make_float4(bf16_round(1.0f + s2.x), bf16_round(1.0f + s2.y), bf16_round(1.0f + s3.x), bf16_round(1.0f + s3.y));
+        ln_smem4[2 * nvec + i] = make_float4(h0.x, h0.y, h1.x, h1.y);
+        ln_smem4[3 * nvec + i] = make_float4(h2.x, h2.y, h3.x, h3.y);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -166,25 +176,33 @@ ln_modulate2_kernel(const LnProblem p0, const LnProblem p1, long long ldx, long 
     const uint4* sc_g = reinterpret_cast<const uint4*>(P.scale + (long long)b * mod_stride);
     uint4* yr = reinterpret_cast<uint4*>(P.y + prow * ldy) + lane;
     // pass 2: re-read, modulate, write
-#pragma unroll 4
+#pragma unroll 2
     for (int c = 0; c < nchunks; ++c) {
         const int vi = c * 32 + lane;
         const uint4 xv = xr[c * 32];
-        const uint4 hu = staged ? ln_smem[vi] : __ldg(sh_g + vi);
-        const uint4 su = staged ? ln_smem[nvec + vi] : __ldg(sc_g + vi);
-        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-        const uint32_t sw[4] = {su.x, su.y, su.z, su.w};
-        const uint32_t hw[4] = {hu.x, hu.y, hu.z, hu.w};
-        uint32_t ow[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float2 xf = unpack_bf16x2(xw[e]);
-            float2 s2 = unpack_bf16x2(sw[e]);
-            float2 h2 = unpack_bf16x2(hw[e]);
-            float a0 = bf16_round(1.0f + s2.x), a1 = bf16_round(1.0f + s2.y);
-            float n0 = (xf.x - mean) * rstd, n1 = (xf.y - mean) * rstd;
-            ow[e] = pack_bf16x2(__fadd_rn(__fmul_rn(a0, n0), h2.x), __fadd_rn(__fmul_rn(a1, n1), h2.y));
+        float4 a0, a1, h0, h1;
+        if (staged) {
+            a0 = ln_smem4[vi]; a1 = ln_smem4[nvec + vi]; h0 = ln_smem4[2 * nvec + vi]; h1 = ln_smem4[3 * nvec + vi];
+        } else {                                    // a block straddling two samples: this row's vectors straight from global
+            const uint4 su = __ldg(sc_g + vi), hu = __ldg(sh_g + vi);
+            const float2 s0 = unpack_bf16x2(su.x), s1 = unpack_bf16x2(su.y), s2 = unpack_bf16x2(su.z), s3 = unpack_bf16x2(su.w);
+            const float2 g0 = unpack_bf16x2(hu.x), g1 = unpack_bf16x2(hu.y), g2 = unpack_bf16x2(hu.z), g3 = unpack_bf16x2(hu.w);
+            a0 = make_float4(bf16_round(1.0f + s0.x), bf16_round(1.0f + s0.y), bf16_round(1.0f + s1.x), bf16_round(1.0f + s1.y));
+            a1 = make_float4(bf16_round(1.0f + s2.x), bf16_round(1.0f + s2.y), bf16_round(1.0f + s3.x), bf16_round(1.0f + s3.y));
+            h0 = make_float4(g0.x, g0.y, g1.x, g1.y);
+            h1 = make_float4(g2.x, g2.y, g3.x, g3.y);
         }
+        // the product and the sum are separate fp32 operations (LayerNorm returns fp32, then (1 + scale) * ln + shift)
+        auto mod2 = [&](uint32_t xw, float ax, float ay, float hx, float hy) {
+            const float2 xf = unpack_bf16x2(xw);
+            const float n0 = (xf.x - mean) * rstd, n1 = (xf.y - mean) * rstd;
+            return pack_bf16x2(__fadd_rn(__fmul_rn(ax, n0), hx), __fadd_rn(__fmul_rn(ay, n1), hy));
+        };
+        uint32_t ow[4];
+        ow[0] = mod2(xv.x, a0.x, a0.y, h0.x, h0.y);
+        ow[1] = mod2(xv.y, a0.z, a0.w, h0.z, h0.w);
+        ow[2] = mod2(xv.z, a1.x, a1.y, h1.x, h1.y);
+        ow[3] = mod2(xv.w, a1.z, a1.w, h1.z, h1.w);
         yr[c * 32] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
 }

@@ -39,7 +39,7 @@ inline int check_launch(const char* what) {
 
 // ---- optional per-category device timing (bench.py roofline numbers): CUDA events around every launch ------------
 enum ProfCat : int { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_OTHER = 3, PROF_CONV = 4, PROF_VAE_EW = 5, PROF_NCAT = 6 };
-// info: what was launched -- GEMM {M, N, K, epilogue | block_n << 8 | cta_group << 16}, conv {pixels, cout, 9 cin, stride},
+// info: what was launched -- GEMM {M, N, K, epilogue | (block_n / 32) << 8 | cta_group << 16 | VAE context << 24}, conv {pixels, cout, 9 cin, stride},
 // attention {B, L, heads, fixed-reference softmax | persistent << 1}, others zero
 struct ProfRec { int cat; cudaEvent_t a, b; int info[4]; };
 struct Profiler {
