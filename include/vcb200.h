@@ -133,8 +133,9 @@ int vcb_attention_fwd_sp(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t
  * after QK-RMSNorm: |q| <= max|q_scale| * sqrt(128), layers.py:63-84): softmax is shift invariant, so the kernel then uses
  * exp2(s - bound) with no running row max -- same result up to rounding, shorter dependency chain.  Must be <= 64 (fp32 /
  * bf16 exponent range); 0 = exact online softmax.  out_peers != NULL selects the sequence-parallel output routing.
- * schedule: AUTO picks the persistent kernel (one CTA per SM, equal contiguous shares of the (query tile x key tile) space,
- * units cut at a share boundary are folded from fp32 partials) for unpadded batches, else one CTA per query pair. */
+ * schedule: PER_PAIR = one CTA per (256-query pair, head, sample); PERSISTENT = one CTA per SM, full rounds dealt like the per-pair
+ * grid and the partial last round cut along the key tiles (cut units are folded from fp32 partials; unpadded batches only);
+ * AUTO = PER_PAIR unless the environment sets VCB_ATTN_PERSIST=1 (measured: faster alone, equal inside the power-capped loop). */
 #define VCB_ATTN_SCHED_AUTO 0
 #define VCB_ATTN_SCHED_PER_PAIR 1
 #define VCB_ATTN_SCHED_PERSISTENT 2

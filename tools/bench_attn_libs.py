@@ -33,6 +33,22 @@ def timeit(fn, iters=15, warm=3):
     return ts[len(ts) // 2]
 
 
+def sustained(fn, seconds=0.5):
+    """back-to-back launches for `seconds`: the power-capped steady state the denoising loop runs in (no flush: K / V of one
+    24-head call are 48 - 91 MB and the launches follow each other like the 57 attention calls of an evaluation do)"""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); fn(); b.record(); torch.cuda.synchronize()
+    n = max(10, int(seconds * 1e3 / max(a.elapsed_time(b), 1e-3)))
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
 def main():
     heads, H = 24, 3072
     rows = []
@@ -48,28 +64,35 @@ def main():
         rec = {"L": L, "heads": heads, "flops": fl}
         for sched, sname in ((1, "per_pair"), (2, "persistent")):
             for sb, bname in ((0.0, "exact"), (bound, "bounded")):
-                ms = timeit(lambda: ops.attention(qkv, 1, L, heads, out, q_col=0, k_col=H, v_col=2 * H, score_bound_log2=sb, schedule=sched))
-                rec[f"vcb_{sname}_{bname}"] = {"us": ms * 1e3, "tflops": fl / ms / 1e9}
+                f = lambda: ops.attention(qkv, 1, L, heads, out, q_col=0, k_col=H, v_col=2 * H, score_bound_log2=sb, schedule=sched)
+                ms = timeit(f)
+                ms_s = sustained(f)
+                rec[f"vcb_{sname}_{bname}"] = {"us": ms * 1e3, "tflops": fl / ms / 1e9, "sustained_us": ms_s * 1e3, "sustained_tflops": fl / ms_s / 1e9}
         q, k, v = (qkv[:, i * H:(i + 1) * H].reshape(1, L, heads, 128) for i in range(3))
         qt, kt, vt = (t.transpose(1, 2).contiguous() for t in (q, k, v))
         try:
             from torch.nn.attention import SDPBackend, sdpa_kernel
             with sdpa_kernel(SDPBackend.CUDNN_ATTENTION):
-                ms = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt))
-            rec["cudnn_sdpa"] = {"us": ms * 1e3, "tflops": fl / ms / 1e9}
+                f = lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt)
+                ms = timeit(f)
+                ms_s = sustained(f)
+            rec["cudnn_sdpa"] = {"us": ms * 1e3, "tflops": fl / ms / 1e9, "sustained_us": ms_s * 1e3, "sustained_tflops": fl / ms_s / 1e9}
         except Exception as e:  # noqa: BLE001
             rec["cudnn_sdpa"] = {"error": str(e)[:200]}
         try:
             from flash_attn import flash_attn_func
             qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
-            ms = timeit(lambda: flash_attn_func(qc, kc, vc))
-            rec["flash_attn2"] = {"us": ms * 1e3, "tflops": fl / ms / 1e9}
+            f = lambda: flash_attn_func(qc, kc, vc)
+            ms = timeit(f)
+            ms_s = sustained(f, 0.3)
+            rec["flash_attn2"] = {"us": ms * 1e3, "tflops": fl / ms / 1e9, "sustained_us": ms_s * 1e3, "sustained_tflops": fl / ms_s / 1e9}
         except Exception as e:  # noqa: BLE001
             rec["flash_attn2"] = {"error": str(e)[:200]}
         print(json.dumps(rec), flush=True)
         rows.append(rec)
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump({"gpu": torch.cuda.get_device_name(0), "method": "CUDA events per launch, 256 MiB L2 flush between launches, median of 15",
+    json.dump({"gpu": torch.cuda.get_device_name(0), "method": "us / tflops: CUDA events per launch, 256 MiB L2 flush between launches, median of 15 (burst clocks); "
+               "sustained_*: back-to-back launches for 0.5 s, CUDA events around the run (power-capped steady state, as in the denoising loop)",
                "rows": rows}, open("gpurun_out/attn_vs_libs.json", "w"), indent=1)
 
 

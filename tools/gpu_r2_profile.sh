@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# round-2 ncu evidence (one GPU; never a number taken from these runs is a bench value):
+#  (1) launch list of prepare + 2 evaluations of cfg B, (2) one --set full capture per hot kernel at its cfg-B shape
+mkdir -p gpurun_out
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r2_launches.csv python tools/time_full.py 3 > gpurun_out/r2_launches.log 2>&1
+cap() {  # name, kernel regex
+  ncu --set full --clock-control none --import-source on -k "regex:$2" -s 1 -c 1 -f -o "gpurun_out/r2_prof_$1" python tools/ncu_targets.py "$1" > "gpurun_out/r2_ncu_$1.log" 2>&1
+  tail -2 "gpurun_out/r2_ncu_$1.log"
+}
+cap ln ln_modulate2
+cap attn_pair attn_fwd3
+cap attn_pair_exact attn_fwd3
+cap attn_persistent attn_fwd4
+cap gemm_linear1 gemm_bf16_tcgen05
+cap gemm_linear2 gemm_bf16_tcgen05
+cap gemm_fp8_linear1 gemm_bf16_tcgen05
+cap conv512 gemm_bf16_tcgen05
+cap conv256 gemm_bf16_tcgen05
+cap conv128 gemm_bf16_tcgen05
+ls -la gpurun_out/r2_prof_*.ncu-rep

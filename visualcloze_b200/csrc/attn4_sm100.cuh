@@ -104,8 +104,10 @@ VCB_DEVICE void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// 576 threads: __launch_bounds__(576, 1) makes ptxas budget for 640 (96 registers, a handful of spills on the S -> P critical path);
+// 18 warps x 32 x 104 registers = 59 904 of the SM's 65 536 fit, so the cap is stated directly.
 template <bool kFixed>
-__global__ void __launch_bounds__(kAttn3Threads, 1)
+__global__ void __maxnreg__(104)
 attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p, const AttnSkParams skp) {
     constexpr int kPC = 2, kCW = 32;
     const uint32_t warp = warp_id_uniform();
@@ -212,8 +214,8 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
         constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);
         int base = 0;
-        int steps[2] = {0, 0};              // running key-tile steps per query tile (parity of s_full / p_full / o_done)
-        int segc[2] = {0, 0};               // segments in which the tile was active (parity of o_free)
+        int steps0 = 0, steps1 = 0;         // running key-tile steps per query tile (parity of s_full / p_full / o_done)
+        int segc0 = 0, segc1 = 0;           // segments in which the tile was active (parity of o_free)
         auto slot_of = [](int seq) { return seq % kAttn3Slots; };
         auto wait_kv = [&](int seq) {
             mbar_wait_wd(&kv_full[slot_of(seq)], (uint32_t)(seq / kAttn3Slots) & 1u);
@@ -232,10 +234,10 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
             }
             __syncwarp();
         };
-        auto issue_pv = [&](int t, int seq, bool first) {      // O_t (+)= P_t V, V in ring entry `seq`; first: overwrite O_t
+        auto issue_pv = [&](int t, int seq, bool first, int& steps) {   // O_t (+)= P_t V, V in ring entry `seq`; first: overwrite O_t
             const uint32_t va = smem_u32(smem_kv + slot_of(seq) * kSlotBytes);
             const uint64_t vd = make_smem_desc(va, kSlotBytes / 2, 1024, kSwizzle128B);
-            const uint32_t par = (uint32_t)steps[t] & 1u;
+            const uint32_t par = (uint32_t)steps & 1u;
 #pragma unroll
             for (int c = 0; c < kPC; ++c) {
                 mbar_wait_wd(&p_full[kPC * t + c], par);
@@ -252,7 +254,7 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 }
                 __syncwarp();
             }
-            ++steps[t];
+            ++steps;
         };
         for (int segn = 0; segn < n_segs; ++segn) {
             const AttnSegEntry g = segs[segn];
@@ -272,12 +274,12 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 const bool more = (jj + 1) < n;
                 const int ev = base + 2 * jj + 1, ek = base + 2 * jj + 2;
                 wait_kv(ev);                                      // V
-                if (jj == 0 && segc[0] > 0) { mbar_wait_wd(&o_free[0], (uint32_t)(segc[0] - 1) & 1u); tc_fence_after(); }
-                issue_pv(0, ev, jj == 0);
+                if (jj == 0 && segc0 > 0) { mbar_wait_wd(&o_free[0], (uint32_t)(segc0 - 1) & 1u); tc_fence_after(); }
+                issue_pv(0, ev, jj == 0, steps0);
                 if (more) { wait_kv(ek); issue_qk(0, ek); }
                 if (tile1) {
-                    if (jj == 0 && segc[1] > 0) { mbar_wait_wd(&o_free[1], (uint32_t)(segc[1] - 1) & 1u); tc_fence_after(); }
-                    issue_pv(1, ev, jj == 0);
+                    if (jj == 0 && segc1 > 0) { mbar_wait_wd(&o_free[1], (uint32_t)(segc1 - 1) & 1u); tc_fence_after(); }
+                    issue_pv(1, ev, jj == 0, steps1);
                 }
                 if (elect_one()) umma_commit<1>(&kv_empty[slot_of(ev)]);      // V free once both PVs have run
                 __syncwarp();
@@ -291,8 +293,8 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 }
             }
             base += 2 * n;
-            ++segc[0];
-            if (tile1) ++segc[1];
+            ++segc0;
+            if (tile1) ++segc1;
         }
         __syncwarp();
     } else {
@@ -306,21 +308,17 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         const uint32_t p_addr = s_addr;                           // packed P overlays the start of my own score columns
         const uint32_t o_addr = tmem_base + lane_addr + 256 + t * 128 + half * 64;
         const uint32_t bar_id = 1 + t * 4 + quarter;              // named barrier of this warp pair (64 threads)
-        float* my_slot = skp.ws + (long long)cta * kAttn4SlotFloats;
         const float sc = p.scale_log2;
         int step = 0, segc = 0;                                   // running key-tile steps / active segments of MY tile
         for (int segn = 0; segn < n_segs; ++segn) {
-            const AttnSegEntry g = segs[segn];
-            const int b = g.b, head = g.head, q0 = g.q0;
-            const bool tile1 = g.tile1 != 0;
-            const bool contributor = g.kv0 > 0;                   // not the piece holding key tile 0: dump partials
-            const bool finaliser_partial = !contributor && g.kv1 < n_kv_all;
-            const bool active = (t == 0) || tile1;
-            const int row = q0 + t * kAttnTile + rit;
+            // only the loop bounds stay live across the key-tile loop; the epilogue re-reads the entry from shared memory
+            const int kv0 = segs[segn].kv0, kv1 = segs[segn].kv1;
+            const bool contributor = kv0 > 0;                     // not the piece holding key tile 0: dump partials
+            const bool active = (t == 0) || segs[segn].tile1 != 0;
             if (active) {
                 [[maybe_unused]] float m_run = -INFINITY;
                 float l_run = 0.f;
-                for (int j = g.kv0; j < g.kv1; ++j, ++step) {
+                for (int j = kv0; j < kv1; ++j, ++step) {
                     mbar_wait_wd(&s_full[t], (uint32_t)step & 1u);
                     tc_fence_after();
                     const int kv_left = seqlen - j * kAttnTile - half * 64;     // my columns >= kv_left are padding
@@ -347,7 +345,7 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                         const bool grow = (m_tile - m_run) > kRescaleThreshold;
                         m_new = grow ? m_tile : m_run;
                         const float alpha = grow ? ex2_approx(m_run - m_new) : 1.0f;
-                        if (j > g.kv0 && __any_sync(0xffffffffu, grow)) {
+                        if (j > kv0 && __any_sync(0xffffffffu, grow)) {
                             mbar_wait_wd(&o_done[t], (uint32_t)(step - 1) & 1u);
                             tc_fence_after();
 #pragma unroll 1
@@ -403,6 +401,11 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 // ---------------- segment epilogue ----------------
                 mbar_wait_wd(&o_done[t], (uint32_t)(step - 1) & 1u);
                 tc_fence_after();
+                const AttnSegEntry g = segs[segn];
+                const int b = g.b, head = g.head;
+                const int row = g.q0 + t * kAttnTile + rit;
+                const bool finaliser_partial = !contributor && kv1 < n_kv_all;
+                float* my_slot = skp.ws + (long long)cta * kAttn4SlotFloats;
                 if (contributor) {
                     // un-normalised O (fp32), my half's row sum and the row's reference exponent -> my workspace slot.
                     // O layout [tile][column quad][row]: the lanes of a warp (consecutive rows) write consecutive 16-byte words

@@ -386,9 +386,13 @@ inline AttnScratch* attn_scratch(cudaStream_t st) {
     }
     return &s;
 }
-// VCB_ATTN_PERSIST: unset = auto (persistent kernel whenever it applies), 0 = never (one CTA per query pair, attn3), 1 = same as auto
+// What VCB_ATTN_SCHED_AUTO resolves to.  Default: one CTA per query pair (attn3).  Measured on B200 (profiles/r02_attn_vs_libs.json,
+// r02_summary.md): timed alone (burst clocks) the per-pair grid is 8 - 20 % FASTER than the persistent kernel although it
+// executes 2.59 waves as 3; inside the denoising loop the two take the same time to the cycle (attention_ms x SM MHz equal within
+// 0.3 % for three schedules) -- the chip sits at its ~1 kW power cap there, idle SMs of a partial wave hand their budget to the
+// busy ones, and what is left to win is energy per FLOP, not occupancy.  VCB_ATTN_PERSIST=1 makes AUTO pick the persistent kernel.
 inline int attn_persist_mode() {
-    static const int m = [] { const char* e = getenv("VCB_ATTN_PERSIST"); return e ? (atoi(e) ? 1 : 0) : -1; }();
+    static const int m = [] { const char* e = getenv("VCB_ATTN_PERSIST"); return (e && atoi(e)) ? 1 : 0; }();
     return m;
 }
 

@@ -297,7 +297,8 @@ ln_modulate_fp8_kernel(const LnFp8Problem p0, const LnFp8Problem p1, long long l
                 float n0 = (xf.x - mean) * rstd, n1 = (xf.y - mean) * rstd;
                 const float y0 = __fadd_rn(__fmul_rn(a0, n0), h2.x), y1 = __fadd_rn(__fmul_rn(a1, n1), h2.y);
                 ow[e] = pack_bf16x2(y0, y1);
-                amax = fmaxf(amax, fmaxf(fabsf(y0), fabsf(y1)));
+                const float2 yr2 = unpack_bf16x2(ow[e]);                 // the scale refers to the bf16 values that get quantised
+                amax = fmaxf(amax, fmaxf(fabsf(yr2.x), fabsf(yr2.y)));
             }
             v[c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
