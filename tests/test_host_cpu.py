@@ -407,3 +407,37 @@ def test_attention_persistent_schedule_covers_every_key_tile_exactly_once():
                     assert (u, k) not in cover
                     cover.add((u, k))
         assert len(cover) == n_units * n_kv, (B, H, L, len(cover), n_units * n_kv)
+
+
+def test_diffusers_style_adapter_maps_the_documented_call():
+    """README.md:141-205 of the reference documents the diffusers ``VisualClozePipeline`` call; the adapter must turn it into the
+    reference entry's arguments (grid size, three prompts, seed from the generator, SDEdit switch) and wrap the result like
+    ``.images[0][0]``."""
+    from PIL import Image
+    from visualcloze_b200.diffusers_adapter import VisualClozePipelineAdapter, layout_prompt
+
+    class Fake:
+        max_length = 512
+
+        def set_grid_size(self, h, w):
+            self.grid = (h, w)
+
+        def process_images(self, images, prompts, **kw):
+            self.call = dict(images=images, prompts=prompts, **kw)
+            return [Image.new("RGB", (64, 64))]
+
+    im = Image.new("RGB", (32, 32))
+    fake = Fake()
+    pipe = VisualClozePipelineAdapter(fake)
+    out = pipe(task_prompt="do the task", content_prompt=None, image=[[im, im, im], [im, im, None]], upsampling_height=160,
+               upsampling_width=128, upsampling_strength=0.3, guidance_scale=30, num_inference_steps=30, max_sequence_length=512,
+               generator=torch.Generator("cpu").manual_seed(7))
+    assert fake.grid == (2, 3) and fake.call["seed"] == 7 and fake.call["cfg"] == 30 and fake.call["steps"] == 30
+    assert fake.call["prompts"] == [layout_prompt(2, 3), "do the task", ""] and fake.call["is_upsampling"] is True
+    assert abs(fake.call["upsampling_noise"] - 0.3) < 1e-9 and fake.call["images"][1][2] is None
+    assert out.images[0][0].size == (128, 160)
+    assert layout_prompt(2, 3) == "A grid layout with 2 rows and 3 columns, displaying 6 images arranged side by side."
+    pipe(task_prompt="t", content_prompt="c", image=[[im, None]], upsampling_strength=1.0)
+    assert fake.call["is_upsampling"] is False and fake.grid == (1, 2)
+    with pytest.raises(ValueError, match="in-context"):
+        pipe(task_prompt="t", content_prompt="c", image=[[im, None], [im, None]])

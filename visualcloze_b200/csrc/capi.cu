@@ -141,7 +141,7 @@ int forced_cta_group() {
 }
 
 // Tile selection.  Cost of a configuration = (tiles per CTA slot, rounded up) x (tile width) / (measured per-SM
-// rate of that configuration, TFLOP/s on B200 at full waves: profiles/r01_gemm_configs.md).  cta_group 2 pairs two
+// rate of that configuration, TFLOP/s on B200 at full waves, from tools/bench_kernels.py runs of round 1).  cta_group 2 pairs two
 // SMs on a 256 x BLOCK_N tile, halving B-operand smem traffic; narrow tiles win when they remove a partial wave.
 struct TileCfg { int cg, bn; float rate; };
 constexpr TileCfg kTileCfgs[] = {{2, 256, 1630.f}, {1, 256, 1445.f}, {1, 192, 1355.f}, {2, 192, 1250.f},
