@@ -6,6 +6,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-fi
 cap() {  # name, kernel regex
   ncu --set full --clock-control none --import-source on -k "regex:$2" -s 1 -c 1 -f -o "gpurun_out/r2_prof_$1" python tools/ncu_targets.py "$1" > "gpurun_out/r2_ncu_$1.log" 2>&1
   tail -2 "gpurun_out/r2_ncu_$1.log"
+  # the .ncu-rep files are ~16 MB each and gpurun_out/ is capped at 64 MiB: keep the raw-page CSV (all metrics of the launch)
+  if [ -f "gpurun_out/r2_prof_$1.ncu-rep" ]; then
+    ncu -i "gpurun_out/r2_prof_$1.ncu-rep" --page raw --csv > "gpurun_out/r2_prof_$1.raw.csv" 2>/dev/null
+    rm -f "gpurun_out/r2_prof_$1.ncu-rep"
+  fi
 }
 cap ln ln_modulate2
 cap attn_pair attn_fwd3
@@ -17,4 +22,4 @@ cap gemm_fp8_linear1 gemm_bf16_tcgen05
 cap conv512 gemm_bf16_tcgen05
 cap conv256 gemm_bf16_tcgen05
 cap conv128 gemm_bf16_tcgen05
-ls -la gpurun_out/r2_prof_*.ncu-rep
+ls -la gpurun_out/r2_prof_*.raw.csv

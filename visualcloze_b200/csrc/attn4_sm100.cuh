@@ -104,10 +104,11 @@ VCB_DEVICE void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// 576 threads: __launch_bounds__(576, 1) makes ptxas budget for 640 (96 registers, a handful of spills on the S -> P critical path);
-// 18 warps x 32 x 104 registers = 59 904 of the SM's 65 536 fit, so the cap is stated directly.
+// 576 threads: registers are allocated in units of 4 warps, so 18 warps cost as much as 20 and the cap is 96 per thread (a
+// __maxnreg__(104) build compiled but could not be launched).  The few spills ptxas reports sit on the per-segment path, not in
+// the key-tile loop.
 template <bool kFixed>
-__global__ void __maxnreg__(104)
+__global__ void __launch_bounds__(kAttn3Threads, 1)
 attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p, const AttnSkParams skp) {
     constexpr int kPC = 2, kCW = 32;
     const uint32_t warp = warp_id_uniform();
