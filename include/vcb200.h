@@ -89,6 +89,10 @@ typedef struct vcb_gemm_args {
        `out` is then unused for the q/k/v columns. */
     int32_t sp_world, sp_row_offset;
     void* sp_out[VCB_SP_MAX];
+    /* VCB_EPI_GATE_RES, optional: row_stats [output rows][N / 64] float2 -- per row and per 64 output columns the (sum, sum of
+       squares) of the bf16 values this GEMM stores, i.e. the statistics the AdaLN LayerNorm that follows needs
+       (vcb_ln_modulate_stats); N % 64 == 0, plain matrices, block_n 128 or 256.  NULL = not produced. */
+    void* row_stats;
     /* FP8 operands (opt-in; VCB_EPI_BIAS / BIAS_GELU / QKV / LINEAR1, plain matrices): operand_dtype = VCB_DTYPE_E4M3 makes A
        and W e4m3 bytes (lda / ldw / a_batch_stride in elements = bytes, multiples of 16), multiplied on the tensor cores with
        tcgen05.mma kind::f8f6f4; the fp32 accumulator is rescaled by a_scale[mapped OUTPUT row] * w_scale[column] before the
@@ -162,6 +166,12 @@ int vcb_ln_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, const void
 typedef struct vcb_ln_args { const void* x; void* y; const void* shift; const void* scale; int32_t rows, rows_per_batch; } vcb_ln_args;
 int vcb_ln_modulate_grouped(const vcb_ln_args* a0, const vcb_ln_args* a1, int64_t ldx, int64_t ldy, int64_t mod_stride,
                             int32_t hidden, int32_t batch_rows, void* stream);
+
+/* Statistics supplied by the producer: stats0 / stats1 [rows of the problem][n_slots] float2 as written by the row_stats member of
+ * the VCB_EPI_GATE_RES GEMM that produced x (positioned at the problem's first row); the kernel adds a row's n_slots pairs in a
+ * fixed order and streams the row once.  One or two problems per launch (a1 / stats1 may be NULL). */
+int vcb_ln_modulate_stats(const vcb_ln_args* a0, const vcb_ln_args* a1, const void* stats0, const void* stats1, int32_t n_slots,
+                          int64_t ldx, int64_t ldy, int64_t mod_stride, int32_t hidden, int32_t batch_rows, void* stream);
 
 /* FP8 form (opt-in fp8 projections): same LayerNorm + modulation, but the output row is e4m3 bytes (y8 [*, ld8], bytes) with one
  * fp32 scale per row, row_scale[physical row] = max|y| / 448 -- the a_scale of the fp8 GEMM that consumes it.  One or two

@@ -576,3 +576,53 @@ def test_attention_persistent_rejects_padded_batches(ops):
     sl = torch.tensor([256, 100], dtype=torch.int32, device="cuda")
     with pytest.raises(Exception, match="persistent"):
         ops.attention(qkv, 2, 256, 2, torch.empty(512, 256, dtype=BF16, device="cuda"), q_col=0, k_col=256, v_col=512, seqlens=sl, schedule=2)
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm statistics produced by the GATE_RES epilogue (row_stats) and consumed by vcb_ln_modulate_stats
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [(256, 2), (256, 1), (128, 1), (128, 2), (0, 0)])
+def test_gate_res_row_stats_and_stats_layernorm(ops, cfg):
+    """x += gate * (a w^T + b) with row_stats: per row and per 64 columns (sum, sum of squares) of the bf16 values written; the
+    LayerNorm fed with them must equal the two-pass LayerNorm kernel on the same x (statistics differ only in fp32 summation
+    order) -- grouped img + txt problems, row-mapped output like a DoubleStreamBlock's proj launch."""
+    bn, cg = cfg
+    g = torch.Generator().manual_seed(13)
+    K, N, Li, Lt = 512, 768, 450, 70
+    L = Li + Lt
+    a = torch.randn(L, K, generator=g).to(BF16).cuda()
+    x0 = torch.randn(L, N, generator=g).to(BF16)
+    x = x0.clone().cuda()
+    stats = torch.full((L, N // 64, 2), -7.0, dtype=torch.float32, device="cuda")
+    probs = []
+    for off, rows in ((Lt, Li), (0, Lt)):
+        w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(BF16).cuda()
+        bias = torch.randn(N, generator=g).cuda()
+        gate = (0.5 * torch.randn(1, N, generator=g)).to(BF16).cuda()
+        probs.append(dict(a=a[off:off + rows], w=w, bias=bias, out=x, epilogue=ops.EPI_GATE_RES, gate=gate, res=x, rows_per_batch=rows,
+                          out_batch_rows=L, out_row_offset=off, row_stats=stats, block_n=bn, cta_group=cg))
+    ops.gemm_grouped(probs[0], probs[1])
+    torch.cuda.synchronize()
+    xf = x.float().reshape(L, N // 64, 64)
+    ref = torch.stack((xf.sum(-1), (xf * xf).sum(-1)), dim=-1)
+    assert torch.allclose(stats, ref, rtol=2e-5, atol=2e-4), float((stats - ref).abs().max())
+    shift = (0.2 * torch.randn(1, N, generator=g)).to(BF16).cuda()
+    scale = (0.3 * torch.randn(1, N, generator=g)).to(BF16).cuda()
+    y_two = torch.empty(L, N, dtype=BF16, device="cuda")
+    y_st = torch.empty(L, N, dtype=BF16, device="cuda")
+    ops.ln_modulate(x, shift, scale, y_two, rows_per_batch=L)
+    ops.ln_modulate_stats(x, shift, scale, y_st, stats, rows_per_batch=L)
+    torch.cuda.synchronize()
+    assert rel_l2(y_st.cpu(), y_two.cpu()) < 2e-3
+    assert float((y_st.float() - y_two.float()).abs().max()) <= 0.0625       # a few bf16 ulps at |y| <= ~8 where the fp32 statistics round differently
+
+
+def test_row_stats_rejected_where_it_cannot_work(ops):
+    a = torch.zeros(128, 256, dtype=BF16, device="cuda")
+    w = torch.zeros(128, 256, dtype=BF16, device="cuda")
+    out = torch.zeros(128, 128, dtype=BF16, device="cuda")
+    st = torch.zeros(128, 2, 2, device="cuda")
+    with pytest.raises(Exception, match="row_stats"):
+        ops.gemm(a, w, None, out, row_stats=st)                                  # not the GATE_RES epilogue
+    with pytest.raises(Exception, match="row_stats"):
+        ops.gemm(a, w, None, out, epilogue=ops.EPI_GATE_RES, res=out, gate=torch.zeros(1, 128, dtype=BF16, device="cuda"), row_stats=st, block_n=192)

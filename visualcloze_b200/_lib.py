@@ -35,6 +35,7 @@ class GemmArgs(C.Structure):
         ("out2", C.c_void_p), ("ldo2", C.c_int64), ("out2_col_offset", C.c_int32),
         ("block_n", C.c_int32), ("cta_group", C.c_int32),
         ("sp_world", C.c_int32), ("sp_row_offset", C.c_int32), ("sp_out", C.c_void_p * SP_MAX),
+        ("row_stats", C.c_void_p),
         ("operand_dtype", C.c_int32), ("a_scale", C.c_void_p), ("w_scale", C.c_void_p),
     ]
 
@@ -192,6 +193,8 @@ _OPTIONAL: dict = {
     "vcb_attention_fwd_ex": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
     "vcb_ln_modulate_grouped": (C.c_int, [C.POINTER(LnArgs), C.POINTER(LnArgs), C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                           C.c_int32, C.c_void_p]),
+    "vcb_ln_modulate_stats": (C.c_int, [C.POINTER(LnArgs), C.POINTER(LnArgs), C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
+                                        C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "vcb_ln_modulate_fp8": (C.c_int, [C.POINTER(LnArgs), C.POINTER(LnArgs), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                       C.c_int32, C.c_int32, C.c_void_p]),
     "vcb_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),

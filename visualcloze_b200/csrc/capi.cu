@@ -209,6 +209,11 @@ int check_gemm_args(const vcb_gemm_args* a) {
     const int64_t a_bstride = a->a_batch_stride ? a->a_batch_stride : (int64_t)a->rows_per_batch * a->lda;
     if (a_bstride % 8) return set_error("gemm: a_batch_stride must be a multiple of 8");
     if (a->cta_group < 0 || a->cta_group > 2) return set_error("gemm: cta_group must be 0 (auto), 1 or 2");
+    if (a->row_stats) {
+        if (a->epilogue != VCB_EPI_GATE_RES) return set_error("gemm: row_stats needs the GATE_RES epilogue");
+        if (a->N % 64) return set_error("gemm: row_stats needs N %% 64 == 0");
+        if (a->block_n && a->block_n != 128 && a->block_n != 256) return set_error("gemm: row_stats needs block_n 128 or 256");
+    }
     if (a->operand_dtype != VCB_DTYPE_BF16 && a->operand_dtype != VCB_DTYPE_E4M3) return set_error("gemm: unknown operand_dtype %d", a->operand_dtype);
     if (a->operand_dtype == VCB_DTYPE_E4M3) {
         if (a->lda % 16 || a->ldw % 16 || a_bstride % 16) return set_error("gemm (fp8): lda / ldw / a_batch_stride must be multiples of 16 bytes");
@@ -231,6 +236,7 @@ int build_problem(const vcb_gemm_args* a, int bn, int cg, Problem* out) {
     p.out = (__nv_bfloat16*)a->out; p.ldo = a->ldo; p.out_col_offset = a->out_col_offset;
     p.gate = (const __nv_bfloat16*)a->gate; p.gate_stride = a->gate_stride;
     p.res = (const __nv_bfloat16*)a->res; p.ld_res = a->ld_res;
+    p.row_stats = a->epilogue == VCB_EPI_GATE_RES ? (float2*)a->row_stats : nullptr;
     p.hidden = a->hidden; p.q_scale = (const __nv_bfloat16*)a->q_scale; p.k_scale = (const __nv_bfloat16*)a->k_scale;
     p.rope = (const float2*)a->rope; p.rope_rows = a->rope_rows;
     p.out2 = (__nv_bfloat16*)a->out2; p.ldo2 = a->ldo2; p.out2_col_offset = a->out2_col_offset;
@@ -266,7 +272,8 @@ int gemm_dispatch(const vcb_gemm_args* a, const vcb_gemm_args* a1, void* stream)
     const int batch = a->M / a->rows_per_batch;
     float rate;
     const bool fp8 = a->operand_dtype == VCB_DTYPE_E4M3;
-    pick_tile(batch, a->rows_per_batch + (a1 ? a1->M / batch : 0), a->N, a->K, head || fp8, a->cta_group ? a->cta_group : forced_cta_group(),
+    const bool stats = a->row_stats || (a1 && a1->row_stats);      // 64-column statistics slots: tiles of 128 or 256 columns
+    pick_tile(batch, a->rows_per_batch + (a1 ? a1->M / batch : 0), a->N, a->K, head || fp8 || stats, a->cta_group ? a->cta_group : forced_cta_group(),
               a->block_n, &cg, &bn, &rate);
     ProfScope prof(PROF_GEMM, stream, a->M + (a1 ? a1->M : 0), a->N, a->K, a->epilogue | ((bn >> 5) << 8) | (cg << 16));
     Problem g0, g1;
@@ -633,6 +640,33 @@ extern "C" int vcb_ln_modulate_grouped(const vcb_ln_args* a0, const vcb_ln_args*
     if (!a0 || !a1) return set_error("ln_modulate (grouped): null problem");
     if (batch_rows <= 0) return set_error("ln_modulate (grouped): batch_rows (rows of one sample in the joint buffer) is required");
     return ln_launch(a0, a1, ldx, ldy, mod_stride, hidden, batch_rows, stream);
+}
+
+extern "C" int vcb_ln_modulate_stats(const vcb_ln_args* a0, const vcb_ln_args* a1, const void* stats0, const void* stats1, int32_t n_slots,
+                                     int64_t ldx, int64_t ldy, int64_t mod_stride, int32_t hidden, int32_t batch_rows, void* stream) {
+    if (!a0 || !stats0 || (a1 && !stats1) || n_slots <= 0) return set_error("ln_modulate_stats: null problem / stats");
+    if (hidden % 256) return set_error("ln_modulate_stats: hidden must be a multiple of 256");
+    if (ldx % 8 || ldy % 8 || mod_stride % 8) return set_error("ln_modulate_stats: strides must be multiples of 8");
+    if (batch_rows <= 0) return set_error("ln_modulate_stats: batch_rows (rows of one sample in the joint buffer) is required");
+    LnStatsProblem p[2] = {};
+    const vcb_ln_args* a[2] = {a0, a1};
+    const void* st[2] = {stats0, stats1};
+    for (int i = 0; i < 2; ++i) {
+        if (!a[i]) continue;
+        if (!a[i]->x || !a[i]->y || !a[i]->shift || !a[i]->scale || a[i]->rows <= 0 || a[i]->rows_per_batch <= 0)
+            return set_error("ln_modulate_stats: bad arguments");
+        p[i] = LnStatsProblem{(const __nv_bfloat16*)a[i]->x, (__nv_bfloat16*)a[i]->y, (const __nv_bfloat16*)a[i]->shift,
+                              (const __nv_bfloat16*)a[i]->scale, (const float2*)st[i], a[i]->rows, a[i]->rows_per_batch,
+                              (a[i]->rows + kLnWarps - 1) / kLnWarps};
+    }
+    if (int rc = ensure_device()) return rc;
+    ProfScope prof(PROF_LN, stream);
+    const dim3 grid(p[0].blocks + p[1].blocks), block(kLnWarps * 32);
+    cudaError_t e = launch_pdl(ln_modulate_stats_kernel, grid, block, (size_t)hidden * 8, (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx,
+                               (long long)ldy, (long long)mod_stride, (int)hidden, (int)batch_rows, (int)n_slots);
+    if (e != cudaSuccess) return set_error("ln_modulate_stats launch: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
 }
 
 extern "C" int vcb_ln_modulate_fp8(const vcb_ln_args* a0, const vcb_ln_args* a1, float* row_scale0, float* row_scale1, int64_t ldx,

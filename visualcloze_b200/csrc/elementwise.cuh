@@ -207,6 +207,97 @@ ln_modulate2_kernel(const LnProblem p0, const LnProblem p1, long long ldx, long 
     }
 }
 
+// Statistics-from-the-producer variant: the GATE_RES epilogue of the GEMM that wrote the residual stream also left, per row, one
+// (sum, sum of squares) pair per 64 columns (gemm_sm100.cuh, row_stats).  The LayerNorm then needs no pass over the row for its
+// statistics: a warp adds the row's n_slots pairs in a fixed order (deterministic), and streams the row ONCE.
+struct LnStatsProblem {
+    const __nv_bfloat16* x; __nv_bfloat16* y;
+    const __nv_bfloat16* shift; const __nv_bfloat16* scale;
+    const float2* stats;                            // [rows of this problem][n_slots], indexed by the physical row like x
+    int rows, rows_per_batch, blocks;
+};
+__global__ void __launch_bounds__(kLnWarps * 32, 5)
+ln_modulate_stats_kernel(const LnStatsProblem p0, const LnStatsProblem p1, long long ldx, long long ldy, long long mod_stride, int H,
+                         int batch_rows, int n_slots) {
+    extern __shared__ float4 ln_smem4[];
+    pdl_launch_dependents();
+    pdl_wait();
+    const bool second = (int)blockIdx.x >= p0.blocks;
+    const LnStatsProblem& P = second ? p1 : p0;
+    const int rows = P.rows, rows_per_batch = P.rows_per_batch;
+    const int row0 = ((int)blockIdx.x - (second ? p0.blocks : 0)) * kLnWarps;
+    const int b0 = row0 / rows_per_batch;
+    const int nvec = H >> 3;
+    const int row = row0 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int nchunks = H >> 8;
+    const bool active = row < rows;
+    const int b = active ? row / rows_per_batch : b0;
+    const long long prow = (long long)b * batch_rows + (row - b * rows_per_batch);
+    float sum = 0.f, sq = 0.f;
+    if (active) {
+        const float2* st = P.stats + prow * n_slots;
+        for (int i = lane; i < n_slots; i += 32) {
+            const float2 v = __ldg(st + i);
+            sum += v.x;
+            sq += v.y;
+        }
+    }
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const uint4 su = __ldg(reinterpret_cast<const uint4*>(P.scale + (long long)b0 * mod_stride) + i);
+        const uint4 hu = __ldg(reinterpret_cast<const uint4*>(P.shift + (long long)b0 * mod_stride) + i);
+        const float2 s0 = unpack_bf16x2(su.x), s1 = unpack_bf16x2(su.y), s2 = unpack_bf16x2(su.z), s3 = unpack_bf16x2(su.w);
+        const float2 h0 = unpack_bf16x2(hu.x), h1 = unpack_bf16x2(hu.y), h2 = unpack_bf16x2(hu.z), h3 = unpack_bf16x2(hu.w);
+        ln_smem4[i] = make_float4(bf16_round(1.0f + s0.x), bf16_round(1.0f + s0.y), bf16_round(1.0f + s1.x), bf16_round(1.0f + s1.y));
+        ln_smem4[nvec + i] = make_float4(bf16_round(1.0f + s2.x), bf16_round(1.0f + s2.y), bf16_round(1.0f + s3.x), bf16_round(1.0f + s3.y));
+        ln_smem4[2 * nvec + i] = make_float4(h0.x, h0.y, h1.x, h1.y);
+        ln_smem4[3 * nvec + i] = make_float4(h2.x, h2.y, h3.x, h3.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    __syncthreads();
+    if (!active) return;
+    const float mean = sum / (float)H;
+    const float var = fmaxf(sq / (float)H - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + 1e-6f);
+    const bool staged = (b == b0);
+    const uint4* sh_g = reinterpret_cast<const uint4*>(P.shift + (long long)b * mod_stride);
+    const uint4* sc_g = reinterpret_cast<const uint4*>(P.scale + (long long)b * mod_stride);
+    const uint4* xr = reinterpret_cast<const uint4*>(P.x + prow * ldx) + lane;
+    uint4* yr = reinterpret_cast<uint4*>(P.y + prow * ldy) + lane;
+#pragma unroll 3
+    for (int c = 0; c < nchunks; ++c) {
+        const int vi = c * 32 + lane;
+        const uint4 xv = xr[c * 32];
+        float4 a0, a1, h0, h1;
+        if (staged) {
+            a0 = ln_smem4[vi]; a1 = ln_smem4[nvec + vi]; h0 = ln_smem4[2 * nvec + vi]; h1 = ln_smem4[3 * nvec + vi];
+        } else {
+            const uint4 su = __ldg(sc_g + vi), hu = __ldg(sh_g + vi);
+            const float2 s0 = unpack_bf16x2(su.x), s1 = unpack_bf16x2(su.y), s2 = unpack_bf16x2(su.z), s3 = unpack_bf16x2(su.w);
+            const float2 g0 = unpack_bf16x2(hu.x), g1 = unpack_bf16x2(hu.y), g2 = unpack_bf16x2(hu.z), g3 = unpack_bf16x2(hu.w);
+            a0 = make_float4(bf16_round(1.0f + s0.x), bf16_round(1.0f + s0.y), bf16_round(1.0f + s1.x), bf16_round(1.0f + s1.y));
+            a1 = make_float4(bf16_round(1.0f + s2.x), bf16_round(1.0f + s2.y), bf16_round(1.0f + s3.x), bf16_round(1.0f + s3.y));
+            h0 = make_float4(g0.x, g0.y, g1.x, g1.y);
+            h1 = make_float4(g2.x, g2.y, g3.x, g3.y);
+        }
+        auto mod2 = [&](uint32_t xw, float ax, float ay, float hx, float hy) {
+            const float2 xf = unpack_bf16x2(xw);
+            const float n0 = (xf.x - mean) * rstd, n1 = (xf.y - mean) * rstd;
+            return pack_bf16x2(__fadd_rn(__fmul_rn(ax, n0), hx), __fadd_rn(__fmul_rn(ay, n1), hy));
+        };
+        uint32_t ow[4];
+        ow[0] = mod2(xv.x, a0.x, a0.y, h0.x, h0.y);
+        ow[1] = mod2(xv.y, a0.z, a0.w, h0.z, h0.w);
+        ow[2] = mod2(xv.z, a1.x, a1.y, h1.x, h1.y);
+        ow[3] = mod2(xv.w, a1.z, a1.w, h1.z, h1.w);
+        yr[c * 32] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+}
+
 // FP8 variant (opt-in fp8 projections): same statistics and modulation, but the row leaves as e4m3 bytes with ONE fp32 scale per
 // row: s = max|y| / 448, y8 = e4m3(y / s).  The fp8 GEMM multiplies its accumulator by s (a_scale) again.  The modulated row is
 // kept in registers between the amax and the quantisation (one warp per row, 3 blocks per SM like the one-pass bf16 kernel).

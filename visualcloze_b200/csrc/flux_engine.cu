@@ -26,7 +26,9 @@ struct vcb_flux {
     bool use_score_bounds = true;
     bool fp8 = false;                 // vcb_flux_set_fp8: LayerNorm-fed projections on e4m3 operands
     uint8_t* xm8 = nullptr;           // [B, L, H] e4m3 LayerNorm output (fp8 mode)
-    float* row_scale = nullptr;       // [B * L] fp32 per-row activation scale (fp8 mode)     // false: every block runs the exact online-max softmax (vcb_flux_use_score_bounds)
+    float* row_scale = nullptr;       // [B * L] fp32 per-row activation scale (fp8 mode)
+    float* row_stats = nullptr;       // [B * L][H / 64] float2: LayerNorm statistics left behind by the GATE_RES epilogues
+    bool stats_valid = false;         // row_stats describes the current x (false right after img_in / the txt copy)     // false: every block runs the exact online-max softmax (vcb_flux_use_score_bounds)
     const int32_t* seqlens = nullptr;
     float2* rope = nullptr;
     uint16_t *txt0 = nullptr, *temb_t = nullptr, *temb_g = nullptr, *h1 = nullptr, *e_time = nullptr, *e_guid = nullptr,
@@ -78,6 +80,7 @@ int64_t carve(vcb_flux* f, uint8_t* base, int B, int Li, int Lt, int E) {
     uint16_t* xm = cv.take<uint16_t>((int64_t)B * L * H);
     uint8_t* xm8 = cv.take<uint8_t>((int64_t)B * L * H);
     float* row_scale = cv.take<float>((int64_t)B * L);
+    float* row_stats = cv.take<float>((int64_t)B * L * (H / 64) * 2);
     // sequence-parallel: qkv [W*L, 3H/W] and cat [L, H+mlp] are the caller's peer-mapped allocations (same sizes)
     const bool sp = f->sp_world > 1;
     uint16_t* qkv = sp ? static_cast<uint16_t*>(f->sp_qkv[f->sp_rank]) : cv.take<uint16_t>((int64_t)B * L * 3 * H);
@@ -85,7 +88,7 @@ int64_t carve(vcb_flux* f, uint8_t* base, int B, int Li, int Lt, int E) {
     if (base) {
         f->rope = rope; f->txt0 = txt0; f->temb_t = temb_t; f->temb_g = temb_g; f->h1 = h1; f->e_time = e_time;
         f->e_guid = e_guid; f->e_vec = e_vec; f->vec = vec; f->svec = svec; f->mod_dbl = md; f->mod_sgl = ms;
-        f->mod_final = mod_final; f->x = x; f->xm = xm; f->qkv = qkv; f->cat = cat; f->xm8 = xm8; f->row_scale = row_scale;
+        f->mod_final = mod_final; f->x = x; f->xm = xm; f->qkv = qkv; f->cat = cat; f->xm8 = xm8; f->row_scale = row_scale; f->row_stats = row_stats;
     }
     return cv.off;
 }
@@ -250,6 +253,8 @@ vcb_gemm_args stream_args(const vcb_flux* f, const StreamView& sv, const uint16_
     g.rows_per_batch = sv.rows; g.out_batch_rows = f->L; g.out_row_offset = sv.off;
     g.epilogue = epi;
     g.gate = gate; g.gate_stride = gate_stride; g.res = out; g.ld_res = ldo;
+    // the GEMMs that write the residual stream leave the next LayerNorm's statistics behind (bf16 path; H % 64 == 0 always holds)
+    if (epi == VCB_EPI_GATE_RES && out == f->x && !f->fp8) g.row_stats = f->row_stats;
     g.hidden = f->cfg.hidden; g.q_scale = q_scale; g.k_scale = k_scale; g.rope = f->rope; g.rope_rows = (int64_t)f->B * f->L;
     g.out2 = out2; g.ldo2 = ldo2; g.out2_col_offset = out2_col;
     if (f->fp8 && a_buf == f->xm && w.w8) {
@@ -308,6 +313,11 @@ int stream_ln(const vcb_flux* f, const StreamView& sv, const uint16_t* shift, co
         vcb_ln_args a{f->x + (int64_t)sv.off * H, f->xm8 + (int64_t)sv.off * H, shift, scale, f->B * sv.rows, sv.rows};
         return vcb_ln_modulate_fp8(&a, nullptr, f->row_scale + sv.off, nullptr, H, H, mod_stride, H, f->L, stream);
     }
+    if (f->stats_valid && !f->fp8) {
+        const int ns = H / 64;
+        vcb_ln_args a{f->x + (int64_t)sv.off * H, f->xm + (int64_t)sv.off * H, shift, scale, f->B * sv.rows, sv.rows};
+        return vcb_ln_modulate_stats(&a, nullptr, f->row_stats + (int64_t)sv.off * ns * 2, nullptr, ns, H, H, mod_stride, H, f->L, stream);
+    }
     return vcb_ln_modulate(f->x + (int64_t)sv.off * H, H, f->xm + (int64_t)sv.off * H, H, shift, scale, mod_stride,
                            f->B * sv.rows, H, sv.rows, f->L, stream);
 }
@@ -325,6 +335,11 @@ int double_ln(const vcb_flux* f, const StreamView* const sv[2], const uint16_t* 
     for (int s = 0; s < 2; ++s)
         a[s] = vcb_ln_args{f->x + (int64_t)sv[s]->off * H, f->xm + (int64_t)sv[s]->off * H, mod[s] + mod_col, mod[s] + mod_col + H,
                            f->B * sv[s]->rows, sv[s]->rows};
+    if (f->stats_valid) {
+        const int ns = H / 64;
+        return vcb_ln_modulate_stats(&a[0], &a[1], f->row_stats + (int64_t)sv[0]->off * ns * 2, f->row_stats + (int64_t)sv[1]->off * ns * 2, ns,
+                                     H, H, 6 * H, H, f->L, stream);
+    }
     return vcb_ln_modulate_grouped(&a[0], &a[1], H, H, 6 * H, H, f->L, stream);
 }
 
@@ -357,6 +372,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
                                          cudaMemcpyDeviceToDevice, st);
         if (ce != cudaSuccess) return set_error("flux_forward: txt copy: %s", cudaGetErrorString(ce));
     }
+    f->stats_valid = false;                  // x was just (re)written by img_in and the txt copy: no statistics yet
     const int64_t erow = (int64_t)e * B;     // first modulation row of this evaluation
     // ---- double-stream blocks (layers.py:158-196) ----
     for (int i = 0; i < c.depth; ++i) {
@@ -380,6 +396,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
                 g[s] = stream_args(f, *sv[s], f->cat, ldc, 0, H, sw[s]->proj, H, VCB_EPI_GATE_RES, f->x, H, 0, mod[s] + 2 * H, 6 * H,
                                    nullptr, nullptr, nullptr, 0, 0);
             if ((rc = vcb_gemm_bf16_grouped(&g[0], &g[1], stream))) return rc;
+            f->stats_valid = !f->fp8;          // both streams' rows of x now have their LayerNorm statistics in row_stats
         }
         if ((rc = double_ln(f, sv, mod, 3 * H, stream))) return rc;
         {
@@ -395,6 +412,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
                 g[s] = stream_args(f, *sv[s], f->cat, ldc, H, mlp, sw[s]->mlp2, H, VCB_EPI_GATE_RES, f->x, H, 0, mod[s] + 5 * H, 6 * H,
                                    nullptr, nullptr, nullptr, 0, 0);
             if ((rc = vcb_gemm_bf16_grouped(&g[0], &g[1], stream))) return rc;
+            f->stats_valid = !f->fp8;
         }
     }
     // ---- single-stream blocks on the joint sequence (layers.py:232-245) ----
@@ -407,6 +425,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
         if ((rc = joint_attention(f, ldc, w.attn_score_bound, stream))) return rc;
         if ((rc = stream_gemm(f, s_all, f->cat, ldc, 0, H + mlp, w.linear2, H, VCB_EPI_GATE_RES, f->x, H, 0, mod + 2 * H, 3 * H,
                               nullptr, nullptr, nullptr, nullptr, 0, 0, stream))) return rc;
+        f->stats_valid = !f->fp8;
     }
     // ---- final layer on the img rows (layers.py:255-259; chunk order shift, scale) ----
     {

@@ -56,6 +56,11 @@ struct GemmParams {
     long long gate_stride;
     const __nv_bfloat16* res;    // [rows, ld_res]; may alias out
     long long ld_res;
+    // EPI_GATE_RES, optional: per-row partial sums of the bf16 residual stream this GEMM writes, one float2 (sum, sum of squares)
+    // per 64 output columns at row_stats[orow * (N / 64) + column / 64] -- the statistics pass of the AdaLN LayerNorm that
+    // follows (layers.py:191,195,234).  Every slot is written by exactly one thread: deterministic, no atomics.  Needs N % 64 == 0
+    // and a tile whose column halves are multiples of 64 (BLOCK_N 128 or 256).
+    float2* row_stats;
     // EPI_QKV / EPI_LINEAR1
     int hidden;                  // H (3H = end of the qkv columns); head_dim is 128
     const __nv_bfloat16* q_scale;  // [128] RMSNorm scale for q
@@ -490,6 +495,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     }
                 }
             } else if constexpr (kEpi == EPI_BIAS || kEpi == EPI_BIAS_GELU || kEpi == EPI_GATE_RES) {
+                [[maybe_unused]] float st_sum = 0.f, st_sq = 0.f;
 #pragma unroll 1
                 for (int c = 0; c < kHalfN / 32; ++c) {
                     const int cc = half * (kHalfN / 32) + c;
@@ -522,6 +528,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                         v[q * 8 + 2 * e] = rf.x + a0;
                                         v[q * 8 + 2 * e + 1] = rf.y + a1;
                                     }
+                                }
+                            }
+                            if constexpr (kAMode == A_MATRIX && (kHalfN % 64 == 0)) {
+                                if (P.row_stats != nullptr) {
+                                    // statistics of the values as STORED (bf16): the LayerNorm reads the stream back in bf16
+                                    if ((c & 1) == 0) { st_sum = 0.f; st_sq = 0.f; }
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) {
+                                        const float xr = bf16_round(v[j]);
+                                        st_sum += xr;
+                                        st_sq = fmaf(xr, xr, st_sq);
+                                    }
+                                    if (c & 1) P.row_stats[orow * (long long)(P.N >> 6) + (n0 >> 6)] = make_float2(st_sum, st_sq);
                                 }
                             }
                         }

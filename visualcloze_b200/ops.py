@@ -51,7 +51,7 @@ def gemm_args(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: 
          hidden: int = 0, q_scale=None, k_scale=None, rope=None, out2=None, out2_col_offset: int = 0,
          block_n: int = 0, cta_group: int = 0, a_batch_stride: int = 0, m: int | None = None,
          sp_out: list | None = None, sp_row_offset: int = 0, a_scale: torch.Tensor | None = None,
-         w_scale: torch.Tensor | None = None):
+         w_scale: torch.Tensor | None = None, row_stats: torch.Tensor | None = None):
     """out[...] = epilogue(a @ w.T).  a [M,K], w [N,K], out 2-D (rows, ld); see include/vcb200.h.
     With batching (rows_per_batch < M) sample b's rows start at a + b * a_batch_stride (elements).
     fp8: a and w of dtype ``torch.float8_e4m3fn`` (both), with ``a_scale`` [output rows] / ``w_scale`` [N] fp32."""
@@ -93,6 +93,9 @@ def gemm_args(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: 
         g.sp_world, g.sp_row_offset = len(sp_out), sp_row_offset
         for r, t in enumerate(sp_out):
             g.sp_out[r] = t.data_ptr() if torch.is_tensor(t) else int(t)
+    if row_stats is not None:
+        _req(row_stats, torch.float32, "row_stats")          # [output rows, N / 64, 2] fp32 (GATE_RES only)
+        g.row_stats = row_stats.data_ptr()
     if fp8:
         g.operand_dtype = 1
         if a_scale is not None:
@@ -100,7 +103,7 @@ def gemm_args(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: 
         if w_scale is not None:
             _req(w_scale, torch.float32, "w_scale")
         g.a_scale, g.w_scale = _p(a_scale), _p(w_scale)
-    g._keepalive = (a, w, bias, out, gate, res, q_scale, k_scale, rope, out2, sp_out, a_scale, w_scale)
+    g._keepalive = (a, w, bias, out, gate, res, q_scale, k_scale, rope, out2, sp_out, a_scale, w_scale, row_stats)
     return g, out
 
 
@@ -160,6 +163,19 @@ def ln_modulate_grouped(x: torch.Tensor, out: torch.Tensor, problems: list, hidd
         args.append(a)
     check(_lib.lib().vcb_ln_modulate_grouped(C.byref(args[0]), C.byref(args[1]), x.stride(0), out.stride(0), mod_stride, hidden,
                                              batch_rows, _stream()), "vcb_ln_modulate_grouped")
+
+
+def ln_modulate_stats(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: torch.Tensor, stats: torch.Tensor,
+                      rows_per_batch: int, mod_stride: int | None = None, batch_rows: int | None = None) -> torch.Tensor:
+    """``ln_modulate`` with the row statistics supplied by the producing GEMM: stats [rows, n_slots, 2] fp32 (sum, sum of squares)."""
+    _req(x, BF16, "x"); _req(out, BF16, "out"); _req(stats, torch.float32, "stats"); _req(shift, BF16, "shift"); _req(scale, BF16, "scale")
+    rows, H = x.shape
+    a = _lib.LnArgs()
+    a.x, a.y, a.shift, a.scale, a.rows, a.rows_per_batch = x.data_ptr(), out.data_ptr(), shift.data_ptr(), scale.data_ptr(), rows, rows_per_batch
+    ms = mod_stride if mod_stride is not None else (shift.stride(0) if shift.dim() > 1 else 0)
+    check(_lib.lib().vcb_ln_modulate_stats(C.byref(a), None, stats.data_ptr(), None, stats.shape[1], x.stride(0), out.stride(0), ms, H,
+                                           batch_rows or rows_per_batch, _stream()), "vcb_ln_modulate_stats")
+    return out
 
 
 def ln_modulate_fp8(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out8: torch.Tensor, row_scale: torch.Tensor,
