@@ -1,6 +1,6 @@
 """Launch ONE hot kernel of the path at its cfg-B shape a few times, for `ncu --set full -k regex:... -c 1` captures.
 
-  python tools/ncu_targets.py ln | attn_pair | attn_pair_exact | attn_persistent | gemm_linear1 | gemm_linear2 | gemm_fp8_linear1 |
+  python tools/ncu_targets.py ln | ln_stats | attn_pair | attn_pair_exact | attn_persistent | gemm_linear1 | gemm_linear2 | gemm_fp8_linear1 |
                               conv512 | conv256 | conv128
 """
 import math
@@ -25,6 +25,14 @@ if what == "ln":
     mods = [(0.2 * rn(1, 6 * H)).to(BF16) for _ in range(2)]
     for _ in range(REP):   # the img + txt LayerNorms of a double block in one launch
         ops.ln_modulate_grouped(x, y, [(Lt, Li, Li, mods[0][:, :H], mods[0][:, H:2 * H]), (0, Lt, Lt, mods[1][:, :H], mods[1][:, H:2 * H])], H, L, 6 * H)
+elif what == "ln_stats":
+    # the LayerNorm that follows a residual GEMM: statistics come from the GEMM's epilogue (row_stats), the row is streamed once
+    x, y = rn(L, H).to(BF16), torch.empty(L, H, dtype=BF16, device="cuda")
+    xf = x.float().reshape(L, H // 64, 64)
+    stats = torch.stack((xf.sum(-1), (xf * xf).sum(-1)), dim=-1).contiguous()
+    mod = (0.2 * rn(1, 3 * H)).to(BF16)
+    for _ in range(REP):
+        ops.ln_modulate_stats(x, mod[:, :H], mod[:, H:2 * H], y, stats, rows_per_batch=L, mod_stride=3 * H)
 elif what.startswith("attn"):
     qkv = rn(L, 3, 24, 128)
     for i, a in ((0, 1.2), (1, 1.1)):
