@@ -445,10 +445,11 @@ def main():
                                "peak": pk["tf"], "unit": "TFLOP/s", "frac": attn_fl / (pms[1] / 1000.0) / 1e12 / pk["tf"],
                                "launches": int(pl[1]), "avg_launch_ms": pms[1] / max(1, pl[1]), "softmax_variant_per_block": variants,
                                "traffic": traffic.get("attention", {}).get("avg_dram_bytes_per_launch")},
-        "roofline_ln_modulate": {"kernel": "ln_modulate2_kernel" if args.precision == "bf16" else "ln_modulate2_kernel + ln_modulate_fp8_kernel (e4m3 rows + per-row scales)", "bound": "hbm", "unit": "GB/s", "peak": pk["hbm"],
+        "roofline_ln_modulate": {"kernel": "ln_modulate_stats_kernel (statistics from the producing GEMM's epilogue; ln_modulate2_kernel for the first LayerNorm of an evaluation)"
+                                 if args.precision == "bf16" else "ln_modulate_fp8_kernel (e4m3 rows + per-row scales) + ln_modulate2_kernel", "bound": "hbm", "unit": "GB/s", "peak": pk["hbm"],
                                  "achieved": ln_bytes / (pms[2] / 1000.0) / 1e9, "frac": ln_bytes / (pms[2] / 1000.0) / 1e9 / pk["hbm"],
                                  "launches": int(pl[2]), "avg_launch_ms": pms[2] / max(1, pl[2]),
-                                 "note": "algorithmic bytes = read + write of the normalised rows (the second read of the two-pass kernel hits L1/L2)"},
+                                 "note": "algorithmic bytes = read + write of the normalised rows; CUDA events around a ~14 us kernel (ncu: 14.0 us, profiles/r02_summary.md) include ~4 us of launch latency"},
         "roofline_vae": {"kernel": "gemm_bf16_tcgen05_kernel<A_CONV3X3> (implicit-GEMM 3x3 convolutions of the decoder, query row)",
                          "bound": "tensor", "unit": "TFLOP/s", "peak": pk["tf"], "achieved": conv_fl / max(conv_ms, 1e-9) / 1e9,
                          "frac": conv_fl / max(conv_ms, 1e-9) / 1e9 / pk["tf"], "launches": int(pl[4]), "conv_ms": conv_ms,

@@ -86,8 +86,9 @@ for name, title in (("r02_fullsize_parity", "full-size parity (tests/test_fullsi
             out.append(f"* `{k}`: " + ", ".join(f"{a} = {b:.4g}" for a, b in v.items()) + "\n")
 
 # ---- ncu launch list -----------------------------------------------------------------------------------------------
-if os.path.exists(f"{G}/r2_launches.csv"):
-    rows = list(csv.reader(open(f"{G}/r2_launches.csv")))
+LL = f"{P}/r02_ncu_launches.csv" if os.path.exists(f"{P}/r02_ncu_launches.csv") else f"{G}/r2_launches.csv"
+if os.path.exists(LL):
+    rows = list(csv.reader(open(LL)))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"]
     if hi:
         hdr, data = rows[hi[0]], rows[hi[0] + 1:]
@@ -141,7 +142,7 @@ if caps:
             t = val(r, "gpu__time_duration.sum")
             out.append(f"| {name} | `{r[hdr.index('Kernel Name')][:48]}` | {r[hdr.index('Grid Size')]} | {t:.1f} | {dram / 1e6:.1f} | "
                        + " | ".join(f"{val(r, n):.1f}" for n in WANT[3:]) + " |\n")
-            key = {"gemm_linear2": "gemm", "attn_pair": "attention", "ln": "ln_modulate", "conv256": "vae_conv3x3"}.get(name)
+            key = {"gemm_linear2": "gemm", "attn_pair": "attention", "ln_stats": "ln_modulate", "conv256": "vae_conv3x3"}.get(name)
             if key:
                 traffic[key] = {"avg_dram_bytes_per_launch": dram, "time_us": t, "tensor_pipe_active_pct": val(r, WANT[3]), "capture": os.path.basename(p)}
 if traffic:

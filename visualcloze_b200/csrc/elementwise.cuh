@@ -216,7 +216,10 @@ struct LnStatsProblem {
     const float2* stats;                            // [rows of this problem][n_slots], indexed by the physical row like x
     int rows, rows_per_batch, blocks;
 };
-__global__ void __launch_bounds__(kLnWarps * 32, 5)
+// 4 blocks x 8 warps per SM = 4736 resident warps >= the 3968 rows of a cfg-B sequence: still one round, and 64 registers let a
+// lane keep six 16-byte loads in flight -- the kernel is latency-bound (ncu: 16 us for 24 MB, one dependent chain per warp), so the
+// row is covered by two batches of loads instead of four.
+__global__ void __launch_bounds__(kLnWarps * 32, 4)
 ln_modulate_stats_kernel(const LnStatsProblem p0, const LnStatsProblem p1, long long ldx, long long ldy, long long mod_stride, int H,
                          int batch_rows, int n_slots) {
     extern __shared__ float4 ln_smem4[];
@@ -268,7 +271,7 @@ ln_modulate_stats_kernel(const LnStatsProblem p0, const LnStatsProblem p1, long 
     const uint4* sc_g = reinterpret_cast<const uint4*>(P.scale + (long long)b * mod_stride);
     const uint4* xr = reinterpret_cast<const uint4*>(P.x + prow * ldx) + lane;
     uint4* yr = reinterpret_cast<uint4*>(P.y + prow * ldy) + lane;
-#pragma unroll 3
+#pragma unroll 6
     for (int c = 0; c < nchunks; ++c) {
         const int vi = c * 32 + lane;
         const uint4 xv = xr[c * 32];

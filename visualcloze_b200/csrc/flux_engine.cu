@@ -175,6 +175,7 @@ extern "C" int vcb_flux_sp_attach(vcb_flux* f, int32_t world, int32_t rank, void
     if (world > VCB_SP_MAX || rank < 0 || rank >= world || !qkv || !cat || !flags || !err)
         return set_error("flux_sp_attach: bad arguments (world <= %d)", VCB_SP_MAX);
     if (f->cfg.heads % world) return set_error("flux_sp_attach: heads (%d) must be a multiple of world (%d)", f->cfg.heads, world);
+    if (f->fp8) return set_error("flux_sp_attach: the sequence-parallel mode runs bf16 projections (switch vcb_flux_set_fp8 off first)");
     for (int r = 0; r < world; ++r) {
         if (!qkv[r] || !cat[r] || !flags[r]) return set_error("flux_sp_attach: null buffer for rank %d", r);
         f->sp_qkv[r] = qkv[r]; f->sp_cat[r] = cat[r]; f->sp_flags[r] = flags[r];
