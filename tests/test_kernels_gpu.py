@@ -626,3 +626,51 @@ def test_row_stats_rejected_where_it_cannot_work(ops):
         ops.gemm(a, w, None, out, row_stats=st)                                  # not the GATE_RES epilogue
     with pytest.raises(Exception, match="row_stats"):
         ops.gemm(a, w, None, out, epilogue=ops.EPI_GATE_RES, res=out, gate=torch.zeros(1, 128, dtype=BF16, device="cuda"), row_stats=st, block_n=192)
+
+
+@pytest.mark.parametrize("raster", ["0", "1"])
+def test_gemm_tile_raster_forced_subprocess(raster):
+    """GemmParams.n_fastest is chosen per shape (A bigger than B -> N-fastest); force each raster in a child process (the switch
+    is read once per process) over plain, batched, grouped and head-structured launches and compare with fp32 matmul."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import math, sys, torch
+sys.path.insert(0, %r)
+from visualcloze_b200 import ops
+BF16 = torch.bfloat16
+g = torch.Generator().manual_seed(1)
+def rel(a, b): return float((a.double() - b.double()).norm() / b.double().norm())
+for (M, N, K) in ((1000, 512, 384), (300, 1536, 512), (3968, 3072, 1024)):
+    a = torch.randn(M, K, generator=g).to(BF16); w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(BF16); b = torch.randn(N, generator=g)
+    out = torch.empty(M, N, dtype=BF16, device="cuda")
+    ops.gemm(a.cuda(), w.cuda(), b.cuda(), out)
+    assert rel(out.cpu(), (a.float() @ w.float().T + b).to(BF16)) < 4e-3, (M, N, K)
+# batched rows with a row-mapped output (two samples of 260 rows inside 300-row slots)
+B, R, S, N, K = 2, 260, 300, 384, 256
+a = torch.randn(B * R, K, generator=g).to(BF16); w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(BF16); bias = torch.randn(N, generator=g)
+out = torch.zeros(B * S, N, dtype=BF16, device="cuda")
+ops.gemm(a.cuda(), w.cuda(), bias.cuda(), out, rows_per_batch=R, out_batch_rows=S, out_row_offset=20)
+ref = (a.float() @ w.float().T + bias).to(BF16).reshape(B, R, N)
+got = out.cpu().reshape(B, S, N)
+assert rel(got[:, 20:20 + R], ref) < 4e-3 and float(got[:, :20].abs().max()) == 0 and float(got[:, 20 + R:].abs().max()) == 0
+# grouped img + txt problems with the gated-residual epilogue
+K, N, Li, Lt = 512, 256, 900, 130
+L = Li + Lt
+a = torch.randn(L, K, generator=g).to(BF16).cuda(); x0 = torch.randn(L, N, generator=g).to(BF16); x = x0.clone().cuda()
+probs, refs = [], []
+for off, rows in ((Lt, Li), (0, Lt)):
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(BF16); bias = torch.randn(N, generator=g); gate = (0.5 * torch.randn(1, N, generator=g)).to(BF16)
+    probs.append(dict(a=a[off:off + rows], w=w.cuda(), bias=bias.cuda(), out=x, epilogue=ops.EPI_GATE_RES, gate=gate.cuda(), res=x, rows_per_batch=rows,
+                      out_batch_rows=L, out_row_offset=off))
+    lin = (a[off:off + rows].cpu().float() @ w.float().T + bias).to(BF16)
+    refs.append((off, rows, (x0[off:off + rows].float() + (gate.float() * lin.float()).to(BF16).float()).to(BF16)))
+ops.gemm_grouped(probs[0], probs[1])
+torch.cuda.synchronize()
+for off, rows, ref in refs:
+    assert rel(x[off:off + rows].cpu(), ref) < 4e-3
+print("raster ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, VCB_GEMM_RASTER=raster), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "raster ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -284,6 +284,15 @@ int gemm_dispatch(const vcb_gemm_args* a, const vcb_gemm_args* a1, void* stream)
         g1 = g0;
         g1.p = GemmParams{};            // batch == 0: no second problem
     }
+    // tile raster: N-fastest (A streamed once, B kept in L2) when A is the bigger operand -- mlp.2 / linear2 / proj at the
+    // single-GPU shapes; VCB_GEMM_RASTER=0 / 1 forces M- / N-fastest for A/B runs
+    {
+        static const int forced = [] { const char* e = getenv("VCB_GEMM_RASTER"); return e ? atoi(e) : -1; }();
+        const long long m_total = (long long)a->M + (a1 ? a1->M : 0);
+        const int nf = forced >= 0 ? (forced ? 1 : 0) : (m_total > (long long)a->N ? 1 : 0);
+        g0.p.n_fastest = nf;
+        g1.p.n_fastest = nf;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (fp8) {
 #define VCB_GEMM_CASE8(BN, CG) \

@@ -43,6 +43,12 @@ struct GemmParams {
     int rows_per_batch;
     int out_batch_rows;
     int out_row_offset;
+    // Tile raster.  0: M-fastest -- the CTAs of a wave share few B (weight) tiles and cover all A rows: right when B is the big
+    // operand (qkv, mlp.0, linear1).  1: N-fastest -- a wave covers a band of A rows x ALL B tiles, A is streamed once
+    // (evict-first) and B is kept in L2 (evict-last): right when A is the big operand (mlp.2: A 97 MB / B 75 MB; linear2: A 122 MB /
+    // B 94 MB, both < the 126 MB L2).  ncu, linear2 at cfg B: 522 MB of DRAM traffic per launch M-fastest (A re-read by each of the
+    // three waves) against 265 MB algorithmic.
+    int n_fastest;
     const float* bias;           // [N] fp32 (may be null)
     // FP8 (e4m3) operands (kFp8 instantiations): acc is rescaled by a_scale[mapped output row] * w_scale[column] before the bias --
     // per-row activation scales written by the producing LayerNorm kernel, per-output-channel weight scales from packing time
@@ -302,10 +308,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const int tt = g1 ? t - tiles0 : t, nm = g1 ? num_m1 : num_m, mps = g1 ? m_per_sample1 : m_per_sample;
                 const CUtensorMap* ta = g1 ? &tmap_a1 : &tmap_a;
                 const CUtensorMap* tb = g1 ? &tmap_b1 : &tmap_b;
-                const int mt = tt % nm;
+                const int mt = p.n_fastest ? tt / num_n : tt % nm;
                 const int bi = mt / mps;
                 const int m0 = (mt % mps) * tile_m + (int)cta_rank * kBlockM;
-                const int n0 = (tt / nm) * BLOCK_N + (int)cta_rank * Cfg::kBRows;
+                const int n0 = (p.n_fastest ? tt % num_n : tt / nm) * BLOCK_N + (int)cta_rank * Cfg::kBRows;
+                const uint64_t hint_a = p.n_fastest ? kEvictFirst : kEvictNormal, hint_b = p.n_fastest ? kEvictLast : kEvictNormal;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (is_leader) mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes * kCtaGroup);
@@ -320,10 +327,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                            kEvictNormal);
                     } else {
                         tma_load_3d<kCtaGroup == 2>(ta, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBlockKEl,
-                                                    m0, bi, kEvictNormal);
+                                                    m0, bi, hint_a);
                     }
                     tma_load_2d<kCtaGroup == 2>(tb, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBlockKEl,
-                                                n0, kEvictNormal);
+                                                n0, hint_b);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -383,9 +390,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const bool sk_contrib = kb0 > 0;                       // tail part of a split tile: dump partials, no epilogue
             const bool sk_final = !sk_contrib && kb1 < num_kb;     // head part: add the partner's partials, then epilogue
             const int tt = g1 ? t - tiles0 : t, nm = g1 ? num_m1 : num_m, mps = g1 ? m_per_sample1 : m_per_sample;
-            const int mt = tt % nm;
+            const int mt = p.n_fastest ? tt / num_n : tt % nm;
             const int b = mt / mps;
-            const int n_tile0 = (tt / nm) * BLOCK_N;
+            const int n_tile0 = (p.n_fastest ? tt % num_n : tt / nm) * BLOCK_N;
             int i;
             bool row_ok;
             if constexpr (kAMode == A_CONV3X3) {
