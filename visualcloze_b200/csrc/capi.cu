@@ -284,12 +284,14 @@ int gemm_dispatch(const vcb_gemm_args* a, const vcb_gemm_args* a1, void* stream)
         g1 = g0;
         g1.p = GemmParams{};            // batch == 0: no second problem
     }
-    // tile raster: N-fastest (A streamed once, B kept in L2) when A is the bigger operand -- mlp.2 / linear2 / proj at the
-    // single-GPU shapes; VCB_GEMM_RASTER=0 / 1 forces M- / N-fastest for A/B runs
+    // tile raster: M-fastest.  The N-fastest alternative (a wave = a band of A rows x all weight tiles, A evict-first, B evict-last),
+    // meant to stop linear2's three waves from re-reading A, was measured WORSE: 642 MB of DRAM traffic per launch instead of 522 MB
+    // (ncu, profiles/r02_summary.md) and the same time in the loop (GEMM 1167.1 vs 1167.3 ms per image) -- the 94 MB weight does not
+    // survive in L2 next to the streamed A, and evict-first drops A tiles before all twelve column tiles have fetched them.
+    // VCB_GEMM_RASTER=1 still selects it (A/B runs, tests).
     {
         static const int forced = [] { const char* e = getenv("VCB_GEMM_RASTER"); return e ? atoi(e) : -1; }();
-        const long long m_total = (long long)a->M + (a1 ? a1->M : 0);
-        const int nf = forced >= 0 ? (forced ? 1 : 0) : (m_total > (long long)a->N ? 1 : 0);
+        const int nf = forced > 0 ? 1 : 0;
         g0.p.n_fastest = nf;
         g1.p.n_fastest = nf;
     }

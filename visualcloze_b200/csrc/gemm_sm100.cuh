@@ -43,11 +43,9 @@ struct GemmParams {
     int rows_per_batch;
     int out_batch_rows;
     int out_row_offset;
-    // Tile raster.  0: M-fastest -- the CTAs of a wave share few B (weight) tiles and cover all A rows: right when B is the big
-    // operand (qkv, mlp.0, linear1).  1: N-fastest -- a wave covers a band of A rows x ALL B tiles, A is streamed once
-    // (evict-first) and B is kept in L2 (evict-last): right when A is the big operand (mlp.2: A 97 MB / B 75 MB; linear2: A 122 MB /
-    // B 94 MB, both < the 126 MB L2).  ncu, linear2 at cfg B: 522 MB of DRAM traffic per launch M-fastest (A re-read by each of the
-    // three waves) against 265 MB algorithmic.
+    // Tile raster.  0 (default): M-fastest -- the CTAs of a wave share few B (weight) tiles and cover all A rows.  1: N-fastest -- a
+    // wave covers a band of A rows x ALL B tiles, A evict-first, B evict-last.  Measured on linear2 (A 122 MB, B 94 MB, three waves):
+    // 522 MB of DRAM traffic per launch M-fastest, 642 MB N-fastest (algorithmic 265 MB), same time -- kept as an experiment switch.
     int n_fastest;
     const float* bias;           // [N] fp32 (may be null)
     // FP8 (e4m3) operands (kFp8 instantiations): acc is rescaled by a_scale[mapped output row] * w_scale[column] before the bias --
