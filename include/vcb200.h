@@ -178,6 +178,10 @@ int vcb_ln_modulate_stats(const vcb_ln_args* a0, const vcb_ln_args* a1, const vo
  * problems per launch (a1 may be NULL); vcb_ln_args.y is then the e4m3 destination of that problem. */
 int vcb_ln_modulate_fp8(const vcb_ln_args* a0, const vcb_ln_args* a1, float* row_scale0, float* row_scale1, int64_t ldx, int64_t ld8,
                         int64_t mod_stride, int32_t hidden, int32_t batch_rows, void* stream);
+/* the same with the row statistics supplied by the producing GEMM (see vcb_ln_modulate_stats) */
+int vcb_ln_modulate_fp8_stats(const vcb_ln_args* a0, const vcb_ln_args* a1, float* row_scale0, float* row_scale1, const void* stats0,
+                              const void* stats1, int32_t n_slots, int64_t ldx, int64_t ld8, int64_t mod_stride, int32_t hidden,
+                              int32_t batch_rows, void* stream);
 
 /* ---- small helpers --------------------------------------------------------------------------------------- */
 /* layers.py:28-49; t_scaled = time_factor * t already in the reference's dtype; freqs[128] fp32; out [n,256] bf16 */

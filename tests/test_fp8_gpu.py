@@ -118,6 +118,15 @@ def test_ln_modulate_fp8_matches_quantised_bf16_kernel(ops):
     err = (deq - y.float()).abs()
     assert bool((err <= y.float().abs() * 2.0 ** -4 + rs[:, None] * 2.0 ** -9 * 1.01).all())
     assert rel_l2(deq, y.float()) < 4e-2
+    # statistics supplied by the producer (what the GATE_RES epilogue leaves behind): same bytes up to the statistics' fp32 rounding
+    xf = x.float().reshape(rows, H // 64, 64)
+    stats = torch.stack((xf.sum(-1), (xf * xf).sum(-1)), dim=-1).contiguous()
+    y8s = torch.empty(rows, H, dtype=F8, device="cuda")
+    rs2 = torch.zeros(rows, dtype=torch.float32, device="cuda")
+    ops.ln_modulate_fp8(x, shift, scale, y8s, rs2, rows_per_batch=rows, stats=stats)
+    torch.cuda.synchronize()
+    assert torch.allclose(rs2, rs, rtol=2e-2, atol=0)        # a row maximum may land on the neighbouring bf16 value
+    assert rel_l2(y8s.float() * rs2[:, None], deq) < 2e-2
 
 
 @pytest.fixture(scope="module")

@@ -195,6 +195,8 @@ _OPTIONAL: dict = {
                                           C.c_int32, C.c_void_p]),
     "vcb_ln_modulate_stats": (C.c_int, [C.POINTER(LnArgs), C.POINTER(LnArgs), C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
                                         C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "vcb_ln_modulate_fp8_stats": (C.c_int, [C.POINTER(LnArgs), C.POINTER(LnArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                            C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "vcb_ln_modulate_fp8": (C.c_int, [C.POINTER(LnArgs), C.POINTER(LnArgs), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                       C.c_int32, C.c_int32, C.c_void_p]),
     "vcb_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),

@@ -468,13 +468,16 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
     if (total_steps / pgrid < 4) pgrid = (int)(total_steps / 4 > 0 ? total_steps / 4 : 1);   // tiny problems: >= 4 key-tile steps per CTA
     // a CTA's segment list: one entry per full round + the pieces of its tail share; beyond the kernel's capacity (huge batches of
     // short sequences) use the per-pair grid
-    // sequence-parallel routing: the persistent kernel stores O rows straight through the peer-mapped pointers (no TMA staging);
-    // opt-in with VCB_SP_ATTN_PERSIST=1 until measured on the NVLink path (few heads per rank: 48 / 96 per-pair CTAs on 148 SMs)
-    static const bool sp_persist = [] { const char* e = getenv("VCB_SP_ATTN_PERSIST"); return e && atoi(e); }();
+    // sequence-parallel routing: the persistent kernel stores O rows straight through the peer-mapped pointers (no TMA staging).
+    // Few heads per rank leave the per-pair grid far below one wave (cfg B: 96 CTAs at 4 ranks, 48 at 8) and these ranks are not
+    // power-capped, so there the split tail pays: used when the per-pair grid would fill < 70 % of the SMs (measured equal at 2
+    // ranks = 192 CTAs, where the staged-TMA kernel stays).  VCB_SP_ATTN_PERSIST=0 / 1 forces it off / on.
+    static const int sp_persist_env = [] { const char* e = getenv("VCB_SP_ATTN_PERSIST"); return e ? (atoi(e) ? 1 : 0) : -1; }();
+    const bool sp_persist = out_peers && (sp_persist_env >= 0 ? sp_persist_env == 1 : n_units * 10 < (long long)num_sms() * 7);
     const bool persist_ok = !seqlens && (!out_peers || sp_persist) && num_sms() <= 160 && n_units / pgrid + 4 <= kAttn4MaxSegs;
     if (schedule == VCB_ATTN_SCHED_PERSISTENT && !persist_ok)
         return set_error("attention: the persistent schedule takes unpadded batches (seqlens == NULL), no sequence-parallel routing");
-    if (persist_ok && (schedule == VCB_ATTN_SCHED_PERSISTENT || (schedule == VCB_ATTN_SCHED_AUTO && attn_persist_mode() != 0))) {
+    if (persist_ok && (schedule == VCB_ATTN_SCHED_PERSISTENT || (schedule == VCB_ATTN_SCHED_AUTO && (attn_persist_mode() != 0 || sp_persist)))) {
         const int grid = pgrid;
         prof.set_info(3, (fixed ? 1 : 0) | 2);
         AttnScratch* sc = attn_scratch((cudaStream_t)stream);
@@ -705,6 +708,33 @@ extern "C" int vcb_ln_modulate_fp8(const vcb_ln_args* a0, const vcb_ln_args* a1,
         : launch_pdl(ln_modulate_fp8_kernel<kLnMaxChunks>, grid, block, (size_t)hidden * 4, (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx,
                      (long long)ld8, (long long)mod_stride, (int)hidden, (int)batch_rows);
     if (e != cudaSuccess) return set_error("ln_modulate_fp8 launch: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
+}
+
+extern "C" int vcb_ln_modulate_fp8_stats(const vcb_ln_args* a0, const vcb_ln_args* a1, float* row_scale0, float* row_scale1, const void* stats0,
+                                         const void* stats1, int32_t n_slots, int64_t ldx, int64_t ld8, int64_t mod_stride, int32_t hidden,
+                                         int32_t batch_rows, void* stream) {
+    if (!a0 || !row_scale0 || !stats0 || (a1 && (!row_scale1 || !stats1)) || n_slots <= 0) return set_error("ln_modulate_fp8_stats: null problem / row_scale / stats");
+    if (hidden % 256) return set_error("ln_modulate_fp8_stats: hidden must be a multiple of 256");
+    if (ldx % 8 || ld8 % 16 || mod_stride % 8) return set_error("ln_modulate_fp8_stats: ldx / mod_stride must be multiples of 8, ld8 of 16");
+    if (batch_rows <= 0) return set_error("ln_modulate_fp8_stats: batch_rows (rows of one sample in the joint buffer) is required");
+    LnFp8Problem p[2] = {};
+    const vcb_ln_args* a[2] = {a0, a1};
+    float* rs[2] = {row_scale0, row_scale1};
+    for (int i = 0; i < 2; ++i) {
+        if (!a[i]) continue;
+        if (!a[i]->x || !a[i]->y || !a[i]->shift || !a[i]->scale || a[i]->rows <= 0 || a[i]->rows_per_batch <= 0)
+            return set_error("ln_modulate_fp8_stats: bad arguments");
+        p[i] = LnFp8Problem{(const __nv_bfloat16*)a[i]->x, (uint8_t*)a[i]->y, rs[i], (const __nv_bfloat16*)a[i]->shift,
+                            (const __nv_bfloat16*)a[i]->scale, a[i]->rows, a[i]->rows_per_batch, (a[i]->rows + kLnWarps - 1) / kLnWarps};
+    }
+    if (int rc = ensure_device()) return rc;
+    ProfScope prof(PROF_LN, stream);
+    const dim3 grid(p[0].blocks + p[1].blocks), block(kLnWarps * 32);
+    cudaError_t e = launch_pdl(ln_modulate_fp8_stats_kernel, grid, block, (size_t)hidden * 8, (cudaStream_t)stream, 1, p[0], p[1], (const float2*)stats0,
+                               (const float2*)stats1, (int)n_slots, (long long)ldx, (long long)ld8, (long long)mod_stride, (int)hidden, (int)batch_rows);
+    if (e != cudaSuccess) return set_error("ln_modulate_fp8_stats launch: %s", cudaGetErrorString(e));
     count_launch();
     return 0;
 }

@@ -413,6 +413,113 @@ ln_modulate_fp8_kernel(const LnFp8Problem p0, const LnFp8Problem p1, long long l
         }
 }
 
+// FP8 + statistics from the producer: with (sum, sum of squares) supplied by the GATE_RES epilogue the fp8 LayerNorm needs no
+// register-resident row either -- pass A streams the row for max|bf16(y)|, pass B re-reads it (L1 / L2) and writes the e4m3 bytes.
+// 48 registers -> 5 blocks per SM: one round at cfg B (the register-resident kernel above: 3 blocks per SM, two rounds).
+__global__ void __launch_bounds__(kLnWarps * 32, 5)
+ln_modulate_fp8_stats_kernel(const LnFp8Problem p0, const LnFp8Problem p1, const float2* stats0, const float2* stats1, int n_slots,
+                             long long ldx, long long ldy, long long mod_stride, int H, int batch_rows) {
+    extern __shared__ float4 ln_smem4[];
+    pdl_launch_dependents();
+    pdl_wait();
+    const bool second = (int)blockIdx.x >= p0.blocks;
+    const LnFp8Problem& P = second ? p1 : p0;
+    const float2* stats = second ? stats1 : stats0;
+    const int rows = P.rows, rows_per_batch = P.rows_per_batch;
+    const int row0 = ((int)blockIdx.x - (second ? p0.blocks : 0)) * kLnWarps;
+    const int b0 = row0 / rows_per_batch;
+    const int nvec = H >> 3;
+    const int row = row0 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int nchunks = H >> 8;
+    const bool active = row < rows;
+    const int b = active ? row / rows_per_batch : b0;
+    const long long prow = (long long)b * batch_rows + (row - b * rows_per_batch);
+    float sum = 0.f, sq = 0.f;
+    if (active) {
+        const float2* st = stats + prow * n_slots;
+        for (int i = lane; i < n_slots; i += 32) {
+            const float2 v = __ldg(st + i);
+            sum += v.x;
+            sq += v.y;
+        }
+    }
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const uint4 su = __ldg(reinterpret_cast<const uint4*>(P.scale + (long long)b0 * mod_stride) + i);
+        const uint4 hu = __ldg(reinterpret_cast<const uint4*>(P.shift + (long long)b0 * mod_stride) + i);
+        const float2 s0 = unpack_bf16x2(su.x), s1 = unpack_bf16x2(su.y), s2 = unpack_bf16x2(su.z), s3 = unpack_bf16x2(su.w);
+        const float2 h0 = unpack_bf16x2(hu.x), h1 = unpack_bf16x2(hu.y), h2 = unpack_bf16x2(hu.z), h3 = unpack_bf16x2(hu.w);
+        ln_smem4[i] = make_float4(bf16_round(1.0f + s0.x), bf16_round(1.0f + s0.y), bf16_round(1.0f + s1.x), bf16_round(1.0f + s1.y));
+        ln_smem4[nvec + i] = make_float4(bf16_round(1.0f + s2.x), bf16_round(1.0f + s2.y), bf16_round(1.0f + s3.x), bf16_round(1.0f + s3.y));
+        ln_smem4[2 * nvec + i] = make_float4(h0.x, h0.y, h1.x, h1.y);
+        ln_smem4[3 * nvec + i] = make_float4(h2.x, h2.y, h3.x, h3.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    __syncthreads();
+    if (!active) return;
+    const float mean = sum / (float)H;
+    const float var = fmaxf(sq / (float)H - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + 1e-6f);
+    const bool staged = (b == b0);
+    const uint4* sh_g = reinterpret_cast<const uint4*>(P.shift + (long long)b * mod_stride);
+    const uint4* sc_g = reinterpret_cast<const uint4*>(P.scale + (long long)b * mod_stride);
+    const uint4* xr = reinterpret_cast<const uint4*>(P.x + prow * ldx) + lane;
+    // the modulated values of one 8-element group, rounded to bf16 like the bf16 path rounds them
+    auto group = [&](int c, float (&y)[8]) {
+        const int vi = c * 32 + lane;
+        const uint4 xv = xr[c * 32];
+        float4 a0, a1, h0, h1;
+        if (staged) {
+            a0 = ln_smem4[vi]; a1 = ln_smem4[nvec + vi]; h0 = ln_smem4[2 * nvec + vi]; h1 = ln_smem4[3 * nvec + vi];
+        } else {
+            const uint4 su = __ldg(sc_g + vi), hu = __ldg(sh_g + vi);
+            const float2 s0 = unpack_bf16x2(su.x), s1 = unpack_bf16x2(su.y), s2 = unpack_bf16x2(su.z), s3 = unpack_bf16x2(su.w);
+            const float2 g0 = unpack_bf16x2(hu.x), g1 = unpack_bf16x2(hu.y), g2 = unpack_bf16x2(hu.z), g3 = unpack_bf16x2(hu.w);
+            a0 = make_float4(bf16_round(1.0f + s0.x), bf16_round(1.0f + s0.y), bf16_round(1.0f + s1.x), bf16_round(1.0f + s1.y));
+            a1 = make_float4(bf16_round(1.0f + s2.x), bf16_round(1.0f + s2.y), bf16_round(1.0f + s3.x), bf16_round(1.0f + s3.y));
+            h0 = make_float4(g0.x, g0.y, g1.x, g1.y);
+            h1 = make_float4(g2.x, g2.y, g3.x, g3.y);
+        }
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 xf = unpack_bf16x2(xw[e]);
+            const float n0 = (xf.x - mean) * rstd, n1 = (xf.y - mean) * rstd;
+            y[2 * e] = bf16_round(__fadd_rn(__fmul_rn(av[2 * e], n0), hv[2 * e]));
+            y[2 * e + 1] = bf16_round(__fadd_rn(__fmul_rn(av[2 * e + 1], n1), hv[2 * e + 1]));
+        }
+    };
+    float amax = 0.f;
+#pragma unroll 2
+    for (int c = 0; c < nchunks; ++c) {
+        float y[8];
+        group(c, y);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(y[e]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float s = fmaxf(amax, 1e-12f) * (1.0f / 448.0f);
+    const float inv = 1.0f / s;
+    if (lane == 0) P.row_scale[prow] = s;
+    uint8_t* yr = P.y8 + prow * ldy;
+#pragma unroll 2
+    for (int c = 0; c < nchunks; ++c) {
+        float y[8];
+        group(c, y);
+        uint2 o;
+        o.x = pack_e4m3x4(y[0] * inv, y[1] * inv, y[2] * inv, y[3] * inv);
+        o.y = pack_e4m3x4(y[4] * inv, y[5] * inv, y[6] * inv, y[7] * inv);
+        *reinterpret_cast<uint2*>(yr + c * 256 + lane * 8) = o;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // small per-step / per-image helpers
 // ------------------------------------------------------------------------------------------------

@@ -255,7 +255,7 @@ vcb_gemm_args stream_args(const vcb_flux* f, const StreamView& sv, const uint16_
     g.epilogue = epi;
     g.gate = gate; g.gate_stride = gate_stride; g.res = out; g.ld_res = ldo;
     // the GEMMs that write the residual stream leave the next LayerNorm's statistics behind (bf16 path; H % 64 == 0 always holds)
-    if (epi == VCB_EPI_GATE_RES && out == f->x && !f->fp8) g.row_stats = f->row_stats;
+    if (epi == VCB_EPI_GATE_RES && out == f->x) g.row_stats = f->row_stats;
     g.hidden = f->cfg.hidden; g.q_scale = q_scale; g.k_scale = k_scale; g.rope = f->rope; g.rope_rows = (int64_t)f->B * f->L;
     g.out2 = out2; g.ldo2 = ldo2; g.out2_col_offset = out2_col;
     if (f->fp8 && a_buf == f->xm && w.w8) {
@@ -312,9 +312,12 @@ int stream_ln(const vcb_flux* f, const StreamView& sv, const uint16_t* shift, co
     const int H = f->cfg.hidden;
     if (fp8) {
         vcb_ln_args a{f->x + (int64_t)sv.off * H, f->xm8 + (int64_t)sv.off * H, shift, scale, f->B * sv.rows, sv.rows};
+        if (f->stats_valid)
+            return vcb_ln_modulate_fp8_stats(&a, nullptr, f->row_scale + sv.off, nullptr, f->row_stats + (int64_t)sv.off * (H / 64) * 2, nullptr,
+                                             H / 64, H, H, mod_stride, H, f->L, stream);
         return vcb_ln_modulate_fp8(&a, nullptr, f->row_scale + sv.off, nullptr, H, H, mod_stride, H, f->L, stream);
     }
-    if (f->stats_valid && !f->fp8) {
+    if (f->stats_valid) {
         const int ns = H / 64;
         vcb_ln_args a{f->x + (int64_t)sv.off * H, f->xm + (int64_t)sv.off * H, shift, scale, f->B * sv.rows, sv.rows};
         return vcb_ln_modulate_stats(&a, nullptr, f->row_stats + (int64_t)sv.off * ns * 2, nullptr, ns, H, H, mod_stride, H, f->L, stream);
@@ -331,6 +334,12 @@ int double_ln(const vcb_flux* f, const StreamView* const sv[2], const uint16_t* 
         for (int s = 0; s < 2; ++s)
             a[s] = vcb_ln_args{f->x + (int64_t)sv[s]->off * H, f->xm8 + (int64_t)sv[s]->off * H, mod[s] + mod_col, mod[s] + mod_col + H,
                                f->B * sv[s]->rows, sv[s]->rows};
+        if (f->stats_valid) {
+            const int ns = H / 64;
+            return vcb_ln_modulate_fp8_stats(&a[0], &a[1], f->row_scale + sv[0]->off, f->row_scale + sv[1]->off,
+                                             f->row_stats + (int64_t)sv[0]->off * ns * 2, f->row_stats + (int64_t)sv[1]->off * ns * 2, ns, H, H,
+                                             6 * H, H, f->L, stream);
+        }
         return vcb_ln_modulate_fp8(&a[0], &a[1], f->row_scale + sv[0]->off, f->row_scale + sv[1]->off, H, H, 6 * H, H, f->L, stream);
     }
     for (int s = 0; s < 2; ++s)
@@ -397,7 +406,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
                 g[s] = stream_args(f, *sv[s], f->cat, ldc, 0, H, sw[s]->proj, H, VCB_EPI_GATE_RES, f->x, H, 0, mod[s] + 2 * H, 6 * H,
                                    nullptr, nullptr, nullptr, 0, 0);
             if ((rc = vcb_gemm_bf16_grouped(&g[0], &g[1], stream))) return rc;
-            f->stats_valid = !f->fp8;          // both streams' rows of x now have their LayerNorm statistics in row_stats
+            f->stats_valid = true;             // both streams' rows of x now have their LayerNorm statistics in row_stats
         }
         if ((rc = double_ln(f, sv, mod, 3 * H, stream))) return rc;
         {
@@ -413,7 +422,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
                 g[s] = stream_args(f, *sv[s], f->cat, ldc, H, mlp, sw[s]->mlp2, H, VCB_EPI_GATE_RES, f->x, H, 0, mod[s] + 5 * H, 6 * H,
                                    nullptr, nullptr, nullptr, 0, 0);
             if ((rc = vcb_gemm_bf16_grouped(&g[0], &g[1], stream))) return rc;
-            f->stats_valid = !f->fp8;
+            f->stats_valid = true;
         }
     }
     // ---- single-stream blocks on the joint sequence (layers.py:232-245) ----
@@ -426,7 +435,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
         if ((rc = joint_attention(f, ldc, w.attn_score_bound, stream))) return rc;
         if ((rc = stream_gemm(f, s_all, f->cat, ldc, 0, H + mlp, w.linear2, H, VCB_EPI_GATE_RES, f->x, H, 0, mod + 2 * H, 3 * H,
                               nullptr, nullptr, nullptr, nullptr, 0, 0, stream))) return rc;
-        f->stats_valid = !f->fp8;
+        f->stats_valid = true;
     }
     // ---- final layer on the img rows (layers.py:255-259; chunk order shift, scale) ----
     {

@@ -179,14 +179,22 @@ def ln_modulate_stats(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor,
 
 
 def ln_modulate_fp8(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out8: torch.Tensor, row_scale: torch.Tensor,
-                    rows_per_batch: int, mod_stride: int | None = None, batch_rows: int | None = None) -> torch.Tensor:
-    """e4m3 form of ``ln_modulate``: out8 [rows, H] float8_e4m3fn, row_scale [rows] fp32 (max|y| / 448 per row)."""
+                    rows_per_batch: int, mod_stride: int | None = None, batch_rows: int | None = None,
+                    stats: torch.Tensor | None = None) -> torch.Tensor:
+    """e4m3 form of ``ln_modulate``: out8 [rows, H] float8_e4m3fn, row_scale [rows] fp32 (max|y| / 448 per row).
+    ``stats`` [rows, n_slots, 2] fp32: row statistics supplied by the producing GEMM (vcb_ln_modulate_fp8_stats)."""
     _req(x, BF16, "x"); _req(out8, torch.float8_e4m3fn, "out8"); _req(row_scale, torch.float32, "row_scale")
     _req(shift, BF16, "shift"); _req(scale, BF16, "scale")
     rows, H = x.shape
     a = _lib.LnArgs()
     a.x, a.y, a.shift, a.scale, a.rows, a.rows_per_batch = x.data_ptr(), out8.data_ptr(), shift.data_ptr(), scale.data_ptr(), rows, rows_per_batch
     ms = mod_stride if mod_stride is not None else (shift.stride(0) if shift.dim() > 1 else 0)
+    if stats is not None:
+        _req(stats, torch.float32, "stats")
+        check(_lib.lib().vcb_ln_modulate_fp8_stats(C.byref(a), None, row_scale.data_ptr(), None, stats.data_ptr(), None, stats.shape[1],
+                                                   x.stride(0), out8.stride(0), ms, H, batch_rows or rows_per_batch, _stream()),
+              "vcb_ln_modulate_fp8_stats")
+        return out8
     check(_lib.lib().vcb_ln_modulate_fp8(C.byref(a), None, row_scale.data_ptr(), None, x.stride(0), out8.stride(0), ms, H,
                                          batch_rows or rows_per_batch, _stream()), "vcb_ln_modulate_fp8")
     return out8
