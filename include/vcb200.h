@@ -152,6 +152,9 @@ typedef struct vcb_attn_args {
     int32_t schedule;            /* VCB_ATTN_SCHED_* ; 0 = auto */
 } vcb_attn_args;
 int vcb_attention_fwd_ex(const vcb_attn_args* args, void* stream);
+/* debug aid (environment VCB_ATTN4_TIMELINE=1): per-CTA globaltimer stamps [grid][66] (start, end of every segment) of the most
+ * recent persistent attention launch; synchronises the device; returns the grid size or -1 */
+int vcb_debug_attn4_timeline(unsigned long long* out, int32_t capacity);
 
 /* ---- AdaLN modulated LayerNorm (layers.py:163-164,191,195,234,257):
  *      y = bf16( bf16(1 + scale[b]) * LayerNorm(x) + shift[b] ), eps 1e-6, no affine; hidden % 256 == 0.

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "vcb_last_error": (C.c_char_p, []),
     "vcb_launch_count": (C.c_longlong, []),
     "vcb_reset_launch_count": (None, []),
+    "vcb_debug_attn4_timeline": (C.c_int, [C.c_void_p, C.c_int32]),
     "vcb_profile_begin": (C.c_int, []),
     "vcb_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "vcb_profile_end_ex": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int32, C.c_void_p, C.c_int64,

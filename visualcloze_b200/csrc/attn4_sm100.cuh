@@ -31,6 +31,8 @@ struct AttnSkParams {
     float* ws;          // [gridDim.x][kAttn4SlotFloats]
     int* flags;         // [gridDim.x]
     int epoch;          // value that marks "this launch's partial is ready"
+    int no_split;       // experiment switch: deal the units of the partial last round out whole (no key-tile split, no partials)
+    unsigned long long* timeline;   // optional [gridDim.x][kAttn4MaxSegs + 2] globaltimer stamps: start, end of every segment (debug)
 };
 
 // Schedule.  Units (sample, head, query pair) in that order; n_units = samples * heads * pairs.
@@ -44,12 +46,13 @@ struct AttnSched {
     int n_pairs, n_kv, n_units, G;
     int R, rem, G2;
     long long U;                                   // key-tile steps of phase 2
-    VCB_DEVICE void init(int n_heads, int n_qt, int grid) {
+    VCB_DEVICE void init(int n_heads, int n_qt, int grid, int no_split = 0) {
         n_pairs = (n_qt + 1) / 2; n_kv = n_qt; n_units = n_heads * n_pairs; G = grid;
         R = n_units / G; rem = n_units - R * G;
         U = (long long)rem * n_kv;
         const long long g2 = U / 4;
         G2 = rem == 0 ? 0 : (int)(g2 < 1 ? 1 : (g2 < G ? g2 : G));
+        if (no_split && rem > 0) G2 = rem;             // one whole unit per CTA c < rem: boundary(c) = c * n_kv
     }
     // start of CTA c's phase-2 range (c == G2: the end of the space)
     VCB_DEVICE void boundary(int c, int& unit, int& kv) const {
@@ -96,7 +99,31 @@ struct AttnSegIter {
 struct AttnSegEntry { int b, head, q0, kv0, kv1, tile1, n_parts, unit; };
 static_assert(sizeof(AttnSegEntry) == 32, "segment entry");
 
+// CTA `cta`'s segment list -> shared memory; returns the count.  Out of line on purpose: its locals (iterator structs, 64-bit schedule
+// arithmetic) get their own stack frame instead of forcing one on the kernel.
+__device__ __noinline__ int attn4_build_segments(const AttnSched& sched, int cta, int heads, int seqlen, AttnSegEntry* segs) {
+    AttnSegIter it(sched, cta);
+    AttnSeg g;
+    int n = 0;
+    while (n < kAttn4MaxSegs && it.next(g)) {
+        AttnSegEntry e;
+        const int hi = g.unit / sched.n_pairs;
+        e.b = hi / heads;
+        e.head = hi - e.b * heads;
+        e.q0 = (g.unit - hi * sched.n_pairs) * 2 * kAttnTile;
+        e.kv0 = g.kv0; e.kv1 = g.kv1; e.unit = g.unit; e.n_parts = g.n_parts;
+        e.tile1 = (e.q0 + kAttnTile) < seqlen ? 1 : 0;
+        segs[n++] = e;
+    }
+    return n;
+}
+
 // mbarrier wait with a watchdog: ~seconds of failed try_waits trap the kernel instead of hanging the GPU box
+VCB_DEVICE unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 VCB_DEVICE void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -118,7 +145,7 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
 
     const int n_qt = (p.L + kAttnTile - 1) / kAttnTile;
     AttnSched sched;
-    sched.init(p.B * p.H, n_qt, G);
+    sched.init(p.B * p.H, n_qt, G, skp.no_split);
     const int n_kv_all = sched.n_kv;
     const int seqlen = p.L;
 
@@ -142,22 +169,7 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     AttnSegEntry* segs = reinterpret_cast<AttnSegEntry*>(smem + (2 + kAttn3Slots) * kSlotBytes + 256 + 8192);
     int* n_segs_smem = reinterpret_cast<int*>(tmem_slot + 1);
 
-    if (warp == 2 && lane == 0) {
-        AttnSegIter it(sched, cta);
-        AttnSeg g;
-        int n = 0;
-        while (n < kAttn4MaxSegs && it.next(g)) {
-            AttnSegEntry e;
-            const int hi = g.unit / sched.n_pairs;
-            e.b = hi / p.H;
-            e.head = hi - e.b * p.H;
-            e.q0 = (g.unit - hi * sched.n_pairs) * 2 * kAttnTile;
-            e.kv0 = g.kv0; e.kv1 = g.kv1; e.unit = g.unit; e.n_parts = g.n_parts;
-            e.tile1 = (e.q0 + kAttnTile) < seqlen ? 1 : 0;
-            segs[n++] = e;
-        }
-        *n_segs_smem = n;
-    }
+    if (warp == 2 && lane == 0) *n_segs_smem = attn4_build_segments(sched, cta, p.H, seqlen, segs);
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_qkv);
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
@@ -179,15 +191,15 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     pdl_wait();
 
     const int n_segs = *n_segs_smem;
+    if (skp.timeline != nullptr && warp == 2 && lane == 0) skp.timeline[(long long)cta * (kAttn4MaxSegs + 2)] = globaltimer_ns();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int seq = 0;
             for (int segn = 0; segn < n_segs; ++segn) {
-                const AttnSegEntry g = segs[segn];
-                const int b = g.b, head = g.head, q0 = g.q0;
-                const bool tile1 = g.tile1 != 0;
+                const int b = segs[segn].b, head = segs[segn].head, q0 = segs[segn].q0, kv0 = segs[segn].kv0, kv1 = segs[segn].kv1;
+                const bool tile1 = segs[segn].tile1 != 0;
                 if (segn > 0) mbar_wait_wd(q_empty, (uint32_t)(segn - 1) & 1u);
                 const int ntile = tile1 ? 2 : 1;
                 mbar_expect_tx(q_full, kSlotBytes * ntile);
@@ -196,10 +208,10 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                     tma_load_3d<false>(&tmap_qkv, q_full, smem_q + t * kSlotBytes + kSlotBytes / 2, p.q_col + head * 128 + 64,
                                        q0 + t * kAttnTile, b, kEvictFirst);
                 }
-                for (int e = 0; e < 2 * (g.kv1 - g.kv0); ++e, ++seq) {       // K V K V ...
+                for (int e = 0; e < 2 * (kv1 - kv0); ++e, ++seq) {       // K V K V ...
                     const int slot = seq % kAttn3Slots;
                     const uint32_t ph = (uint32_t)(seq / kAttn3Slots) & 1u;
-                    const int j = g.kv0 + (e >> 1);
+                    const int j = kv0 + (e >> 1);
                     const int col = ((e & 1) ? p.v_col : p.k_col) + head * 128;
                     mbar_wait_wd(&kv_empty[slot], ph ^ 1);
                     mbar_expect_tx(&kv_full[slot], kSlotBytes);
@@ -235,10 +247,12 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
             }
             __syncwarp();
         };
-        auto issue_pv = [&](int t, int seq, bool first, int& steps) {   // O_t (+)= P_t V, V in ring entry `seq`; first: overwrite O_t
+        // O_t (+)= P_t V, V in ring entry `seq`; first: overwrite O_t; par: parity of tile t's running step (plain values only:
+        // anything address-taken here lands in local memory, and with the whole L1 carved out as shared memory a local load is an L2
+        // round trip on the S -> P -> PV critical path -- ncu showed 63 K of them and a 20 % slower key-tile step)
+        auto issue_pv = [&](int t, int seq, bool first, uint32_t par) {
             const uint32_t va = smem_u32(smem_kv + slot_of(seq) * kSlotBytes);
             const uint64_t vd = make_smem_desc(va, kSlotBytes / 2, 1024, kSwizzle128B);
-            const uint32_t par = (uint32_t)steps & 1u;
 #pragma unroll
             for (int c = 0; c < kPC; ++c) {
                 mbar_wait_wd(&p_full[kPC * t + c], par);
@@ -255,12 +269,10 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 }
                 __syncwarp();
             }
-            ++steps;
         };
         for (int segn = 0; segn < n_segs; ++segn) {
-            const AttnSegEntry g = segs[segn];
-            const bool tile1 = g.tile1 != 0;
-            const int n = g.kv1 - g.kv0;
+            const bool tile1 = segs[segn].tile1 != 0;
+            const int n = segs[segn].kv1 - segs[segn].kv0;
             mbar_wait_wd(q_full, (uint32_t)segn & 1u);
             tc_fence_after();
             wait_kv(base);
@@ -276,11 +288,13 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 const int ev = base + 2 * jj + 1, ek = base + 2 * jj + 2;
                 wait_kv(ev);                                      // V
                 if (jj == 0 && segc0 > 0) { mbar_wait_wd(&o_free[0], (uint32_t)(segc0 - 1) & 1u); tc_fence_after(); }
-                issue_pv(0, ev, jj == 0, steps0);
+                issue_pv(0, ev, jj == 0, (uint32_t)steps0 & 1u);
+                ++steps0;
                 if (more) { wait_kv(ek); issue_qk(0, ek); }
                 if (tile1) {
                     if (jj == 0 && segc1 > 0) { mbar_wait_wd(&o_free[1], (uint32_t)(segc1 - 1) & 1u); tc_fence_after(); }
-                    issue_pv(1, ev, jj == 0, steps1);
+                    issue_pv(1, ev, jj == 0, (uint32_t)steps1 & 1u);
+                    ++steps1;
                 }
                 if (elect_one()) umma_commit<1>(&kv_empty[slot_of(ev)]);      // V free once both PVs have run
                 __syncwarp();
@@ -402,9 +416,8 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 // ---------------- segment epilogue ----------------
                 mbar_wait_wd(&o_done[t], (uint32_t)(step - 1) & 1u);
                 tc_fence_after();
-                const AttnSegEntry g = segs[segn];
-                const int b = g.b, head = g.head;
-                const int row = g.q0 + t * kAttnTile + rit;
+                const int b = segs[segn].b, head = segs[segn].head;
+                const int row = segs[segn].q0 + t * kAttnTile + rit;
                 const bool finaliser_partial = !contributor && kv1 < n_kv_all;
                 float* my_slot = skp.ws + (long long)cta * kAttn4SlotFloats;
                 if (contributor) {
@@ -431,7 +444,7 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                     // empty: the host sizes the grid so that every CTA owns >= 8 half-iterations)
                     float a_own = 1.0f;
                     [[maybe_unused]] float m_fin = m_run;
-                    const int n_parts = finaliser_partial ? g.n_parts : 0;
+                    const int n_parts = finaliser_partial ? segs[segn].n_parts : 0;
                     if (n_parts > 0) {
                         if (lane == 0) {
                             for (int pc = cta + 1; pc <= cta + n_parts; ++pc) {
@@ -512,6 +525,8 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 named_bar_sync(9, 512);
                 if (warp == 2 && lane == 0) st_release_gpu(skp.flags + cta, skp.epoch);
             }
+            if (skp.timeline != nullptr && warp == 2 && lane == 0)
+                skp.timeline[(long long)cta * (kAttn4MaxSegs + 2) + 1 + segn] = globaltimer_ns();
         }
         __syncwarp();
     }

@@ -390,7 +390,8 @@ extern "C" int vcb_conv3x3_nhwc(const void* x, const void* w, const float* bias,
 namespace {
 // workspace of the persistent attention kernel (attn4): one (O, l, m) slot and one flag per CTA, per stream; allocated on
 // first use (call once before CUDA-graph capture)
-struct AttnScratch { float* ws = nullptr; int* flags = nullptr; int epoch = 0; };
+struct AttnScratch { float* ws = nullptr; int* flags = nullptr; int epoch = 0; unsigned long long* timeline = nullptr; int last_grid = 0; };
+AttnScratch* g_last_attn_scratch = nullptr;       // debug: the scratch of the most recent persistent launch (vcb_debug_attn4_timeline)
 inline AttnScratch* attn_scratch(cudaStream_t st) {
     static std::mutex mu;
     static std::map<cudaStream_t, AttnScratch> pool;
@@ -401,6 +402,8 @@ inline AttnScratch* attn_scratch(cudaStream_t st) {
         if (cudaMalloc(&s.ws, n * kAttn4SlotFloats * sizeof(float)) != cudaSuccess) return nullptr;
         if (cudaMalloc(&s.flags, n * sizeof(int)) != cudaSuccess) return nullptr;
         cudaMemset(s.flags, 0, n * sizeof(int));
+        static const bool tl = [] { const char* e = getenv("VCB_ATTN4_TIMELINE"); return e && atoi(e); }();
+        if (tl && cudaMalloc(&s.timeline, n * (kAttn4MaxSegs + 2) * sizeof(unsigned long long)) != cudaSuccess) s.timeline = nullptr;
     }
     return &s;
 }
@@ -482,7 +485,11 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
         prof.set_info(3, (fixed ? 1 : 0) | 2);
         AttnScratch* sc = attn_scratch((cudaStream_t)stream);
         if (!sc) return set_error("attention: workspace allocation failed");
-        AttnSkParams skp{sc->ws, sc->flags, ++sc->epoch};
+        static const int no_split = [] { const char* e = getenv("VCB_ATTN4_NOSPLIT"); return (e && atoi(e)) ? 1 : 0; }();
+        AttnSkParams skp{sc->ws, sc->flags, ++sc->epoch, no_split, sc->timeline};
+        if (sc->timeline) cudaMemsetAsync(sc->timeline, 0, 160 * (kAttn4MaxSegs + 2) * sizeof(unsigned long long), (cudaStream_t)stream);
+        sc->last_grid = grid;
+        g_last_attn_scratch = sc;
         cudaError_t e = fixed ? launch_pdl(attn_fwd4_tcgen05_kernel<true>, dim3(grid), dim3(kAttn3Threads), (size_t)kAttn4SmemBytes, (cudaStream_t)stream, 1, tm, p, skp)
                               : launch_pdl(attn_fwd4_tcgen05_kernel<false>, dim3(grid), dim3(kAttn3Threads), (size_t)kAttn4SmemBytes, (cudaStream_t)stream, 1, tm, p, skp);
         if (e != cudaSuccess) return set_error("attention (persistent) launch: %s", cudaGetErrorString(e));
@@ -512,6 +519,18 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
     }
 }
 }  // namespace
+
+// debug (VCB_ATTN4_TIMELINE=1): per-CTA globaltimer stamps of the most recent persistent attention launch -- [grid][kAttn4MaxSegs + 2]
+// = start, end of every segment (0 = unused).  Synchronises the device.  Returns the grid size, or -1.
+extern "C" int vcb_debug_attn4_timeline(unsigned long long* out, int32_t capacity) {
+    AttnScratch* sc = g_last_attn_scratch;
+    if (!sc || !sc->timeline || !out) return -1;
+    cudaDeviceSynchronize();
+    const int n = sc->last_grid * (kAttn4MaxSegs + 2);
+    if (capacity < n) return -1;
+    if (cudaMemcpy(out, sc->timeline, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return sc->last_grid;
+}
 
 extern "C" int vcb_attention_fwd(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_col, int32_t v_col,
                                  const int32_t* seqlens, int32_t B, int32_t L, int32_t heads, void* out, int64_t ldo,
