@@ -124,7 +124,12 @@ VCB_DEVICE unsigned long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+// Segment-level waits only (q_full / q_empty / o_free): the per-key-tile waits use the plain mbar_wait.  ncu (source page) of the
+// first version, where EVERY wait was this loop: the compiler put a YIELD in front of each try_wait, a failed attempt then returned
+// after ~70 ns instead of parking the warp, and the s_full wait alone executed 4.4 M try_waits per launch (24 per key-tile step and
+// warp) against 0.18 M in the per-pair kernel.
 VCB_DEVICE void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) __trap();
@@ -213,7 +218,7 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                     const uint32_t ph = (uint32_t)(seq / kAttn3Slots) & 1u;
                     const int j = kv0 + (e >> 1);
                     const int col = ((e & 1) ? p.v_col : p.k_col) + head * 128;
-                    mbar_wait_wd(&kv_empty[slot], ph ^ 1);
+                    mbar_wait(&kv_empty[slot], ph ^ 1);
                     mbar_expect_tx(&kv_full[slot], kSlotBytes);
                     uint8_t* dst = smem_kv + slot * kSlotBytes;
                     tma_load_3d<false>(&tmap_qkv, &kv_full[slot], dst, col, j * kAttnTile, b, kEvictLast);
@@ -231,7 +236,7 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         int segc0 = 0, segc1 = 0;           // segments in which the tile was active (parity of o_free)
         auto slot_of = [](int seq) { return seq % kAttn3Slots; };
         auto wait_kv = [&](int seq) {
-            mbar_wait_wd(&kv_full[slot_of(seq)], (uint32_t)(seq / kAttn3Slots) & 1u);
+            mbar_wait(&kv_full[slot_of(seq)], (uint32_t)(seq / kAttn3Slots) & 1u);
             tc_fence_after();
         };
         auto issue_qk = [&](int t, int seq) {                  // S_t = Q_t K^T, K in ring entry `seq`
@@ -255,7 +260,7 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
             const uint64_t vd = make_smem_desc(va, kSlotBytes / 2, 1024, kSwizzle128B);
 #pragma unroll
             for (int c = 0; c < kPC; ++c) {
-                mbar_wait_wd(&p_full[kPC * t + c], par);
+                mbar_wait(&p_full[kPC * t + c], par);
                 tc_fence_after();
                 if (elect_one()) {
                     constexpr int kPer = kCW / 16;
@@ -333,10 +338,12 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
             if (active) {
                 [[maybe_unused]] float m_run = -INFINITY;
                 float l_run = 0.f;
-                for (int j = kv0; j < kv1; ++j, ++step) {
-                    mbar_wait_wd(&s_full[t], (uint32_t)step & 1u);
+                // loop state kept minimal (the kernel sits at the 96-register cap: a spilled loop constant is a local load -- an L2
+                // round trip with L1 carved out as shared memory -- between s_full and the first tcgen05.ld of EVERY step)
+                int kv_left = seqlen - kv0 * kAttnTile - half * 64;             // my columns >= kv_left are padding
+                for (int n_left = kv1 - kv0; n_left > 0; --n_left, ++step, kv_left -= kAttnTile) {
+                    mbar_wait(&s_full[t], (uint32_t)step & 1u);
                     tc_fence_after();
-                    const int kv_left = seqlen - j * kAttnTile - half * 64;     // my columns >= kv_left are padding
                     float m_new = p.fixed_max;
                     if constexpr (!kFixed) {
                         float m_tile = -INFINITY;
@@ -360,8 +367,8 @@ attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                         const bool grow = (m_tile - m_run) > kRescaleThreshold;
                         m_new = grow ? m_tile : m_run;
                         const float alpha = grow ? ex2_approx(m_run - m_new) : 1.0f;
-                        if (j > kv0 && __any_sync(0xffffffffu, grow)) {
-                            mbar_wait_wd(&o_done[t], (uint32_t)(step - 1) & 1u);
+                        if (n_left != kv1 - kv0 && __any_sync(0xffffffffu, grow)) {
+                            mbar_wait(&o_done[t], (uint32_t)(step - 1) & 1u);
                             tc_fence_after();
 #pragma unroll 1
                             for (int c = 0; c < 2; ++c) {
