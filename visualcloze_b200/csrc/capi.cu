@@ -473,10 +473,11 @@ int attention_launch(const void* qkv, int64_t ld_qkv, int32_t q_col, int32_t k_c
     // short sequences) use the per-pair grid
     // sequence-parallel routing: the persistent kernel stores O rows straight through the peer-mapped pointers (no TMA staging).
     // Few heads per rank leave the per-pair grid far below one wave (cfg B: 96 CTAs at 4 ranks, 48 at 8) and these ranks are not
-    // power-capped, so there the split tail pays: used when the per-pair grid would fill < 70 % of the SMs (measured equal at 2
-    // ranks = 192 CTAs, where the staged-TMA kernel stays).  VCB_SP_ATTN_PERSIST=0 / 1 forces it off / on.
+    // power-capped.  The split costs ~20 us per launch (partial dump, fold, phase hand-over; tools/attn4_timeline.py), so it
+    // pays only when the per-pair grid would fill < 40 % of the SMs (8 ranks); measured equal at 2 ranks and at 96 CTAs.
+    // VCB_SP_ATTN_PERSIST=0 / 1 forces it off / on.
     static const int sp_persist_env = [] { const char* e = getenv("VCB_SP_ATTN_PERSIST"); return e ? (atoi(e) ? 1 : 0) : -1; }();
-    const bool sp_persist = out_peers && (sp_persist_env >= 0 ? sp_persist_env == 1 : n_units * 10 < (long long)num_sms() * 7);
+    const bool sp_persist = out_peers && (sp_persist_env >= 0 ? sp_persist_env == 1 : n_units * 10 < (long long)num_sms() * 4);
     const bool persist_ok = !seqlens && (!out_peers || sp_persist) && num_sms() <= 160 && n_units / pgrid + 4 <= kAttn4MaxSegs;
     if (schedule == VCB_ATTN_SCHED_PERSISTENT && !persist_ok)
         return set_error("attention: the persistent schedule takes unpadded batches (seqlens == NULL), no sequence-parallel routing");
