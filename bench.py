@@ -256,8 +256,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=5))   # a stuck rank ends the run, not the lease
     from visualcloze_b200 import _lib, model as M, transport as T
     lib = _lib.lib()
     with torch.device(dev):
