@@ -10,9 +10,9 @@ echo "| mnemonic | count | meaning |"
 echo "|---|---|---|"
 SASS=$(mktemp)
 cuobjdump -sass "$SO" > "$SASS"
-row() { printf '| `%s` | %s | %s |\n' "$1" "$(grep -cE -- "(^|[^A-Z.])$1" "$SASS")" "$2"; }
+row() { printf '| `%s` | %s | %s |\n' "${3:-$1}" "$(grep -cE -- "(^|[^A-Z.])$1" "$SASS")" "$2"; }
 row "UTCHMMA" "tcgen05.mma (all kinds, incl. the .2CTA forms)"
-row "UTCHMMA\.2CTA" "tcgen05.mma cta_group::2 (CTA-pair tiles)"
+row "UTCHMMA\.2CTA" "tcgen05.mma cta_group::2 (CTA-pair tiles)" "UTCHMMA.2CTA"
 row "UTCQMMA" "tcgen05.mma kind::f8f6f4 (e4m3 operands of the opt-in fp8 projections)"
 row "LDTM" "tcgen05.ld (TMEM -> registers)"
 row "STTM" "tcgen05.st (registers -> TMEM: P of the attention kernel, stream-K folds)"
