@@ -136,15 +136,33 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # CPU port of the reference (oracle) on a bounded sample
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(workload: str, threads: int):
+def host_threads() -> int:
+    """Threads this process may really use: the affinity mask, capped by the cgroup CPU quota (a container on a 128-thread
+    host often owns far fewer; asking torch for all 128 then oversubscribes and slows the CPU arm several-fold)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, math.ceil(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+def cpu_reference_sample(workload: str, threads=None):
     """Times 1 DoubleStreamBlock + 1 SingleStreamBlock of the reference at full width on the workload's token count and
     extrapolates to one image (x 19 / x 38 blocks x NFE; embedders, final layer and the VAE decode -- together < 0.5 % of the
     image's FLOPs, SURVEY.md 8 -- are not in the sample).  Preferred: the UNMODIFIED reference modules from oracle/_ref under
-    ``torch.autocast("cpu", bf16)`` (kind "reference"); fallback: the restated oracle (kind "port")."""
+    ``torch.autocast("cpu", bf16)`` (kind "reference"); fallback: the restated oracle (kind "port").
+
+    ``threads`` = None tries host_threads() and its halves down to 1/8 (>= 4), each once after a warm-up pass, and reports the
+    FASTEST -- the reference arm gets the thread count that suits it, not a blind os.cpu_count()."""
     import contextlib
     from oracle import flux_oracle as fo
     from oracle import ref_runner as rr
-    torch.set_num_threads(threads)
     gh, gw, res, num_steps, *_ = WORKLOADS[workload]
     cfg = fo.FluxConfig(depth=1, depth_single_blocks=1, lora_rank=256)
     H = cfg.hidden_size
@@ -182,21 +200,49 @@ def cpu_reference_sample(workload: str, threads: int):
         cos, sin = fo.rope_table(ids, cfg.axes_dim, cfg.theta)
         nm = fo.Numerics("cuda_bf16")
         ctx = contextlib.nullcontext()
-    with torch.no_grad(), ctx:
-        t0 = time.perf_counter()
-        if kind == "reference":
-            img2, txt2 = dbl(img=img, txt=txt, vec=vec, pe=pe, img_mask=mask[:, Lt:], txt_mask=mask[:, :Lt])
-        else:
-            img2, txt2 = fo.double_block(p, 0, cfg, img, txt, vec, cos, sin, mask, nm, 1.0)
-        t1 = time.perf_counter()
-        if kind == "reference":
-            sgl(torch.cat((txt2, img2), 1), vec=vec, pe=pe, attn_mask=mask)
-        else:
-            fo.single_block(p, 0, cfg, torch.cat((txt2, img2), 1), vec, cos, sin, mask, nm, 1.0)
-        t2 = time.perf_counter()
+
+    def one_pass():
+        with torch.no_grad(), ctx:
+            t0 = time.perf_counter()
+            if kind == "reference":
+                img2, txt2 = dbl(img=img, txt=txt, vec=vec, pe=pe, img_mask=mask[:, Lt:], txt_mask=mask[:, :Lt])
+            else:
+                img2, txt2 = fo.double_block(p, 0, cfg, img, txt, vec, cos, sin, mask, nm, 1.0)
+            t1 = time.perf_counter()
+            if kind == "reference":
+                sgl(torch.cat((txt2, img2), 1), vec=vec, pe=pe, attn_mask=mask)
+            else:
+                fo.single_block(p, 0, cfg, torch.cat((txt2, img2), 1), vec, cos, sin, mask, nm, 1.0)
+            t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
     nfe = num_steps - 1
-    sec_per_image = nfe * (19 * (t1 - t0) + 38 * (t2 - t1))
-    return 1.0 / sec_per_image, dict(double_block_s=t1 - t0, single_block_s=t2 - t1, tokens=L, kind=kind)
+    if threads is None:
+        top = host_threads()
+        cands = sorted({max(4, top >> s) if top >= 4 else top for s in range(4)}, reverse=True)
+    else:
+        cands = [int(threads)]
+    tried, best = {}, None
+    for n in cands:
+        torch.set_num_threads(n)
+        one_pass()                                   # warm-up at this thread count (thread pool, allocator, oneDNN primitives)
+        td, ts = one_pass()
+        sec = nfe * (19 * td + 38 * ts)
+        tried[n] = round(sec, 1)
+        if best is None or sec < best[0]:
+            best = (sec, n, td, ts)
+    sec, n, td, ts = best
+    return 1.0 / sec, dict(double_block_s=td, single_block_s=ts, tokens=L, kind=kind, threads=n, host_threads=host_threads(),
+                           tried_threads_sec_per_image=tried)
+
+
+def cpu_sample_text(info: dict, nfe: int) -> str:
+    what = ("UNMODIFIED reference modules from oracle/_ref, autocast cpu bf16, SDPA attention" if info["kind"] == "reference"
+            else "restated oracle")
+    return (f"1 DoubleStreamBlock + 1 SingleStreamBlock ({what}, un-merged LoRA r=256) at hidden 3072 on {info['tokens']} tokens: "
+            f"{info['double_block_s']:.2f}s + {info['single_block_s']:.2f}s on {info['threads']} threads (fastest of the thread counts tried, "
+            f"s/image: {info['tried_threads_sec_per_image']}; the process may use {info['host_threads']}), extrapolated x(19,38) blocks x {nfe} "
+            "evaluations; embedders / final layer / VAE decode (< 0.5 % of the image's FLOPs) not in the sample; each timed once after a warm-up pass")
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -232,16 +278,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cores = os.cpu_count() or 1
-        # one bounded sample per group: one warm-up sample (thread pools, allocator), ONE timed sample -- the result is an
-        # extrapolation of two block timings, repeating it --steps times would only multiply ~25 s of host time
-        if args.warmup > 0:
-            cpu_reference_sample(args.workload, cores)
-        v, info = cpu_reference_sample(args.workload, cores)
-        sample = f"1 DoubleStreamBlock + 1 SingleStreamBlock ({'UNMODIFIED reference modules from oracle/_ref, autocast cpu bf16, SDPA attention' if info['kind'] == 'reference' else 'restated oracle'}, " \
-                 f"un-merged LoRA r=256) at hidden 3072 on {info['tokens']} tokens: {info['double_block_s']:.2f}s + {info['single_block_s']:.2f}s, " \
-                 f"extrapolated x(19,38) blocks x {nfe} evaluations; embedders / final layer / VAE decode (< 0.5 % of the image's FLOPs) not in the sample; " \
-                 "timed once after one warm-up sample"
+        # one bounded sample per group (the result is an extrapolation of two block timings; repeating it --steps times would
+        # only multiply the host time): per thread count one warm-up pass and ONE timed pass, the fastest count is reported
+        v, info = cpu_reference_sample(args.workload)
+        cores = info["threads"]
+        sample = cpu_sample_text(info, nfe)
         print(json.dumps({"impl": "reference", "metric": "images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
@@ -468,12 +509,9 @@ def main():
     if sp_extra is not None:
         out["extra"]["sp"] = sp_extra
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        v, info = cpu_reference_sample(args.workload, cores)
-        out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": info["kind"],
-                               "sample": "1 DoubleStreamBlock + 1 SingleStreamBlock (" + ("UNMODIFIED reference modules from oracle/_ref, autocast cpu bf16" if info["kind"] == "reference" else "restated oracle") +
-                                         f", un-merged LoRA r=256) at hidden 3072 on {info['tokens']} tokens: {info['double_block_s']:.2f}s + {info['single_block_s']:.2f}s, "
-                                         f"extrapolated x(19,38) blocks x {nfe} evaluations; embedders / final layer / VAE decode (< 0.5 % of the FLOPs) not in the sample"}
+        v, info = cpu_reference_sample(args.workload)
+        out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": info["threads"], "kind": info["kind"],
+                               "sample": cpu_sample_text(info, nfe)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -1,12 +1,12 @@
 """Materialise ``oracle/_ref/`` -- the UNMODIFIED reference modules of the hot path, importable on the GPU box.
 
 TEST INFRASTRUCTURE ONLY.  ``/root/reference`` exists in the build container and not on the GPU box; the reference is pure
-Python (nothing to compile), so "building" it means placing byte-identical copies of the packages the path
-needs where a ``gpurun`` snapshot carries them:
+Python (nothing to compile), so "building" it means packing the packages the path needs, byte for byte, into one
+build artefact that a ``gpurun`` snapshot carries (the Python analogue of the ``.so`` a compiled reference would yield):
 
-    oracle/_ref/models/**      <- /root/reference/models/**        (model.py, math.py, sampling.py, modules/*)
-    oracle/_ref/transport/**   <- /root/reference/transport/**
-    oracle/_ref/MANIFEST.json  sha256 of every copied file (``verify()`` re-hashes them: the copies must stay unmodified)
+    oracle/_ref/reference_modules.zip   members models/** and transport/** of /root/reference (model.py, math.py, sampling.py,
+                                        modules/*, transport/*), imported straight from the archive (zipimport)
+    oracle/_ref/MANIFEST.json           sha256 of every member (``verify()`` re-hashes them: they must stay unmodified)
 
 plus two third-party stand-ins that are absent from the image (written by THIS script, not reference code):
 
@@ -23,10 +23,12 @@ import hashlib
 import json
 import os
 import shutil
+import zipfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference"
 DST = os.path.join(HERE, "_ref")
+ARCHIVE = os.path.join(DST, "reference_modules.zip")
 PACKAGES = ("models", "transport")
 
 _IMWATERMARK = '''"""Stand-in for the absent third-party `imwatermark` (written by oracle/build_ref.py; models/util.py:7 imports it)."""
@@ -70,55 +72,57 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
 '''
 
 
-def _sha(path: str) -> str:
-    h = hashlib.sha256()
-    with open(path, "rb") as f:
-        h.update(f.read())
-    return h.hexdigest()
+def _sha_bytes(data: bytes) -> str:
+    return hashlib.sha256(data).hexdigest()
 
 
 def build(force: bool = False) -> bool:
-    """Returns True when oracle/_ref is in place (freshly copied or already present), False when there is no reference here."""
+    """Returns True when oracle/_ref is in place (freshly packed or already present), False when there is no reference here."""
     if not os.path.isdir(REF_SRC):
-        return os.path.exists(os.path.join(DST, "MANIFEST.json"))
+        return os.path.exists(os.path.join(DST, "MANIFEST.json")) and os.path.exists(ARCHIVE)
     if os.path.isdir(DST) and not force:
         try:
             if verify(against_source=True):
                 return True
-        except Exception:  # noqa: BLE001  (stale or partial copy: rebuild)
+        except Exception:  # noqa: BLE001  (stale or partial artefact: rebuild)
             pass
     shutil.rmtree(DST, ignore_errors=True)
     os.makedirs(DST)
     manifest = {}
-    for pkg in PACKAGES:
-        for root, dirs, files in os.walk(os.path.join(REF_SRC, pkg)):
-            dirs[:] = [d for d in dirs if d != "__pycache__"]
-            for fn in files:
-                if not fn.endswith(".py"):
-                    continue
-                src = os.path.join(root, fn)
-                rel = os.path.relpath(src, REF_SRC)
-                dst = os.path.join(DST, rel)
-                os.makedirs(os.path.dirname(dst), exist_ok=True)
-                shutil.copyfile(src, dst)
-                manifest[rel] = _sha(dst)
+    with zipfile.ZipFile(ARCHIVE, "w", compression=zipfile.ZIP_DEFLATED) as z:
+        for pkg in PACKAGES:
+            for root, dirs, files in os.walk(os.path.join(REF_SRC, pkg)):
+                dirs[:] = sorted(d for d in dirs if d != "__pycache__")
+                # explicit directory members: models/modules has no __init__.py and zipimport finds namespace packages by them
+                z.writestr(zipfile.ZipInfo(os.path.relpath(root, REF_SRC) + "/", date_time=(2020, 1, 1, 0, 0, 0)), b"")
+                for fn in sorted(files):
+                    if not fn.endswith(".py"):
+                        continue
+                    src = os.path.join(root, fn)
+                    rel = os.path.relpath(src, REF_SRC)
+                    data = open(src, "rb").read()
+                    z.writestr(zipfile.ZipInfo(rel, date_time=(2020, 1, 1, 0, 0, 0)), data)
+                    manifest[rel] = _sha_bytes(data)
     with open(os.path.join(DST, "imwatermark.py"), "w") as f:
         f.write(_IMWATERMARK)
     with open(os.path.join(DST, "torchdiffeq.py"), "w") as f:
         f.write(_TORCHDIFFEQ)
     with open(os.path.join(DST, "MANIFEST.json"), "w") as f:
-        json.dump({"source": REF_SRC, "files": manifest, "stand_ins": ["imwatermark.py", "torchdiffeq.py"]}, f, indent=1, sort_keys=True)
+        json.dump({"source": REF_SRC, "archive": os.path.basename(ARCHIVE), "files": manifest, "stand_ins": ["imwatermark.py", "torchdiffeq.py"]},
+                  f, indent=1, sort_keys=True)
     return True
 
 
 def verify(against_source: bool = False) -> bool:
-    """Every copied file still has the hash recorded at copy time (and, in the build container, equals the source)."""
+    """Every archive member still has the hash recorded at packing time (and, in the build container, equals the source)."""
     man = json.load(open(os.path.join(DST, "MANIFEST.json")))
-    for rel, sha in man["files"].items():
-        if _sha(os.path.join(DST, rel)) != sha:
-            raise RuntimeError(f"oracle/_ref/{rel} was modified after the copy")
-        if against_source and os.path.isdir(REF_SRC) and _sha(os.path.join(REF_SRC, rel)) != sha:
-            raise RuntimeError(f"oracle/_ref/{rel} differs from {REF_SRC}/{rel}")
+    with zipfile.ZipFile(ARCHIVE) as z:
+        names = set(z.namelist())
+        for rel, sha in man["files"].items():
+            if rel not in names or _sha_bytes(z.read(rel)) != sha:
+                raise RuntimeError(f"oracle/_ref: member {rel} of the archive does not match the manifest")
+            if against_source and os.path.isdir(REF_SRC) and _sha_bytes(open(os.path.join(REF_SRC, rel), "rb").read()) != sha:
+                raise RuntimeError(f"oracle/_ref: member {rel} differs from {REF_SRC}/{rel}")
     return True
 
 

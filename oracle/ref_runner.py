@@ -19,10 +19,11 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "_ref")
+ARCHIVE = os.path.join(REF, "reference_modules.zip")      # the unmodified models/ and transport/ packages, imported by zipimport
 
 
 def available() -> bool:
-    return os.path.exists(os.path.join(REF, "MANIFEST.json"))
+    return os.path.exists(os.path.join(REF, "MANIFEST.json")) and os.path.exists(ARCHIVE)
 
 
 def _import():
@@ -30,8 +31,9 @@ def _import():
         raise RuntimeError("oracle/_ref is missing: run `python oracle/build_ref.py` in the build container (needs /root/reference)")
     from oracle import build_ref
     build_ref.verify()
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
+    for entry in (REF, ARCHIVE):                       # stand-ins (torchdiffeq, imwatermark) as files, the reference from the archive
+        if entry not in sys.path:
+            sys.path.insert(0, entry)
     import models.model as ref_model
     import models.modules.autoencoder as ref_ae
     import models.modules.layers as ref_layers
