@@ -254,7 +254,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="B", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp8"],
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp8", "fp8_all"],
                     help="bf16 = the reference's numerics (the headline); fp8 = opt-in e4m3 projections for the LayerNorm-fed Linears "
                          "(a separate line with its own tolerance contract, never the headline)")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sp"],
@@ -305,10 +305,13 @@ def main():
     with torch.device(dev):
         model = M.FluxLoraWrapper(lora_rank=256, params=M.flux_dev_fill_params())
     model.init_synthetic(0)
-    if args.precision == "fp8":
-        model.set_linear_precision("fp8")
-        config["precision"] = ("fp8: qkv / mlp.0 / linear1 (58 % of the GEMM FLOPs) on e4m3 operands (tcgen05 kind::f8f6f4, per-row activation "
-                               "and per-channel weight scales); everything else bf16.  NOT the reference's numerics: tests/test_fp8_gpu.py")
+    if args.precision != "bf16":
+        model.set_linear_precision(args.precision)
+        config["precision"] = (("fp8: qkv / mlp.0 / linear1 (58 % of the GEMM FLOPs)" if args.precision == "fp8" else
+                                "fp8_all: every Linear of the blocks (qkv, proj, mlp.0, mlp.2, linear1, linear2; inputs of the gated-residual ones "
+                                "quantised row-wise by quantize_rows_e4m3_kernel, booked under other_ms)") +
+                               " on e4m3 operands (tcgen05 kind::f8f6f4, per-row activation and per-channel weight scales); everything else bf16.  "
+                               "NOT the reference's numerics: tests/test_fp8_gpu.py")
     model.engine()
     decoder = None
     try:
@@ -480,8 +483,9 @@ def main():
                      "frac": gemm_fl / (dit_gemm_ms / 1000.0) / 1e12 / pk["tf"],
                      "traffic": traffic.get("gemm", {}).get("avg_dram_bytes_per_launch"), "traffic_source": traffic.get("source"), "peak_source": pk["src"] + " sustained",
                      "launches": int(pl[0]), "avg_launch_ms": pms[0] / max(1, pl[0]), "flops_per_image": gemm_fl,
-                     **({"peak_note": "58 % of these FLOPs ran on e4m3 operands, whose dense peak is 2x the bf16 peak used as the denominator here"}
-                        if args.precision == "fp8" else {})},
+                     **({"peak_note": ("58 % of these FLOPs" if args.precision == "fp8" else "the blocks' FLOPs (all but img_in / final / modulation)") +
+                                      " ran on e4m3 operands, whose dense peak is 2x the bf16 peak used as the denominator here"}
+                        if args.precision != "bf16" else {})},
         "roofline_attention": {"kernel": "attn_fwd4_tcgen05_kernel (persistent schedule; fixed-reference softmax where the block's QK-norm bound applies)",
                                "bound": "tensor", "achieved": attn_fl / (pms[1] / 1000.0) / 1e12,
                                "peak": pk["tf"], "unit": "TFLOP/s", "frac": attn_fl / (pms[1] / 1000.0) / 1e12 / pk["tf"],

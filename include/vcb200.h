@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define VCB_ABI_VERSION 4
+#define VCB_ABI_VERSION 5
 #define VCB_SP_MAX 8          /* ranks of one sequence-parallel group (one NVSwitch domain) */
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -186,6 +186,12 @@ int vcb_ln_modulate_fp8_stats(const vcb_ln_args* a0, const vcb_ln_args* a1, floa
                               const void* stats1, int32_t n_slots, int64_t ldx, int64_t ld8, int64_t mod_stride, int32_t hidden,
                               int32_t batch_rows, void* stream);
 
+/* Row-wise e4m3 quantisation of a bf16 matrix x [rows, K] (row stride ldx elements; K % 8 == 0, K <= 15360): y8 [rows, K] e4m3
+ * bytes (row stride ld8 bytes) and row_scale[row] = max(max|x|, 1e-12) / 448, so that x ~= y8 * row_scale.  Feeds the fp8 form of
+ * the Linears whose input is NOT a LayerNorm output (fp8 level 2: attn.proj, mlp.2, linear2 -- layers.py:190-195, 244). */
+int vcb_quantize_rows_e4m3(const void* x, int64_t ldx, void* y8, int64_t ld8, float* row_scale, int64_t rows, int32_t K,
+                           void* stream);
+
 /* ---- small helpers --------------------------------------------------------------------------------------- */
 /* layers.py:28-49; t_scaled = time_factor * t already in the reference's dtype; freqs[128] fp32; out [n,256] bf16 */
 int vcb_timestep_embedding(const float* t_scaled, const float* freqs, void* out, int32_t n, void* stream);
@@ -208,7 +214,8 @@ int vcb_copy_cols(const void* src, int64_t lds, void* dst, int64_t ldd, int32_t 
  * Weights are the reference's tensors with LoRA merged (W' = W + s*B*A, b' = b + s*b_B; lora.py:92-98), bf16
  * weights [out, in], fp32 biases.  The engine keeps pointers only; the caller owns weights and workspace. */
 /* w8 / w8_scale (optional): the same merged weight quantised to e4m3 with one fp32 scale per output channel (w ~= w8 * scale),
- * used by the opt-in fp8 projections (vcb_flux_set_fp8) of the LayerNorm-fed Linears (qkv, mlp.0, linear1); NULL = bf16 only. */
+ * used by the opt-in fp8 projections (vcb_flux_set_fp8): level 1 needs it on the LayerNorm-fed Linears (qkv, mlp.0, linear1), level 2
+ * also on attn.proj, mlp.2 and linear2; NULL = bf16 only. */
 typedef struct vcb_linear_w { const void* w; const float* b; const void* w8; const float* w8_scale; } vcb_linear_w;
 
 typedef struct vcb_stream_w {           /* one stream of a DoubleStreamBlock (layers.py:129-156) */
@@ -247,8 +254,13 @@ int  vcb_flux_use_score_bounds(vcb_flux* f, int32_t enable);
 /* opt-in FP8 (e4m3) projections: the Linears fed by an AdaLN LayerNorm (double blocks: img/txt qkv and mlp.0; single blocks:
  * linear1 -- 58 % of the step's GEMM FLOPs) run on tcgen05.mma kind::f8f6f4 with per-row activation scales (written by the
  * LayerNorm kernel) and per-output-channel weight scales; everything else stays bf16.  Needs the w8 / w8_scale members of those
- * weights.  NOT the reference's numerics: a separate tolerance contract applies (tests/test_fp8_gpu.py). */
-int  vcb_flux_set_fp8(vcb_flux* f, int32_t enable);
+ * weights.  level 2 (VCB_FP8_ALL_LINEARS) adds the gated-residual Linears (attn.proj, mlp.2, linear2 -- all of the blocks' GEMM
+ * FLOPs): their bf16 inputs (attention output, GELU output) are quantised row-wise by vcb_quantize_rows_e4m3 first.
+ * NOT the reference's numerics: a separate tolerance contract applies per level (tests/test_fp8_gpu.py). */
+#define VCB_FP8_OFF 0
+#define VCB_FP8_LN_FED 1
+#define VCB_FP8_ALL_LINEARS 2
+int  vcb_flux_set_fp8(vcb_flux* f, int32_t level);
 /* bytes of device workspace for B samples of Li image + Lt text tokens and n_evals model evaluations */
 int64_t vcb_flux_workspace_bytes(const vcb_flux* f, int32_t B, int32_t Li, int32_t Lt, int32_t n_evals);
 /* Step-invariant work, once per image (txt_in, RoPE table, and the AdaLN modulation vectors of

@@ -6,7 +6,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvcb200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 SP_MAX = 8
 
 _lib = None
@@ -183,6 +183,7 @@ _OPTIONAL: dict = {
     "vcb_flux_destroy": (None, [C.c_void_p]),
     "vcb_flux_use_score_bounds": (C.c_int, [C.c_void_p, C.c_int32]),
     "vcb_flux_set_fp8": (C.c_int, [C.c_void_p, C.c_int32]),
+    "vcb_quantize_rows_e4m3": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "vcb_flux_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "vcb_flux_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

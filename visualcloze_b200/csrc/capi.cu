@@ -103,11 +103,13 @@ int launch_gemm_inst(const Problem& g0, const Problem& g1, float rate, cudaStrea
     return 0;
 }
 
-// fp8 operands: the LayerNorm-fed projections of the FLUX blocks (qkv, mlp-up, linear1) and plain bias GEMMs
+// fp8 operands: the LayerNorm-fed projections of the FLUX blocks (qkv, mlp-up, linear1), plain bias GEMMs and -- level 2, A
+// quantised by vcb_quantize_rows_e4m3 -- the gated-residual projections (proj, mlp-down, linear2)
 template <int BN, int CG>
 int launch_gemm_epi_fp8(int epi, const Problem& g0, const Problem& g1, float rate, cudaStream_t st) {
     if (epi == EPI_BIAS) return launch_gemm_inst<BN, CG, EPI_BIAS, false, true>(g0, g1, rate, st);
     if (epi == EPI_BIAS_GELU) return launch_gemm_inst<BN, CG, EPI_BIAS_GELU, false, true>(g0, g1, rate, st);
+    if (epi == EPI_GATE_RES) return launch_gemm_inst<BN, CG, EPI_GATE_RES, false, true>(g0, g1, rate, st);
     if constexpr (BN % 128 == 0) {
         if (epi == EPI_QKV) return launch_gemm_inst<BN, CG, EPI_QKV, false, true>(g0, g1, rate, st);
         if (epi == EPI_LINEAR1) return launch_gemm_inst<BN, CG, EPI_LINEAR1, false, true>(g0, g1, rate, st);
@@ -218,8 +220,7 @@ int check_gemm_args(const vcb_gemm_args* a) {
     if (a->operand_dtype == VCB_DTYPE_E4M3) {
         if (a->lda % 16 || a->ldw % 16 || a_bstride % 16) return set_error("gemm (fp8): lda / ldw / a_batch_stride must be multiples of 16 bytes");
         if (a->sp_world > 1) return set_error("gemm (fp8): the sequence-parallel routing takes bf16 operands");
-        if (a->epilogue == VCB_EPI_GATE_RES || a->epilogue == VCB_EPI_BIAS_F32)
-            return set_error("gemm (fp8): epilogue %d is bf16-only (its A operand is produced by a GEMM epilogue, not by the LayerNorm)", a->epilogue);
+        if (a->epilogue == VCB_EPI_BIAS_F32) return set_error("gemm (fp8): the fp32-output epilogue is bf16-operand only");
         if (a->block_n && a->block_n != 128 && a->block_n != 256) return set_error("gemm (fp8): block_n must be 128 or 256");
     }
     return 0;
@@ -728,6 +729,22 @@ extern "C" int vcb_ln_modulate_fp8(const vcb_ln_args* a0, const vcb_ln_args* a1,
         : launch_pdl(ln_modulate_fp8_kernel<kLnMaxChunks>, grid, block, (size_t)hidden * 4, (cudaStream_t)stream, 1, p[0], p[1], (long long)ldx,
                      (long long)ld8, (long long)mod_stride, (int)hidden, (int)batch_rows);
     if (e != cudaSuccess) return set_error("ln_modulate_fp8 launch: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
+}
+
+extern "C" int vcb_quantize_rows_e4m3(const void* x, int64_t ldx, void* y8, int64_t ld8, float* row_scale, int64_t rows, int32_t K,
+                                      void* stream) {
+    if (!x || !y8 || !row_scale) return set_error("quantize_rows_e4m3: null argument");
+    if (rows <= 0 || rows > 0x7fffffffLL || K <= 0 || K % 8 || K > kQuantThreads * kQuantMaxChunks * 8)
+        return set_error("quantize_rows_e4m3: need rows > 0 and K a multiple of 8, <= %d", kQuantThreads * kQuantMaxChunks * 8);
+    if (ldx % 8 || ld8 % 8 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y8) & 7))
+        return set_error("quantize_rows_e4m3: ldx / ld8 must be multiples of 8 elements, x 16-byte and y8 8-byte aligned");
+    if (int rc = ensure_device()) return rc;
+    ProfScope prof(PROF_OTHER, stream);
+    cudaError_t e = launch_pdl(quantize_rows_e4m3_kernel, dim3((unsigned)rows), dim3(kQuantThreads), (size_t)0, (cudaStream_t)stream, 1,
+                               (const __nv_bfloat16*)x, (long long)ldx, (uint8_t*)y8, (long long)ld8, row_scale, (int)K);
+    if (e != cudaSuccess) return set_error("quantize_rows_e4m3 launch: %s", cudaGetErrorString(e));
     count_launch();
     return 0;
 }

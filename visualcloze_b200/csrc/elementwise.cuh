@@ -413,6 +413,63 @@ ln_modulate_fp8_kernel(const LnFp8Problem p0, const LnFp8Problem p1, long long l
         }
 }
 
+// Row-wise e4m3 quantisation of a bf16 matrix that a GEMM epilogue or the attention kernel produced (fp8 level 2: the A operands
+// of proj / mlp.2 / linear2).  One block per row: the row (<= 15360 elements) stays in registers between the max|x| reduction and
+// the conversion, so the matrix is read once and the e4m3 copy written once.  Same scale rule as the fp8 LayerNorm:
+// s = max(max|x|, 1e-12) / 448,  y8 = e4m3_rn_satfinite(x * (1 / s)).
+constexpr int kQuantThreads = 192;
+constexpr int kQuantMaxChunks = 10;                  // 16-byte chunks per thread: K <= 192 * 10 * 8 = 15360
+__global__ void __launch_bounds__(kQuantThreads, 4)
+quantize_rows_e4m3_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, uint8_t* __restrict__ y8, long long ld8,
+                          float* __restrict__ row_scale, int K) {
+    __shared__ float red[kQuantThreads / 32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long row = blockIdx.x;
+    const int nvec = K >> 3;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+    uint4 v[kQuantMaxChunks];
+    float amax = 0.f;
+#pragma unroll
+    for (int c = 0; c < kQuantMaxChunks; ++c) {
+        const int idx = c * kQuantThreads + (int)threadIdx.x;
+        if (idx < nvec) v[c] = xr[idx];
+    }
+#pragma unroll
+    for (int c = 0; c < kQuantMaxChunks; ++c) {
+        const int idx = c * kQuantThreads + (int)threadIdx.x;
+        if (idx < nvec) {
+            const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16x2(w[e]);
+                amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kQuantThreads / 32; ++w) amax = fmaxf(amax, red[w]);
+    const float s = fmaxf(amax, 1e-12f) * (1.0f / 448.0f);
+    const float inv = 1.0f / s;
+    if (threadIdx.x == 0) row_scale[row] = s;
+    uint8_t* yr = y8 + row * ld8;
+#pragma unroll
+    for (int c = 0; c < kQuantMaxChunks; ++c) {
+        const int idx = c * kQuantThreads + (int)threadIdx.x;
+        if (idx < nvec) {
+            const float2 f0 = unpack_bf16x2(v[c].x), f1 = unpack_bf16x2(v[c].y), f2 = unpack_bf16x2(v[c].z), f3 = unpack_bf16x2(v[c].w);
+            uint2 o;
+            o.x = pack_e4m3x4(f0.x * inv, f0.y * inv, f1.x * inv, f1.y * inv);
+            o.y = pack_e4m3x4(f2.x * inv, f2.y * inv, f3.x * inv, f3.y * inv);
+            *reinterpret_cast<uint2*>(yr + (long long)idx * 8) = o;
+        }
+    }
+}
+
 // FP8 + statistics from the producer: with (sum, sum of squares) supplied by the GATE_RES epilogue the fp8 LayerNorm needs no
 // register-resident row either -- pass A streams the row for max|bf16(y)|, pass B re-reads it (L1 / L2) and writes the e4m3 bytes.
 // 48 registers -> 5 blocks per SM: one round at cfg B (the register-resident kernel above: 3 blocks per SM, two rounds).

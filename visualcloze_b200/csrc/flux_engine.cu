@@ -24,7 +24,9 @@ struct vcb_flux {
     bool prepared = false;
     int B = 0, Li = 0, Lt = 0, L = 0, E = 0;
     bool use_score_bounds = true;
-    bool fp8 = false;                 // vcb_flux_set_fp8: LayerNorm-fed projections on e4m3 operands
+    int fp8 = 0;                      // vcb_flux_set_fp8 level: 1 = LayerNorm-fed projections on e4m3 operands, 2 = every block Linear
+    uint8_t* cat8 = nullptr;          // [B, L, H + mlp] e4m3 copy of `cat` (level 2)
+    float* cat_scale = nullptr;       // [B * L] fp32 per-row scale of the cat8 columns last quantised (level 2)
     uint8_t* xm8 = nullptr;           // [B, L, H] e4m3 LayerNorm output (fp8 mode)
     float* row_scale = nullptr;       // [B * L] fp32 per-row activation scale (fp8 mode)
     float* row_stats = nullptr;       // [B * L][H / 64] float2: LayerNorm statistics left behind by the GATE_RES epilogues
@@ -80,6 +82,8 @@ int64_t carve(vcb_flux* f, uint8_t* base, int B, int Li, int Lt, int E) {
     uint16_t* xm = cv.take<uint16_t>((int64_t)B * L * H);
     uint8_t* xm8 = cv.take<uint8_t>((int64_t)B * L * H);
     float* row_scale = cv.take<float>((int64_t)B * L);
+    uint8_t* cat8 = cv.take<uint8_t>(f->fp8 >= 2 ? (int64_t)B * L * (H + f->cfg.mlp_hidden) : 0);
+    float* cat_scale = cv.take<float>(f->fp8 >= 2 ? (int64_t)B * L : 0);
     float* row_stats = cv.take<float>((int64_t)B * L * (H / 64) * 2);
     // sequence-parallel: qkv [W*L, 3H/W] and cat [L, H+mlp] are the caller's peer-mapped allocations (same sizes)
     const bool sp = f->sp_world > 1;
@@ -89,6 +93,7 @@ int64_t carve(vcb_flux* f, uint8_t* base, int B, int Li, int Lt, int E) {
         f->rope = rope; f->txt0 = txt0; f->temb_t = temb_t; f->temb_g = temb_g; f->h1 = h1; f->e_time = e_time;
         f->e_guid = e_guid; f->e_vec = e_vec; f->vec = vec; f->svec = svec; f->mod_dbl = md; f->mod_sgl = ms;
         f->mod_final = mod_final; f->x = x; f->xm = xm; f->qkv = qkv; f->cat = cat; f->xm8 = xm8; f->row_scale = row_scale; f->row_stats = row_stats;
+        f->cat8 = cat8; f->cat_scale = cat_scale;
     }
     return cv.off;
 }
@@ -130,18 +135,28 @@ extern "C" int vcb_flux_create(const vcb_flux_config* cfg, const vcb_flux_weight
 
 extern "C" void vcb_flux_destroy(vcb_flux* f) { delete f; }
 
-extern "C" int vcb_flux_set_fp8(vcb_flux* f, int32_t enable) {
+extern "C" int vcb_flux_set_fp8(vcb_flux* f, int32_t level) {
     if (!f) return set_error("flux_set_fp8: null engine");
-    if (enable) {
+    if (level < VCB_FP8_OFF || level > VCB_FP8_ALL_LINEARS) return set_error("flux_set_fp8: level must be 0 (off), 1 (LayerNorm-fed Linears) or 2 (all block Linears)");
+    if (level) {
         if (f->sp_world > 1) return set_error("flux_set_fp8: the sequence-parallel mode runs bf16 projections");
+        auto has8 = [](const vcb_linear_w& w) { return w.w8 && w.w8_scale; };
         for (const auto& d : f->dbl)
-            for (const vcb_stream_w* s : {&d.img, &d.txt})
-                if (!s->qkv.w8 || !s->qkv.w8_scale || !s->mlp0.w8 || !s->mlp0.w8_scale)
+            for (const vcb_stream_w* s : {&d.img, &d.txt}) {
+                if (!has8(s->qkv) || !has8(s->mlp0))
                     return set_error("flux_set_fp8: double-block qkv / mlp.0 weights carry no e4m3 copy (w8, w8_scale)");
-        for (const auto& g : f->sgl)
-            if (!g.linear1.w8 || !g.linear1.w8_scale) return set_error("flux_set_fp8: linear1 weights carry no e4m3 copy (w8, w8_scale)");
+                if (level >= 2 && (!has8(s->proj) || !has8(s->mlp2)))
+                    return set_error("flux_set_fp8: level 2 needs e4m3 copies of the double-block attn.proj / mlp.2 weights too");
+            }
+        for (const auto& g : f->sgl) {
+            if (!has8(g.linear1)) return set_error("flux_set_fp8: linear1 weights carry no e4m3 copy (w8, w8_scale)");
+            if (level >= 2 && !has8(g.linear2)) return set_error("flux_set_fp8: level 2 needs an e4m3 copy of the linear2 weights too");
+        }
+        if (level >= 2 && (f->cfg.hidden + f->cfg.mlp_hidden > 15360 || f->cfg.hidden % 16 || f->cfg.mlp_hidden % 16))
+            return set_error("flux_set_fp8: level 2 quantises rows of up to 15360 columns (hidden + mlp_hidden), both multiples of 16");
     }
-    f->fp8 = enable != 0;
+    if (f->fp8 != level) f->prepared = false;       // the workspace layout depends on the level
+    f->fp8 = level;
     return 0;
 }
 
@@ -264,6 +279,12 @@ vcb_gemm_args stream_args(const vcb_flux* f, const StreamView& sv, const uint16_
         g.A = f->xm8 + (int64_t)sv.off * lda + a_col;
         g.W = w.w8;
         g.a_scale = f->row_scale; g.w_scale = w.w8_scale;
+    } else if (f->fp8 >= 2 && a_buf == f->cat && w.w8) {
+        // level 2: A = the e4m3 copy of the cat columns vcb_quantize_rows_e4m3 produced just before (same row layout, bytes)
+        g.operand_dtype = VCB_DTYPE_E4M3;
+        g.A = f->cat8 + (int64_t)sv.off * lda + a_col;
+        g.W = w.w8;
+        g.a_scale = f->cat_scale; g.w_scale = w.w8_scale;
     }
     if (f->sp_world > 1 && (epi == VCB_EPI_QKV || epi == VCB_EPI_LINEAR1)) {
         g.sp_world = f->sp_world; g.sp_row_offset = f->sp_rank * f->L;
@@ -294,6 +315,12 @@ int joint_attention(vcb_flux* f, int64_t ldc, float score_bound, void* stream) {
     a.out_peers = f->sp_cat; a.world = W; a.rows_per_rank = f->L; a.out_col_offset = f->sp_rank * hw;
     if ((rc = vcb_attention_fwd_ex(&a, stream))) return rc;
     return vcb_sp_barrier(f->sp_flags, W, f->sp_rank, ++f->sp_epoch, f->sp_err, f->sp_timeout_ms, stream);
+}
+
+// fp8 level 2: e4m3 copy of columns [col0, col0 + K) of every row of `cat` (+ per-row scales) for the Linear that reads them next
+int quantize_cat(const vcb_flux* f, int64_t ldc, int col0, int K, void* stream) {
+    if (f->fp8 < 2) return 0;
+    return vcb_quantize_rows_e4m3(f->cat + col0, ldc, f->cat8 + col0, ldc, f->cat_scale, (int64_t)f->B * f->L, K, stream);
 }
 
 int stream_gemm(const vcb_flux* f, const StreamView& sv, const uint16_t* a_buf, int64_t lda, int a_col, int K,
@@ -400,6 +427,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
             if ((rc = vcb_gemm_bf16_grouped(&g[0], &g[1], stream))) return rc;
         }
         if ((rc = joint_attention(f, ldc, w.attn_score_bound, stream))) return rc;
+        if ((rc = quantize_cat(f, ldc, 0, H, stream))) return rc;
         {
             vcb_gemm_args g[2];
             for (int s = 0; s < 2; ++s)
@@ -416,6 +444,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
                                    nullptr, nullptr, 0, 0);
             if ((rc = vcb_gemm_bf16_grouped(&g[0], &g[1], stream))) return rc;
         }
+        if ((rc = quantize_cat(f, ldc, H, mlp, stream))) return rc;
         {
             vcb_gemm_args g[2];
             for (int s = 0; s < 2; ++s)
@@ -433,6 +462,7 @@ extern "C" int vcb_flux_forward(vcb_flux* f, int32_t e, const void* img, int64_t
         if ((rc = stream_gemm(f, s_all, f->xm, H, 0, H, w.linear1, 3 * H + mlp, VCB_EPI_LINEAR1, f->qkv, 3 * H, 0, nullptr, 0,
                               nullptr, w.q_scale, w.k_scale, f->cat, ldc, H, stream))) return rc;
         if ((rc = joint_attention(f, ldc, w.attn_score_bound, stream))) return rc;
+        if ((rc = quantize_cat(f, ldc, 0, H + mlp, stream))) return rc;
         if ((rc = stream_gemm(f, s_all, f->cat, ldc, 0, H + mlp, w.linear2, H, VCB_EPI_GATE_RES, f->x, H, 0, mod + 2 * H, 3 * H,
                               nullptr, nullptr, nullptr, nullptr, 0, 0, stream))) return rc;
         f->stats_valid = true;

@@ -25,7 +25,7 @@ def _freqs() -> Tensor:
 
 
 class FluxEngine:
-    def __init__(self, params, named_params: dict[str, Tensor], lora_scale: float = 1.0, fp8: bool = False):
+    def __init__(self, params, named_params: dict[str, Tensor], lora_scale: float = 1.0, fp8: int = 0):
         some = next(iter(named_params.values()))
         if not some.is_cuda:
             raise _lib.VcbError("FluxEngine needs the model on a CUDA device: the hot path has no CPU fallback")
@@ -35,7 +35,7 @@ class FluxEngine:
         self._keep: list[Tensor] = []          # packed tensors referenced by the C structs
         self._p = named_params
         self._scale = float(lora_scale)
-        self.fp8 = bool(fp8)
+        self.fp8 = int(fp8)                    # 0 = bf16, 1 = LayerNorm-fed Linears on e4m3, 2 = every block Linear on e4m3
         self.H = params.hidden_size
         self.mlp = int(params.hidden_size * params.mlp_ratio)
         with torch.no_grad():
@@ -124,8 +124,8 @@ class FluxEngine:
         for i in range(P.depth):
             for s, dst in (("img", dbl[i].img), ("txt", dbl[i].txt)):
                 b = f"double_blocks.{i}.{s}"
-                dst.mod, dst.qkv, dst.proj = self._linear(b + "_mod.lin"), self._linear(b + "_attn.qkv", self.fp8), self._linear(b + "_attn.proj")
-                dst.mlp0, dst.mlp2 = self._linear(b + "_mlp.0", self.fp8), self._linear(b + "_mlp.2")
+                dst.mod, dst.qkv, dst.proj = self._linear(b + "_mod.lin"), self._linear(b + "_attn.qkv", self.fp8 >= 1), self._linear(b + "_attn.proj", self.fp8 >= 2)
+                dst.mlp0, dst.mlp2 = self._linear(b + "_mlp.0", self.fp8 >= 1), self._linear(b + "_mlp.2", self.fp8 >= 2)
                 dst.q_scale = self._scale_vec(b + "_attn.norm.query_norm.scale")
                 dst.k_scale = self._scale_vec(b + "_attn.norm.key_norm.scale")
             dbl[i].attn_score_bound = self._score_bound(
@@ -134,7 +134,7 @@ class FluxEngine:
         sgl = (SingleW * max(1, P.depth_single_blocks))()
         for i in range(P.depth_single_blocks):
             b = f"single_blocks.{i}"
-            sgl[i].mod, sgl[i].linear1, sgl[i].linear2 = self._linear(b + ".modulation.lin"), self._linear(b + ".linear1", self.fp8), self._linear(b + ".linear2")
+            sgl[i].mod, sgl[i].linear1, sgl[i].linear2 = self._linear(b + ".modulation.lin"), self._linear(b + ".linear1", self.fp8 >= 1), self._linear(b + ".linear2", self.fp8 >= 2)
             sgl[i].q_scale = self._scale_vec(b + ".norm.query_norm.scale")
             sgl[i].k_scale = self._scale_vec(b + ".norm.key_norm.scale")
             sgl[i].attn_score_bound = self._score_bound([b + ".norm.query_norm.scale"], [b + ".norm.key_norm.scale"])
@@ -144,7 +144,7 @@ class FluxEngine:
         check(self.lib.vcb_flux_create(C.byref(cfg), C.byref(w), C.byref(h)), "vcb_flux_create")
         self._h = h
         if self.fp8:
-            check(self.lib.vcb_flux_set_fp8(h, 1), "vcb_flux_set_fp8")
+            check(self.lib.vcb_flux_set_fp8(h, self.fp8), "vcb_flux_set_fp8")
 
     def use_score_bounds(self, enable: bool) -> None:
         """False: every block runs the exact online-max softmax kernel (what a checkpoint whose QK-norm scales leave the safe

@@ -181,7 +181,7 @@ class Flux(nn.Module):
         key = (self.lora_scale, self.linear_precision) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._engine is None or key != self._packed_key:
             self._engine = None                     # release the previous packing before building the next one
-            self._engine = FluxEngine(self.params, dict(self.named_parameters()), self.lora_scale, fp8=self.linear_precision == "fp8")
+            self._engine = FluxEngine(self.params, dict(self.named_parameters()), self.lora_scale, fp8={"bf16": 0, "fp8": 1, "fp8_all": 2}[self.linear_precision])
             self._packed_key = key
             if getattr(self, "_sp", None) is not None:
                 self._engine.enable_sequence_parallel(self._sp)
@@ -190,9 +190,11 @@ class Flux(nn.Module):
     def set_linear_precision(self, precision: str) -> None:
         """"bf16" (default; the reference's numerics) or "fp8": the LayerNorm-fed projections (qkv, mlp.0, linear1 -- 58 % of the
         step's GEMM FLOPs) run on e4m3 operands with per-row activation / per-channel weight scales.  Opt-in, NOT the reference's
-        numerics: see DESIGN.md (fp8 contract) for the measured deviation.  No counterpart in the reference."""
-        if precision not in ("bf16", "fp8"):
-            raise ValueError("linear precision must be 'bf16' or 'fp8'")
+        numerics: see DESIGN.md (fp8 contract) for the measured deviation.  "fp8_all" adds the gated-residual Linears (attn.proj,
+        mlp.2, linear2: every GEMM of the blocks), whose bf16 inputs are quantised row-wise first -- faster, and further from the
+        bf16 path (its own numbers in the same contract).  No counterpart in the reference."""
+        if precision not in ("bf16", "fp8", "fp8_all"):
+            raise ValueError("linear precision must be 'bf16', 'fp8' or 'fp8_all'")
         self.linear_precision = precision
 
     def enable_sequence_parallel(self, sp) -> None:

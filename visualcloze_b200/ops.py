@@ -178,6 +178,16 @@ def ln_modulate_stats(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor,
     return out
 
 
+def quantize_rows_e4m3(x: torch.Tensor, out8: torch.Tensor, row_scale: torch.Tensor) -> None:
+    """x [rows, K] bf16 (any row stride) -> out8 [rows, K] float8_e4m3fn and row_scale [rows] fp32 = max(max|x|, 1e-12) / 448
+    (x ~= out8 * row_scale): the activation side of the fp8 Linears that are not fed by a LayerNorm (vcb_quantize_rows_e4m3)."""
+    rows, K = x.shape
+    assert x.dtype == torch.bfloat16 and out8.dtype == torch.float8_e4m3fn and row_scale.dtype == torch.float32
+    assert out8.shape == x.shape and row_scale.numel() == rows and x.stride(1) == 1 and out8.stride(1) == 1
+    check(_lib.lib().vcb_quantize_rows_e4m3(x.data_ptr(), x.stride(0), out8.data_ptr(), out8.stride(0), row_scale.data_ptr(), rows, K,
+                                            _stream()), "vcb_quantize_rows_e4m3")
+
+
 def ln_modulate_fp8(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out8: torch.Tensor, row_scale: torch.Tensor,
                     rows_per_batch: int, mod_stride: int | None = None, batch_rows: int | None = None,
                     stats: torch.Tensor | None = None) -> torch.Tensor:
