@@ -95,7 +95,7 @@ def test_gemm_fp8_rejects_unsupported(ops):
     w8 = torch.zeros(128, 256, dtype=F8, device="cuda")
     out = torch.zeros(128, 128, dtype=BF16, device="cuda")
     with pytest.raises(Exception, match="fp8"):
-        ops.gemm(a8, w8, None, torch.zeros(128, 128, dtype=torch.float32, device="cuda"), epilogue=ops.EPI_BIAS_F32)
+        ops.gemm(a8, w8, None, out, epilogue=5)                  # VCB_EPI_BIAS_F32 (fp32 scores of the VAE attention): bf16 operands only
     with pytest.raises(Exception, match="fp8"):
         ops.gemm(a8, w8, None, out, block_n=192)
 
@@ -223,6 +223,30 @@ def test_fp8_forward_reduced_depth_vs_bf16(pair):
     _record("forward_2+4_blocks_cfgA", rel_l2_fp8_vs_bf16=e, rel_l2_fp8_all_vs_bf16=e2)
     assert torch.isfinite(out).all() and 1e-4 < e < 1e-1, e
     assert torch.isfinite(out2).all() and e < e2 < 1.5e-1, (e, e2)          # more Linears quantised: further from bf16, same order
+
+
+@pytest.mark.parametrize("precision", ["fp8", "fp8_all"])
+def test_fp8_ragged_batch_matches_bf16_on_valid_tokens(precision):
+    """batch 2 with different image lengths (the reference golden's ragged case, tests/golden/flux_small_b2r.pt): padded rows are
+    don't-care, valid rows of the fp8 paths stay finite and close to the bf16 path -- the row quantiser and the per-row scales
+    must follow the physical row mapping of the joint buffer for every sample."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import visualcloze_b200.model as M
+    from test_flux_gpu import _build, _load
+    g = _load("flux_small_b2r.pt")
+    cfg, params, model = _build(M, g["cfg"], g["param_seed"])
+    inp = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in g["inputs"].items()}
+    ref = model(**inp).float()
+    model.set_linear_precision(precision)
+    out = model(**inp).float()
+    mask = inp["img_mask"].bool()
+    assert bool(torch.isfinite(out[mask]).all())
+    e = rel_l2(out[mask], ref[mask])
+    for b in range(mask.shape[0]):                       # per sample: a wrong row mapping would wreck one sample, not the average
+        eb = rel_l2(out[b][mask[b]], ref[b][mask[b]])
+        assert 0 < eb < 1.5e-1, (precision, b, eb)
+    _record(f"ragged_b2_small_{precision}", rel_l2_vs_bf16=e)
 
 
 def test_fp8_full_depth_forward_trajectory_and_image():

@@ -1,7 +1,7 @@
 """Launch ONE hot kernel of the path at its cfg-B shape a few times, for `ncu --set full -k regex:... -c 1` captures.
 
   python tools/ncu_targets.py ln | ln_stats | attn_pair | attn_pair_exact | attn_persistent | gemm_linear1 | gemm_linear2 | gemm_fp8_linear1 |
-                              conv512 | conv256 | conv128
+                              gemm_fp8_linear2 | quantize_cat | conv512 | conv256 | conv128
 """
 import math
 import os
@@ -49,7 +49,17 @@ elif what.startswith("gemm"):
     x = rn(L, H).to(BF16)
     qkv = torch.empty(L, 3 * H, dtype=BF16, device="cuda")
     cat = rn(L, H + MLP).to(BF16)
-    if what == "gemm_linear2":
+    if what == "gemm_fp8_linear2":
+        # fp8 level 2: linear2 (K = 15360, gated residual) on the e4m3 copy of cat that quantize_rows_e4m3_kernel produced
+        w32, b, gate = rn(H, H + MLP) / math.sqrt(H + MLP), rn(H), (0.3 * rn(1, H)).to(BF16)
+        sw = w32.abs().amax(1) / 448.0
+        w8 = (w32 / sw[:, None]).to(torch.float8_e4m3fn)
+        c8, sa = torch.empty(L, H + MLP, dtype=torch.float8_e4m3fn, device="cuda"), torch.empty(L, device="cuda")
+        ops.quantize_rows_e4m3(cat, c8, sa)
+        stats = torch.zeros(L, H // 64, 2, device="cuda")
+        for _ in range(REP):
+            ops.gemm(c8, w8, b, x, epilogue=ops.EPI_GATE_RES, gate=gate, res=x, a_scale=sa, w_scale=sw, row_stats=stats)
+    elif what == "gemm_linear2":
         w, b, gate = (rn(H, H + MLP) / math.sqrt(H + MLP)).to(BF16), rn(H), (0.3 * rn(1, H)).to(BF16)
         for _ in range(REP):
             ops.gemm(cat, w, b, x, epilogue=ops.EPI_GATE_RES, gate=gate, res=x)
@@ -69,6 +79,11 @@ elif what.startswith("gemm"):
             w = w32.to(BF16)
             for _ in range(REP):
                 ops.gemm(x, w, b, qkv, **kw)
+elif what == "quantize_cat":
+    cat = rn(L, H + MLP).to(BF16)
+    c8, sa = torch.empty(L, H + MLP, dtype=torch.float8_e4m3fn, device="cuda"), torch.empty(L, device="cuda")
+    for _ in range(REP):
+        ops.quantize_rows_e4m3(cat, c8, sa)
 elif what.startswith("conv"):
     C = int(what[4:])
     Hh, Ww = {512: (96, 288), 256: (192, 576), 128: (384, 1152)}[C]     # decoder levels of one cfg-B grid row
