@@ -221,6 +221,7 @@ int check_gemm_args(const vcb_gemm_args* a) {
         if (a->lda % 16 || a->ldw % 16 || a_bstride % 16) return set_error("gemm (fp8): lda / ldw / a_batch_stride must be multiples of 16 bytes");
         if (a->sp_world > 1) return set_error("gemm (fp8): the sequence-parallel routing takes bf16 operands");
         if (a->epilogue == VCB_EPI_BIAS_F32) return set_error("gemm (fp8): the fp32-output epilogue is bf16-operand only");
+        if (reinterpret_cast<uintptr_t>(a->w_scale) & 15) return set_error("gemm (fp8): w_scale must be 16-byte aligned (read as float4)");
         if (a->block_n && a->block_n != 128 && a->block_n != 256) return set_error("gemm (fp8): block_n must be 128 or 256");
     }
     return 0;

@@ -184,36 +184,92 @@ VCB_DEVICE void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int n0, 
     }
 }
 
-// sa: this thread's row scale (1 for bf16 operands); ws: per-column weight scales or null.  fp8: acc * sa * ws[n] + bias
+// One 32-column chunk of this thread's accumulator row, in two halves so that callers can put their own global loads (gate,
+// residual, RoPE, norm scales) between them: acc_issue starts the asynchronous TMEM load; acc_finish first issues the bias /
+// weight-scale loads, THEN waits for the accumulator -- the three latencies overlap instead of adding up (the epilogue warps are
+// latency-bound: two per scheduler, ncu long_scoreboard was the top stall).  The registers of `r` must not be touched between the
+// two calls.  sa: this thread's row scale (1 for bf16 operands); ws: per-column weight scales or null.
+// bf16: v = bf16(acc + bias) (the reference's Linear output); fp8: v = bf16(fma(acc, sa * ws[n], bias)).
+VCB_DEVICE void acc_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge after predicated stores
+    tmem_ld_x32(taddr, r);
+}
+// kRound: round the Linear output to the bf16 grid (the reference's Linear returns a bf16 tensor).  The fp8 instantiations skip
+// the intermediate roundings -- their values are off the reference's grid already and every rounding is two more instructions
+// in an epilogue that bounds the short-K fp8 tiles; the final store still rounds once.
+// kHoist: issue the bias / scale loads before the accumulator wait (default); false = after it, for callers that keep other
+// prefetched data live across the wait and cannot spare 64 registers (the loads hit L1: every row reads the same addresses).
+template <bool kRound = true, bool kHoist = true>
+VCB_DEVICE void acc_finish(uint32_t (&r)[32], const float* __restrict__ bias, int n0, int N, float (&v)[32], float sa = 1.0f,
+                           const float* __restrict__ ws = nullptr) {
+    auto rnd = [](float x) { return kRound ? bf16_round(x) : x; };
+    if (n0 + 32 <= N) {
+        if constexpr (kHoist) {
+            float4 b4[8];
+            if (bias != nullptr) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) b4[q] = __ldg(reinterpret_cast<const float4*>(bias + n0) + q);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) b4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (ws != nullptr) {
+                float4 w4[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) w4[q] = __ldg(reinterpret_cast<const float4*>(ws + n0) + q);
+                tmem_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    v[q * 4 + 0] = rnd(fmaf(__uint_as_float(r[q * 4 + 0]), sa * w4[q].x, b4[q].x));
+                    v[q * 4 + 1] = rnd(fmaf(__uint_as_float(r[q * 4 + 1]), sa * w4[q].y, b4[q].y));
+                    v[q * 4 + 2] = rnd(fmaf(__uint_as_float(r[q * 4 + 2]), sa * w4[q].z, b4[q].z));
+                    v[q * 4 + 3] = rnd(fmaf(__uint_as_float(r[q * 4 + 3]), sa * w4[q].w, b4[q].w));
+                }
+            } else {
+                tmem_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    v[q * 4 + 0] = rnd(__uint_as_float(r[q * 4 + 0]) + b4[q].x);
+                    v[q * 4 + 1] = rnd(__uint_as_float(r[q * 4 + 1]) + b4[q].y);
+                    v[q * 4 + 2] = rnd(__uint_as_float(r[q * 4 + 2]) + b4[q].z);
+                    v[q * 4 + 3] = rnd(__uint_as_float(r[q * 4 + 3]) + b4[q].w);
+                }
+            }
+        } else {
+            tmem_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 b4 = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias + n0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ws != nullptr) {
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(ws + n0) + q);
+                    v[q * 4 + 0] = rnd(fmaf(__uint_as_float(r[q * 4 + 0]), sa * w4.x, b4.x));
+                    v[q * 4 + 1] = rnd(fmaf(__uint_as_float(r[q * 4 + 1]), sa * w4.y, b4.y));
+                    v[q * 4 + 2] = rnd(fmaf(__uint_as_float(r[q * 4 + 2]), sa * w4.z, b4.z));
+                    v[q * 4 + 3] = rnd(fmaf(__uint_as_float(r[q * 4 + 3]), sa * w4.w, b4.w));
+                } else {
+                    v[q * 4 + 0] = rnd(__uint_as_float(r[q * 4 + 0]) + b4.x);
+                    v[q * 4 + 1] = rnd(__uint_as_float(r[q * 4 + 1]) + b4.y);
+                    v[q * 4 + 2] = rnd(__uint_as_float(r[q * 4 + 2]) + b4.z);
+                    v[q * 4 + 3] = rnd(__uint_as_float(r[q * 4 + 3]) + b4.w);
+                }
+            }
+        }
+    } else {                                        // ragged last chunk of N: column by column
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float sw = (ws != nullptr && n0 + j < N) ? sa * __ldg(ws + n0 + j) : 1.0f;
+            const float bj = (bias != nullptr && n0 + j < N) ? __ldg(bias + n0 + j) : 0.0f;
+            v[j] = ws != nullptr ? rnd(fmaf(__uint_as_float(r[j]), sw, bj)) : rnd(__uint_as_float(r[j]) + bj);
+        }
+    }
+}
+template <bool kRound = true, bool kHoist = true>
 VCB_DEVICE void load_acc_bias(uint32_t taddr, const float* __restrict__ bias, int n0, int N, float (&v)[32], float sa = 1.0f,
                               const float* __restrict__ ws = nullptr) {
     uint32_t r[32];
-    __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge after predicated stores
-    tmem_ld_x32(taddr, r);
-    tmem_wait_ld();
-    if (ws != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float sw = (n0 + j < N) ? __ldg(ws + n0 + j) : 0.0f;
-            r[j] = __float_as_uint(__uint_as_float(r[j]) * (sa * sw));
-        }
-    }
-    if (bias != nullptr && n0 + 32 <= N) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0) + q);
-            v[q * 4 + 0] = bf16_round(__uint_as_float(r[q * 4 + 0]) + b4.x);   // Linear output is a bf16 tensor in the reference
-            v[q * 4 + 1] = bf16_round(__uint_as_float(r[q * 4 + 1]) + b4.y);
-            v[q * 4 + 2] = bf16_round(__uint_as_float(r[q * 4 + 2]) + b4.z);
-            v[q * 4 + 3] = bf16_round(__uint_as_float(r[q * 4 + 3]) + b4.w);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float b = (bias != nullptr && n0 + j < N) ? __ldg(bias + n0 + j) : 0.0f;
-            v[j] = bf16_round(__uint_as_float(r[j]) + b);
-        }
-    }
+    acc_issue(taddr, r);
+    acc_finish<kRound, kHoist>(r, bias, n0, N, v, sa, ws);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -406,6 +462,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const long long orow = (long long)b * P.out_batch_rows + P.out_row_offset + (row_ok ? i : 0);
             [[maybe_unused]] const float sa = (kFp8 && P.a_scale) ? __ldg(P.a_scale + orow) : 1.0f;
             [[maybe_unused]] const float* ws = kFp8 ? P.w_scale : nullptr;
+            // intermediate roundings to the bf16 grid: the reference's autocast semantics; skipped for e4m3 operands (see acc_finish)
+            [[maybe_unused]] auto rnd = [](float x) { return kFp8 ? x : bf16_round(x); };
 
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -507,29 +565,39 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const int n0 = n_tile0 + cc * 32;
                     if (n0 >= P.N) break;
                     float v[32];
-                    load_acc_bias(taddr + cc * 32, P.bias, n0, P.N, v, sa, ws);
+                    uint32_t racc[32];
+                    acc_issue(taddr + cc * 32, racc);
+                    // gate / residual of this chunk: issued before the accumulator wait (neither depends on it)
+                    [[maybe_unused]] uint4 gu[4], ru[4];
+                    if constexpr (kEpi == EPI_GATE_RES) {
+                        const uint32_t one2 = 0x3F803F80u;          // bf16 (1.0, 1.0)
+                        const __nv_bfloat16* g = P.gate ? P.gate + (long long)b * P.gate_stride + n0 : nullptr;
+                        const __nv_bfloat16* rs = P.res + orow * P.ld_res + n0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const bool in = row_ok && n0 + q * 8 < P.N;
+                            gu[q] = (in && g) ? __ldg(reinterpret_cast<const uint4*>(g + q * 8)) : make_uint4(one2, one2, one2, one2);
+                            ru[q] = in ? *reinterpret_cast<const uint4*>(rs + q * 8) : make_uint4(0u, 0u, 0u, 0u);
+                        }
+                    }
+                    acc_finish<!kFp8>(racc, P.bias, n0, P.N, v, sa, ws);
                     if (row_ok) {
                         if constexpr (kEpi == EPI_BIAS_GELU) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+                            for (int j = 0; j < 32; ++j) v[j] = kFp8 ? gelu_tanh_fast(v[j]) : gelu_tanh(v[j]);
                         }
                         if constexpr (kEpi == EPI_GATE_RES) {
-                            const __nv_bfloat16* g = P.gate ? P.gate + (long long)b * P.gate_stride + n0 : nullptr;
-                            const __nv_bfloat16* rs = P.res + orow * P.ld_res + n0;
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 if (n0 + q * 8 < P.N) {
-                                    const uint32_t one2 = 0x3F803F80u;          // bf16 (1.0, 1.0)
-                                    uint4 gu = g ? __ldg(reinterpret_cast<const uint4*>(g + q * 8)) : make_uint4(one2, one2, one2, one2);
-                                    uint4 ru = *reinterpret_cast<const uint4*>(rs + q * 8);
-                                    const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
-                                    const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
+                                    const uint32_t gw[4] = {gu[q].x, gu[q].y, gu[q].z, gu[q].w};
+                                    const uint32_t rw[4] = {ru[q].x, ru[q].y, ru[q].z, ru[q].w};
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
                                         float2 gf = unpack_bf16x2(gw[e]);
                                         float2 rf = unpack_bf16x2(rw[e]);
-                                        float a0 = bf16_round(gf.x * v[q * 8 + 2 * e]);
-                                        float a1 = bf16_round(gf.y * v[q * 8 + 2 * e + 1]);
+                                        float a0 = rnd(gf.x * v[q * 8 + 2 * e]);
+                                        float a1 = rnd(gf.y * v[q * 8 + 2 * e + 1]);
                                         v[q * 8 + 2 * e] = rf.x + a0;
                                         v[q * 8 + 2 * e + 1] = rf.y + a1;
                                     }
@@ -608,11 +676,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         for (int c = 0; c < 4; ++c) {
                             const int n0 = ng + c * 32;
                             float v[32];
-                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v, sa, ws);
+                            load_acc_bias<!kFp8>(tg + c * 32, P.bias, n0, P.N, v, sa, ws);
                             if (kEpi == EPI_LINEAR1 && region >= 3) {
                                 if (row_ok) {
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+                                    for (int j = 0; j < 32; ++j) v[j] = kFp8 ? gelu_tanh_fast(v[j]) : gelu_tanh(v[j]);
                                     store_bf16x32(P.out2 + orow * P.ldo2 + P.out2_col_offset + (n0 - 3 * P.hidden), v, n0, P.N);
                                 }
                             } else if constexpr (kSp) {
@@ -622,47 +690,62 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             }
                         }
                     } else {
-                        // pass 1: sum of squares of the bf16-rounded projection over the head (RMSNorm, layers.py:68-72)
+                        const __nv_bfloat16* sc = region == 0 ? P.q_scale : P.k_scale;
+                        // rope table is stored pair-major [64][rope_rows]: consecutive lanes (rows) read consecutive float2.
+                        // Its entries are fetched ONE CHUNK AHEAD of their use (plain global loads are scoreboarded, so they may
+                        // stay in flight across the accumulator waits and the math): the table is the only per-row global
+                        // traffic of this epilogue and its L2 latency was what the two warps per scheduler could not hide.
+                        const float2* rp = P.rope + orow;
+                        auto load_rope = [&](int c, float2 (&dst)[16]) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                dst[j] = row_ok ? __ldg(rp + (long long)(c * 16 + j) * P.rope_rows) : make_float2(1.f, 0.f);
+                        };
+                        float2 cs_a[16], cs_b[16];
+                        load_rope(0, cs_a);
+                        // pass 1: sum of squares of the (bf16-rounded) projection over the head (RMSNorm, layers.py:68-72)
                         float ss = 0.f;
 #pragma unroll 1
                         for (int c = 0; c < 4; ++c) {
                             float v[32];
-                            load_acc_bias(tg + c * 32, P.bias, ng + c * 32, P.N, v, sa, ws);
+                            load_acc_bias<!kFp8, false>(tg + c * 32, P.bias, ng + c * 32, P.N, v, sa, ws);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
                         }
                         const float rrms = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
-                        const __nv_bfloat16* sc = region == 0 ? P.q_scale : P.k_scale;
-                        // rope table is stored pair-major [64][rope_rows]: consecutive lanes (rows) read consecutive float2
-                        const float2* rp = P.rope + orow;
                         // pass 2: normalise, scale, rotate, store
-#pragma unroll 1
-                        for (int c = 0; c < 4; ++c) {
+                        auto chunk = [&](int c, float2 (&cs)[16], float2 (&cs_next)[16]) {
                             const int n0 = ng + c * 32;
                             float v[32];
-                            load_acc_bias(tg + c * 32, P.bias, n0, P.N, v, sa, ws);
+                            uint32_t racc[32];
+                            acc_issue(tg + c * 32, racc);
+                            if (c < 3) load_rope(c + 1, cs_next);
+                            acc_finish<!kFp8, false>(racc, P.bias, n0, P.N, v, sa, ws);
                             if (row_ok) {
-                                uint32_t sw[16];
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
-                                    uint4 su = __ldg(reinterpret_cast<const uint4*>(sc + c * 32 + q * 8));
-                                    sw[q * 4 + 0] = su.x; sw[q * 4 + 1] = su.y; sw[q * 4 + 2] = su.z; sw[q * 4 + 3] = su.w;
-                                }
+                                    const uint4 su = __ldg(reinterpret_cast<const uint4*>(sc + c * 32 + q * 8));
+                                    const uint32_t sw[4] = {su.x, su.y, su.z, su.w};
 #pragma unroll
-                                for (int j = 0; j < 32; j += 2) {
-                                    const int pr = (c * 32 + j) >> 1;               // pair index inside the head
-                                    const float2 s2 = unpack_bf16x2(sw[j >> 1]);
-                                    float x0 = bf16_round(bf16_round(v[j] * rrms) * s2.x);
-                                    float x1 = bf16_round(bf16_round(v[j + 1] * rrms) * s2.y);
-                                    float2 cs = __ldg(rp + (long long)pr * P.rope_rows);
-                                    // math.py:112-117: two fp32 products, one fp32 add (no contraction)
-                                    v[j] = __fadd_rn(__fmul_rn(cs.x, x0), __fmul_rn(-cs.y, x1));
-                                    v[j + 1] = __fadd_rn(__fmul_rn(cs.y, x0), __fmul_rn(cs.x, x1));
+                                    for (int e = 0; e < 4; ++e) {
+                                        const int j = q * 8 + 2 * e;
+                                        const float2 s2 = unpack_bf16x2(sw[e]);
+                                        const float x0 = rnd(rnd(v[j] * rrms) * s2.x);
+                                        const float x1 = rnd(rnd(v[j + 1] * rrms) * s2.y);
+                                        const float2 t = cs[j >> 1];
+                                        // math.py:112-117: two fp32 products, one fp32 add (no contraction)
+                                        v[j] = __fadd_rn(__fmul_rn(t.x, x0), __fmul_rn(-t.y, x1));
+                                        v[j + 1] = __fadd_rn(__fmul_rn(t.y, x0), __fmul_rn(t.x, x1));
+                                    }
                                 }
                                 if constexpr (!kSp) store_bf16x32(qkv_dst + c * 32, v, n0, P.N);
                             }
                             if constexpr (kSp) sp_emit(c, v);
-                        }
+                        };
+                        chunk(0, cs_a, cs_b);
+                        chunk(1, cs_b, cs_a);
+                        chunk(2, cs_a, cs_b);
+                        chunk(3, cs_b, cs_a);
                     }
                 }
             }
