@@ -216,6 +216,7 @@ int check_gemm_args(const vcb_gemm_args* a) {
         if (a->N % 64) return set_error("gemm: row_stats needs N %% 64 == 0");
         if (a->block_n && a->block_n != 128 && a->block_n != 256) return set_error("gemm: row_stats needs block_n 128 or 256");
     }
+    if (reinterpret_cast<uintptr_t>(a->bias) & 15) return set_error("gemm: bias must be 16-byte aligned (the epilogue reads it as float4)");
     if (a->operand_dtype != VCB_DTYPE_BF16 && a->operand_dtype != VCB_DTYPE_E4M3) return set_error("gemm: unknown operand_dtype %d", a->operand_dtype);
     if (a->operand_dtype == VCB_DTYPE_E4M3) {
         if (a->lda % 16 || a->ldw % 16 || a_bstride % 16) return set_error("gemm (fp8): lda / ldw / a_batch_stride must be multiples of 16 bytes");
