@@ -24,7 +24,8 @@ def jl(path):
 
 # ---- bench lines -------------------------------------------------------------------------------------------------
 rows = []
-for tag, path in (("bf16 (headline)", f"{P}/r02_bench_1gpu.json"), ("fp8 projections (opt-in)", f"{P}/r02_bench_fp8_1gpu.json"),
+for tag, path in (("bf16 (headline)", f"{P}/r02_bench_1gpu.json"), ("fp8 LayerNorm-fed Linears (opt-in)", f"{P}/r02_bench_fp8_1gpu.json"),
+                  ("fp8 every block Linear (opt-in, fp8_all)", f"{P}/r02_bench_fp8_all_1gpu.json"),
                   ("bf16, VCB_STREAMK=1", f"{P}/r02_bench_streamk_1gpu.json")):
     if os.path.exists(path):
         rows.append((tag, json.load(open(path))))

@@ -22,6 +22,7 @@ row "UTCBAR" "tcgen05.commit -> mbarrier"
 row "SYNCS" "mbarrier operations"
 row "HMMA" "legacy mma.sync tensor instructions (must be 0)"
 row "MUFU.EX2" "ex2.approx (softmax / GELU)"
+row "MUFU.TANH" "tanh.approx (GELU of the fp8 instantiations)"
 row "F2FP" "packed float conversions (bf16 / e4m3 packs)"
 echo
 echo "Kernels in the cubin:"
