@@ -301,6 +301,29 @@ def test_never_loaded_weights_are_refused():
         d._engine()
 
 
+def test_linear_precision_levels_and_the_header_constants_agree():
+    """set_linear_precision takes "bf16" | "fp8" | "fp8_all" and nothing else; the levels the Python side passes to
+    vcb_flux_set_fp8 are the VCB_FP8_* constants of include/vcb200.h; the row quantiser is part of the exported ABI."""
+    import re
+    from visualcloze_b200 import _lib, model as M
+    small = dict(in_channels=384, out_channels=64, vec_in_dim=32, context_in_dim=64, hidden_size=256, mlp_ratio=2.0, num_heads=2,
+                 depth=1, depth_single_blocks=1, axes_dim=[16, 56, 56], theta=10_000, qkv_bias=True, guidance_embed=True)
+    m = M.FluxLoraWrapper(lora_rank=8, params=M.FluxParams(**small))
+    assert m.linear_precision == "bf16"
+    for p in ("fp8", "fp8_all", "bf16"):
+        m.set_linear_precision(p)
+        assert m.linear_precision == p
+    for bad in ("fp16", "FP8", "", None):
+        with pytest.raises(ValueError):
+            m.set_linear_precision(bad)
+    hdr = open(os.path.join(REPO, "include", "vcb200.h")).read()
+    consts = {k: int(v) for k, v in re.findall(r"#define (VCB_FP8_[A-Z_]+) (\d+)", hdr)}
+    assert consts == {"VCB_FP8_OFF": 0, "VCB_FP8_LN_FED": 1, "VCB_FP8_ALL_LINEARS": 2}
+    src = open(os.path.join(REPO, "visualcloze_b200", "model.py")).read()
+    assert '{"bf16": 0, "fp8": 1, "fp8_all": 2}' in src
+    assert hasattr(_lib.lib(), "vcb_quantize_rows_e4m3")
+
+
 def test_diffusers_vae_keys_convert_to_the_reference_names():
     """visualcloze.py:100 loads diffusers' AutoencoderKL; our VAE modules carry the in-repo AutoEncoder names (autoencoder.py).
     The converter must map a diffusers-named state dict of the FLUX VAE geometry onto exactly our parameter set."""
