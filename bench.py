@@ -401,7 +401,9 @@ def main():
 
     # ---- sequence-parallel single-image mode on the same process group (strong scaling; N > 1 only) ----
     sp_extra = None
-    if world > 1 and not sp_mode:
+    if world > 1 and not sp_mode and args.precision != "bf16":
+        sp_extra = {"skipped": "the sequence-parallel mode runs the bf16 projections only (vcb_flux_sp_attach refuses an fp8 engine)"}
+    elif world > 1 and not sp_mode:
         from visualcloze_b200.parallel import SequenceParallel
         try:
             x_s, kw_s, _, _ = make_inputs(args.workload, 1234)              # every rank: the SAME sample
