@@ -4,7 +4,8 @@ oracle (``oracle/flux_oracle.py``, ``cuda_bf16`` mode) executed on the same GPU.
 
   cfg B  full depth 19 + 38, hidden 3072, 24 heads, LoRA r=256, L = 3968: one evaluation, a 3-evaluation trajectory and the
          headline's whole 30-point (29-evaluation) trajectory with the decoded query row
-  cfg D  L = 7424 (3x4 grid) and cfg E  L = 4608 (SDEdit 1024^2): one evaluation each on the same weights
+  cfg C  L = 6656 (512 grid 2x3), cfg D  L = 7424 (3x4 grid) and cfg E  L = 4608 (SDEdit 1024^2): one evaluation each on the
+         same weights -- with B, every configuration BASELINE.json lists at its real size and depth
   attention alone at 24 heads, L in {3968, 7424}: vcb (exact and fixed-reference softmax) vs flash-attn vs an fp32 reference
   VAE decode of one cfg-B grid row (latent 16 x 48 x 144 -> 3 x 384 x 1152), mid-block attention over 6912 pixels
 
@@ -125,8 +126,8 @@ def test_cfgB_full_depth_forward_vs_reference_and_oracle(full):
         pytest.skip("oracle/_ref absent: compared with the restated oracle only")
 
 
-@pytest.mark.parametrize("workload", ["D", "E"])
-def test_cfgD_cfgE_forward(full, workload):
+@pytest.mark.parametrize("workload", ["C", "D", "E"])
+def test_cfgC_cfgD_cfgE_forward(full, workload):
     r = _one_eval(full, workload, t=0.41)
     _record(f"cfg{workload}_forward_19+38_L{int(r['tokens'])}", **r)
     _check_forward(r)
