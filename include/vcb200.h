@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define VCB_ABI_VERSION 5
+#define VCB_ABI_VERSION 6
 #define VCB_SP_MAX 8          /* ranks of one sequence-parallel group (one NVSwitch domain) */
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -191,6 +191,34 @@ int vcb_ln_modulate_fp8_stats(const vcb_ln_args* a0, const vcb_ln_args* a1, floa
  * the Linears whose input is NOT a LayerNorm output (fp8 level 2: attn.proj, mlp.2, linear2 -- layers.py:190-195, 244). */
 int vcb_quantize_rows_e4m3(const void* x, int64_t ldx, void* y8, int64_t ld8, float* row_scale, int64_t rows, int32_t K,
                            void* stream);
+
+/* ---- text encoders: the reference wraps HF T5EncoderModel("google/t5-v1_1-xxl") and CLIPTextModel(
+ * "openai/clip-vit-large-patch14") in models/modules/conditioner.py:5-37 (bf16, models/util.py:425-431) and calls them with
+ * attention_mask=None.  Their Linears run through vcb_gemm_bf16; these entry points are everything else.  All tensors bf16. -------- */
+/* out[t, :] = table[ids[t], :] (+ pos_table[t % L, :] when pos_table != NULL: CLIP's token + position embedding); ids int64 */
+int vcb_embedding_bf16(const void* table, int64_t vocab, int32_t dim, const int64_t* ids, const void* pos_table, int32_t L,
+                       void* out, int64_t ldo, int64_t n_tokens, void* stream);
+/* T5LayerNorm: y = weight * bf16(x * rsqrt(mean(x^2) + eps)), fp32 statistics, no mean subtraction, no bias */
+int vcb_rmsnorm_weight(const void* x, int64_t ldx, const void* weight, void* y, int64_t ldy, int64_t rows, int32_t dim, float eps,
+                       void* stream);
+/* nn.LayerNorm with affine parameters (CLIP): y = bf16((x - mean) * rstd * weight + bias), fp32 statistics */
+int vcb_layernorm_affine(const void* x, int64_t ldx, const void* weight, const void* bias, void* y, int64_t ldy, int64_t rows,
+                         int32_t dim, float eps, void* stream);
+/* T5DenseGatedActDense: out[:, j] = gelu_new(ab[:, j]) * ab[:, dff + j] (wi_0 and wi_1 computed by ONE GEMM of width 2 * dff) */
+int vcb_gated_gelu(const void* ab, int64_t ld, void* out, int64_t ldo, int64_t rows, int32_t dff, void* stream);
+/* CLIP's quick_gelu: y = x * sigmoid(1.702 x) */
+int vcb_quick_gelu(const void* x, void* y, int64_t n, void* stream);
+/* attention of the two text encoders: head_dim 64, L <= 512, row (b * L + i) of q / k / v with head h at column h * 64 (row stride
+ * ld: the three may point into one fused [B * L, 3 * heads * 64] buffer); scores = bf16(q k^T) (* scale), + bias[h, i, j] (T5's
+ * relative position bias, may be NULL), causal mask (CLIP), fp32 softmax, bf16 probabilities -- the HF modules' rounding points */
+typedef struct vcb_attn_small_args {
+    const void* q; const void* k; const void* v; int64_t ld;
+    const void* bias;            /* [heads, L, L] bf16 or NULL */
+    void* out; int64_t ldo;      /* [B * L, heads * 64] */
+    int32_t B, L, heads, head_dim, causal;
+    float scale;                 /* 0 or 1 = no scaling (T5); CLIP: head_dim^-0.5 */
+} vcb_attn_small_args;
+int vcb_attention_small(const vcb_attn_small_args* a, void* stream);
 
 /* ---- small helpers --------------------------------------------------------------------------------------- */
 /* layers.py:28-49; t_scaled = time_factor * t already in the reference's dtype; freqs[128] fp32; out [n,256] bf16 */

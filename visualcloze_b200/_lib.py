@@ -6,7 +6,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvcb200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 SP_MAX = 8
 
 _lib = None
@@ -60,6 +60,11 @@ _SIGNATURES = {
                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vcb_timestep_embedding": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "vcb_silu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "vcb_embedding_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "vcb_rmsnorm_weight": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
+    "vcb_layernorm_affine": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
+    "vcb_gated_gelu": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
+    "vcb_quick_gelu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "vcb_add3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                            C.c_int32, C.c_void_p]),
     "vcb_rope_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
@@ -103,6 +108,13 @@ class AttnArgs(C.Structure):
                 ("out", C.c_void_p), ("ldo", C.c_int64), ("out_col_offset", C.c_int32),
                 ("out_peers", C.POINTER(C.c_void_p)), ("world", C.c_int32), ("rows_per_rank", C.c_int32),
                 ("score_bound_log2", C.c_float), ("schedule", C.c_int32)]
+
+
+class AttnSmallArgs(C.Structure):
+    """struct vcb_attn_small_args (include/vcb200.h)."""
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("ld", C.c_int64), ("bias", C.c_void_p),
+                ("out", C.c_void_p), ("ldo", C.c_int64), ("B", C.c_int32), ("L", C.c_int32), ("heads", C.c_int32),
+                ("head_dim", C.c_int32), ("causal", C.c_int32), ("scale", C.c_float)]
 
 
 class ProfRecord(C.Structure):
@@ -193,6 +205,7 @@ _OPTIONAL: dict = {
     "vcb_attention_fwd_sp": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
     "vcb_attention_fwd_ex": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
+    "vcb_attention_small": (C.c_int, [C.POINTER(AttnSmallArgs), C.c_void_p]),
     "vcb_ln_modulate_grouped": (C.c_int, [C.POINTER(LnArgs), C.POINTER(LnArgs), C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                           C.c_int32, C.c_void_p]),
     "vcb_ln_modulate_stats": (C.c_int, [C.POINTER(LnArgs), C.POINTER(LnArgs), C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,

@@ -10,5 +10,6 @@ if [[ "${VCB_PTXAS_V:-0}" == "1" ]]; then FLAGS+=(-Xptxas -v); fi
 SRCS=("${HERE}/capi.cu")
 [[ -f "${HERE}/flux_engine.cu" ]] && SRCS+=("${HERE}/flux_engine.cu")
 [[ -f "${HERE}/vae.cu" ]] && SRCS+=("${HERE}/vae.cu")
+[[ -f "${HERE}/text_encoders.cu" ]] && SRCS+=("${HERE}/text_encoders.cu")
 "${NVCC}" "${FLAGS[@]}" -o "${OUT}" "${SRCS[@]}"
 echo "built ${OUT}"

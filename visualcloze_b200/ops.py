@@ -78,8 +78,10 @@ def gemm_args(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: 
     g.out_row_offset = out_row_offset
     g.epilogue = epilogue
     if gate is not None:
-        _req(gate, BF16, "gate"); _req(res, BF16, "res")
+        _req(gate, BF16, "gate")
         g.gate, g.gate_stride = gate.data_ptr(), gate.stride(0)
+    if res is not None:                                   # gate None + res: the ungated residual out = bf16(res + bf16(acc + bias))
+        _req(res, BF16, "res")
         g.res, g.ld_res = res.data_ptr(), res.stride(0)
     g.hidden = hidden
     g.q_scale, g.k_scale, g.rope = _p(q_scale), _p(k_scale), _p(rope)
@@ -208,6 +210,64 @@ def ln_modulate_fp8(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, o
     check(_lib.lib().vcb_ln_modulate_fp8(C.byref(a), None, row_scale.data_ptr(), None, x.stride(0), out8.stride(0), ms, H,
                                          batch_rows or rows_per_batch, _stream()), "vcb_ln_modulate_fp8")
     return out8
+
+
+# ---- text encoders (models/modules/conditioner.py:5-37; include/vcb200.h "text encoders") -----------------------------------
+def embedding(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor, pos_table: torch.Tensor | None = None, L: int = 0) -> torch.Tensor:
+    """out[t] = table[ids[t]] (+ pos_table[t % L]); table [vocab, dim] bf16, ids int64 [n], out [n, dim] bf16"""
+    _req(table, BF16, "table"); _req(out, BF16, "out"); _req(ids, torch.int64, "ids")
+    check(_lib.lib().vcb_embedding_bf16(table.data_ptr(), table.shape[0], table.shape[1], ids.data_ptr(), _p(pos_table), L, out.data_ptr(),
+                                        out.stride(0), ids.numel(), _stream()), "vcb_embedding_bf16")
+    return out
+
+
+def rmsnorm_weight(x: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, eps: float) -> torch.Tensor:
+    """T5LayerNorm: out = weight * bf16(x * rsqrt(mean(x^2) + eps)); x / out [rows, dim] bf16"""
+    _req(x, BF16, "x"); _req(weight, BF16, "weight"); _req(out, BF16, "out")
+    check(_lib.lib().vcb_rmsnorm_weight(x.data_ptr(), x.stride(0), weight.data_ptr(), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1],
+                                        float(eps), _stream()), "vcb_rmsnorm_weight")
+    return out
+
+
+def layernorm_affine(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, eps: float) -> torch.Tensor:
+    _req(x, BF16, "x"); _req(weight, BF16, "weight"); _req(bias, BF16, "bias"); _req(out, BF16, "out")
+    check(_lib.lib().vcb_layernorm_affine(x.data_ptr(), x.stride(0), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), out.stride(0),
+                                          x.shape[0], x.shape[1], float(eps), _stream()), "vcb_layernorm_affine")
+    return out
+
+
+def gated_gelu(ab: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out = gelu_new(ab[:, :dff]) * ab[:, dff:]; ab [rows, 2 * dff], out [rows, dff]"""
+    _req(ab, BF16, "ab"); _req(out, BF16, "out")
+    check(_lib.lib().vcb_gated_gelu(ab.data_ptr(), ab.stride(0), out.data_ptr(), out.stride(0), ab.shape[0], out.shape[1], _stream()),
+          "vcb_gated_gelu")
+    return out
+
+
+def quick_gelu(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _req(x, BF16, "x"); _req(out, BF16, "out")
+    check(_lib.lib().vcb_quick_gelu(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "vcb_quick_gelu")
+    return out
+
+
+def attention_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, B: int, L: int, heads: int, *,
+                    bias: torch.Tensor | None = None, scale: float = 1.0, causal: bool = False) -> torch.Tensor:
+    """head_dim-64 attention of the text encoders; q / k / v: 2-D views [B * L, heads * 64] (may be column windows of one fused
+    buffer, equal row strides); bias [heads, L, L] bf16 or None"""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _req(t, BF16, n)
+    assert q.stride(0) == k.stride(0) == v.stride(0)
+    a = _lib.AttnSmallArgs()
+    a.q, a.k, a.v, a.ld = q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0)
+    if bias is not None:
+        _req(bias, BF16, "bias")
+        assert tuple(bias.shape) == (heads, L, L) and bias.is_contiguous()
+    a.bias = _p(bias)
+    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    a.B, a.L, a.heads, a.head_dim, a.causal, a.scale = B, L, heads, 64, int(causal), float(scale)
+    a._keepalive = (q, k, v, out, bias)
+    check(_lib.lib().vcb_attention_small(C.byref(a), _stream()), "vcb_attention_small")
+    return out
 
 
 def timestep_embedding(t_scaled: torch.Tensor, freqs: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
