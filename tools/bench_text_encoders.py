@@ -47,6 +47,12 @@ with torch.no_grad():
     o = ours(ids)
     out["t5_xxl_512_tokens"] = {"native_ms": timed(lambda: ours(ids)), "hf_bf16_ms": timed(lambda: hf(input_ids=ids, attention_mask=None)),
                                 "rel_l2_vs_hf_bf16": rel(o, ref), "gflop": 2e-9 * 512 * 24 * (4 * 4096 * 4096 + 3 * 4096 * 10240) + 24 * 4e-9 * 512 * 512 * 4096}
+from visualcloze_b200 import _lib  # noqa: E402
+_lib.lib().vcb_profile_begin()
+ours(ids)
+cat, _ = _lib.profile_end()
+out["t5_xxl_512_tokens"]["native_kernel_ms"] = {k: round(v[0], 3) for k, v in cat.items() if v[1]}
+out["t5_xxl_512_tokens"]["native_launches"] = int(sum(v[1] for v in cat.values()))
 print(out, flush=True)
 del hf, ours
 torch.cuda.empty_cache()

@@ -118,15 +118,17 @@ __global__ void quick_gelu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
 
 // ------------------------------------------------------------------------------------------------
 // Small attention: head_dim 64, L <= 512 keys, additive bias (T5: relative position bias, no 1/sqrt(d)) or scale + causal mask
-// (CLIP).  One block = 16 query rows of one (sample, head); K and V of the head live in shared memory.
-//   phase 1  scores: thread t owns keys t, t+128, ... and all 16 rows: per dim pair one K load per key (conflict-free: rows are
-//            padded to 66 elements) and 16 broadcast q loads feed 16 x 4 x 2 FMAs
+// (CLIP).  One block (256 threads) = 32 query rows of one (sample, head); the head's K, then its V, live in ONE shared buffer.
+//   stage K  16-byte global loads, eight in flight per thread before the first shared store (the loop is latency-bound otherwise)
+//   phase 1  scores: thread t owns keys t%128 + {0, 128, 256, 384} and 16 of the rows: per dim pair one K load per key
+//            (conflict-free: rows are padded to 66 elements) and 16 broadcast q loads feed 16 x 4 x 2 FMAs
+//   stage V  over K (no longer needed), then
 //   phase 2  softmax per row in fp32 (one warp per 4 rows), probabilities rounded to bf16 (HF: softmax(scores.float()).type_as)
 //   phase 3  out: thread t owns row t / 8 and 8 head dims
 // HF rounding points: scores = bf16(q k^T) [* scale], + bias in bf16, fp32 softmax, bf16 probabilities, fp32 PV sum, bf16 out.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSaRows = 16;
-constexpr int kSaThreads = 128;
+constexpr int kSaRows = 32;
+constexpr int kSaThreads = 256;
 constexpr int kSaMaxL = 512;
 constexpr int kSaKStride = 66;     // bf16 elements per K row in shared memory (33 words: bank = key index)
 struct SmallAttnParams {
@@ -138,31 +140,36 @@ struct SmallAttnParams {
 };
 inline size_t small_attn_smem(int L) {
     const int Lp = (L + 3) & ~3;
-    return (size_t)Lp * kSaKStride * 2 + (size_t)Lp * 64 * 2 + (size_t)kSaRows * Lp * 4 + (size_t)kSaRows * Lp * 2 + (size_t)kSaRows * 64 * 4;
+    return (size_t)Lp * kSaKStride * 2 + (size_t)kSaRows * Lp * 4 + (size_t)kSaRows * Lp * 2 + (size_t)kSaRows * 64 * 4;
 }
 __global__ void __launch_bounds__(kSaThreads)
 small_attention_kernel(const SmallAttnParams p) {
     extern __shared__ uint8_t sa_smem[];
     const int L = p.L, Lp = (L + 3) & ~3;
-    __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(sa_smem);                       // [Lp][66]
-    __nv_bfloat16* sV = sK + (size_t)Lp * kSaKStride;                                    // [Lp][64]
-    float* sS = reinterpret_cast<float*>(sV + (size_t)Lp * 64);                          // [16][Lp]
-    __nv_bfloat16* sP = reinterpret_cast<__nv_bfloat16*>(sS + (size_t)kSaRows * Lp);     // [16][Lp]
-    float* sQ = reinterpret_cast<float*>(sP + (size_t)kSaRows * Lp);                     // [16][64]
+    __nv_bfloat16* sKV = reinterpret_cast<__nv_bfloat16*>(sa_smem);                      // K [Lp][66], later V [Lp][64]
+    float* sS = reinterpret_cast<float*>(sKV + (size_t)Lp * kSaKStride);                 // [32][Lp]
+    __nv_bfloat16* sP = reinterpret_cast<__nv_bfloat16*>(sS + (size_t)kSaRows * Lp);     // [32][Lp]
+    float* sQ = reinterpret_cast<float*>(sP + (size_t)kSaRows * Lp);                     // [32][64]
     const int row0 = blockIdx.x * kSaRows, h = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x;
     const long long base = (long long)b * L;
-    // ---- stage K, V (whole head) and the 16 query rows ----
-    for (int i = tid; i < Lp * 8; i += kSaThreads) {             // 8 x 16-byte pieces per row
-        const int j = i >> 3, c = i & 7;
-        uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
-        if (j < L) {
-            kv = *reinterpret_cast<const uint4*>(p.k + (base + j) * p.ld + h * 64 + c * 8);
-            vv = *reinterpret_cast<const uint4*>(p.v + (base + j) * p.ld + h * 64 + c * 8);
+    const int pieces = Lp * 8;                                   // 16-byte pieces of one [Lp][64] operand
+    // ---- stage K and the 32 query rows ----
+    for (int i0 = tid; i0 < pieces; i0 += 8 * kSaThreads) {
+        uint4 buf[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * kSaThreads, j = i >> 3, c = i & 7;
+            buf[u] = (i < pieces && j < L) ? *reinterpret_cast<const uint4*>(p.k + (base + j) * p.ld + h * 64 + c * 8) : make_uint4(0, 0, 0, 0);
         }
-        uint32_t* kd = reinterpret_cast<uint32_t*>(sK + (size_t)j * kSaKStride + c * 8);   // 4-byte aligned (66 * 2 = 132)
-        kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
-        *reinterpret_cast<uint4*>(sV + (size_t)j * 64 + c * 8) = vv;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * kSaThreads, j = i >> 3, c = i & 7;
+            if (i < pieces) {
+                uint32_t* kd = reinterpret_cast<uint32_t*>(sKV + (size_t)j * kSaKStride + c * 8);     // 4-byte aligned (66 * 2 = 132)
+                kd[0] = buf[u].x; kd[1] = buf[u].y; kd[2] = buf[u].z; kd[3] = buf[u].w;
+            }
+        }
     }
     for (int i = tid; i < kSaRows * 64; i += kSaThreads) {
         const int r = i >> 6, d = i & 63;
@@ -170,45 +177,59 @@ small_attention_kernel(const SmallAttnParams p) {
     }
     __syncthreads();
     // ---- phase 1: scores ----
-    for (int j0 = 0; j0 < Lp; j0 += 4 * kSaThreads) {
-        float acc[kSaRows][4];
+    {
+        const int kt = tid & 127, rg = (tid >> 7) * 16;          // my keys kt + 128 u, my rows rg .. rg + 15
+        float acc[16][4];
 #pragma unroll
-        for (int r = 0; r < kSaRows; ++r)
+        for (int r = 0; r < 16; ++r)
 #pragma unroll
             for (int u = 0; u < 4; ++u) acc[r][u] = 0.f;
-        int key[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) key[u] = j0 + u * kSaThreads + tid;
 #pragma unroll 4
         for (int d = 0; d < 64; d += 2) {
             float2 kf[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                kf[u] = key[u] < Lp ? unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sK + (size_t)key[u] * kSaKStride + d)) : make_float2(0.f, 0.f);
+            for (int u = 0; u < 4; ++u) {
+                const int j = kt + u * 128;
+                kf[u] = j < Lp ? unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sKV + (size_t)j * kSaKStride + d)) : make_float2(0.f, 0.f);
+            }
 #pragma unroll
-            for (int r = 0; r < kSaRows; ++r) {
-                const float2 qf = *reinterpret_cast<const float2*>(sQ + r * 64 + d);
+            for (int r = 0; r < 16; ++r) {
+                const float2 qf = *reinterpret_cast<const float2*>(sQ + (rg + r) * 64 + d);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) acc[r][u] = fmaf(qf.x, kf[u].x, fmaf(qf.y, kf[u].y, acc[r][u]));
             }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int j = key[u];
+            const int j = kt + u * 128;
             if (j >= Lp) continue;
 #pragma unroll
-            for (int r = 0; r < kSaRows; ++r) {
-                const int i = row0 + r;
+            for (int r = 0; r < 16; ++r) {
+                const int i = row0 + rg + r;
                 float s = bf16_round(acc[r][u]);                                  // the bf16 matmul output
                 if (p.scale != 1.0f) s = bf16_round(s * p.scale);
                 if (p.bias != nullptr && i < L && j < L)
                     s = bf16_round(s + __bfloat162float(p.bias[((long long)h * L + i) * L + j]));
                 if (j >= L || (p.causal && j > i)) s = -INFINITY;
-                sS[r * Lp + j] = s;
+                sS[(rg + r) * Lp + j] = s;
             }
         }
     }
-    __syncthreads();
+    __syncthreads();                                             // K fully consumed, scores complete
+    // ---- stage V over K ----
+    for (int i0 = tid; i0 < pieces; i0 += 8 * kSaThreads) {
+        uint4 buf[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * kSaThreads, j = i >> 3, c = i & 7;
+            buf[u] = (i < pieces && j < L) ? *reinterpret_cast<const uint4*>(p.v + (base + j) * p.ld + h * 64 + c * 8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * kSaThreads;
+            if (i < pieces) *reinterpret_cast<uint4*>(sKV + (size_t)i * 8) = buf[u];          // [Lp][64]: piece i at element 8 i
+        }
+    }
     // ---- phase 2: softmax (warp w: rows 4w .. 4w+3) ----
     {
         const int warp = tid >> 5, lane = tid & 31;
@@ -234,9 +255,10 @@ small_attention_kernel(const SmallAttnParams p) {
     {
         const int r = tid >> 3, d0 = (tid & 7) * 8;
         float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
         for (int j = 0; j < L; ++j) {
             const float pj = __bfloat162float(sP[r * Lp + j]);
-            const uint4 vv = *reinterpret_cast<const uint4*>(sV + (size_t)j * 64 + d0);
+            const uint4 vv = *reinterpret_cast<const uint4*>(sKV + (size_t)j * 64 + d0);
             const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
