@@ -324,6 +324,35 @@ def test_linear_precision_levels_and_the_header_constants_agree():
     assert hasattr(_lib.lib(), "vcb_quantize_rows_e4m3")
 
 
+def test_text_encoder_host_logic():
+    """the T5 relative-position bucket rule equals HF's (modeling_t5.T5Attention._relative_position_bucket), the
+    encoders refuse a CPU device (no fallback), and the reference-shaped HFEmbedder wrapper returns what conditioner.py:10 selects."""
+    from transformers.models.t5.modeling_t5 import T5Attention
+    from visualcloze_b200 import _lib, text_encoders as T
+    rp = torch.arange(-700, 700)[None, :] - torch.arange(0, 3)[:, None]
+    for nb, md in ((32, 128), (16, 64)):
+        assert torch.equal(T.t5_relative_position_bucket(rp, nb, md),
+                           T5Attention._relative_position_bucket(rp, bidirectional=True, num_buckets=nb, max_distance=md))
+    with pytest.raises(_lib.VcbError, match="no CPU fallback"):
+        T.T5Encoder({}, num_heads=4, num_layers=0, device="cpu")
+    with pytest.raises(ValueError):
+        T.T5Encoder({}, num_heads=4, num_layers=0, d_kv=128)
+
+    class Tok:                                   # tokenizer stand-in: records the reference's call (conditioner.py:23-31)
+        def __call__(self, text, **kw):
+            self.kw = kw
+            return {"input_ids": torch.zeros(len(text), kw["max_length"], dtype=torch.long)}
+    enc = T.CLIPTextEncoder.__new__(T.CLIPTextEncoder)
+    enc.__call__ = None
+    tok = Tok()
+    emb = T.HFEmbedder(tok, lambda ids: ("last", "pooled"), 77)
+    emb.is_clip = True
+    assert emb(["a", "b"]) == "pooled" and tok.kw["padding"] == "max_length" and tok.kw["truncation"] is True and tok.kw["max_length"] == 77
+    emb.is_clip = False
+    emb.encoder = lambda ids: "hidden"
+    assert emb.forward(["a"]) == "hidden"
+
+
 def test_diffusers_vae_keys_convert_to_the_reference_names():
     """visualcloze.py:100 loads diffusers' AutoencoderKL; our VAE modules carry the in-repo AutoEncoder names (autoencoder.py).
     The converter must map a diffusers-named state dict of the FLUX VAE geometry onto exactly our parameter set."""
