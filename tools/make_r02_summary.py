@@ -78,6 +78,13 @@ if os.path.exists(p):
         out.append(f"| {r['L']} | " + " | ".join(cells) + " |\n")
     out.append(f"\nmethod: {d['method']}\n")
 
+p = f"{P}/r02_text_encoders.json"
+if os.path.exists(p):
+    d = json.load(open(p))
+    section("text encoders, once per image (tools/bench_text_encoders.py; real geometry, random weights; HF bf16 is a reference point only)")
+    for k, v in d.items():
+        out.append(f"* `{k}`: " + ", ".join(f"{a} = {b:.4g}" if isinstance(b, float) else f"{a} = {b}" for a, b in v.items()) + "\n")
+
 # ---- parity --------------------------------------------------------------------------------------------------------
 for name, title in (("r02_fullsize_parity", "full-size parity (tests/test_fullsize_gpu.py)"), ("r02_fp8_parity", "fp8 vs bf16 projections (tests/test_fp8_gpu.py)")):
     p = f"{P}/{name}.json"
